@@ -1,0 +1,133 @@
+/*
+ * ckks_b200.h -- C ABI of libckks_b200.so, the sm_100a replacement for the reference's `ntt_cuda`
+ * extension (Desilo/liberate-fhe, src/liberate/ntt/ntt.cpp + ntt_cuda_kernel.cu).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to int64 data on the current CUDA device unless noted;
+ *   - a "[C,N] limb matrix" is C rows of N contiguous int64 coefficients, rows `stride` ELEMENTS apart
+ *     (so the reference's strided row views d[:-K], x[start:] are passed as pointer + stride);
+ *   - per-limb constant arrays (_2q, ql, qh, kl, kh, Rs, Ninv, ...) are contiguous int64[C] -- exactly the
+ *     tensors ntt_context hands to ntt_cuda (src/liberate/ntt/ntt_context.py:138-189);
+ *   - `stream` is a cudaStream_t (pass torch.cuda.current_stream().cuda_stream); launches are asynchronous;
+ *   - return value: 0 on success, otherwise the cudaError_t of the failed launch, or a negative CKKS_E_*
+ *     code for an argument the kernels do not support.  The reference checks nothing (ntt.cpp has no
+ *     TORCH_CHECK) -- success-path behaviour is identical, failures are reported instead of ignored.
+ *   - results are BIT-IDENTICAL to the reference kernels, including lazy [0,2q) representatives, for
+ *     |inputs| < 2^62 (the reference's own arithmetic overflows beyond that).
+ *
+ * Each entry point cites the reference interface it replaces (paths relative to src/liberate/ntt/).
+ */
+#ifndef CKKS_B200_H
+#define CKKS_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CKKS_E_BADARG (-1)     /* null pointer / non-positive size */
+#define CKKS_E_LOGN (-2)       /* logN outside [12, 17] */
+#define CKKS_E_ALIGN (-3)      /* pointer or stride not 16-byte aligned */
+
+int ckks_abi_version(void);
+
+/* ---- level 1: the 15 ntt_cuda operators (ntt.cpp:421-437), one device per call ---------------------- */
+
+/* mont_mult (ntt.cpp:120-139, kern.cu:66-146): c = a (*) b, lazy Montgomery product, out of place */
+int ckks_mont_mult(const int64_t* a, int64_t a_stride, const int64_t* b, int64_t b_stride, int64_t* c,
+                   int64_t c_stride, int C, int N, const int64_t* ql, const int64_t* qh, const int64_t* kl,
+                   const int64_t* kh, void* stream);
+
+/* mont_enter (ntt.cpp:141-156, kern.cu:154-226): a[i][:] = mont(a[i][:], Rs[i]) in place (any per-limb scalar) */
+int ckks_mont_enter(int64_t* a, int64_t a_stride, const int64_t* Rs, int C, int N, const int64_t* ql,
+                    const int64_t* qh, const int64_t* kl, const int64_t* kh, void* stream);
+
+/* ntt / enter_ntt (ntt.cpp:158-204, kern.cu:278-423): forward negacyclic NTT in place, natural -> bit-reversed.
+ * tw = COMPACT Montgomery twiddles psi^bitrev(i), [C][N], rows tw_stride apart (build once with
+ * ckks_compact_twiddles from the reference's painted psi[C][logN][N/2]).  Rs != NULL fuses mont_enter. */
+int ckks_ntt(int64_t* a, int64_t a_stride, int C, int logN, const int64_t* tw, int64_t tw_stride,
+             const int64_t* Rs, const int64_t* _2q, const int64_t* ql, const int64_t* qh, const int64_t* kl,
+             const int64_t* kh, void* stream);
+
+/* intt / intt_exit / intt_exit_reduce / intt_exit_reduce_signed (ntt.cpp:206-318, kern.cu:476-973):
+ * inverse NTT in place, bit-reversed -> natural, x N^-1 (Ninv = N^-1 R mod q), then exit_mode
+ * 0: nothing, 1: mont_redc, 2: + reduce to [0,q), 3: + make_signed. */
+int ckks_intt(int64_t* a, int64_t a_stride, int C, int logN, const int64_t* tw, int64_t tw_stride,
+              const int64_t* Ninv, const int64_t* _2q, const int64_t* ql, const int64_t* qh, const int64_t* kl,
+              const int64_t* kh, int exit_mode, void* stream);
+
+/* mont_redc (ntt.cpp:320-334, kern.cu:559-653) */
+int ckks_mont_redc(int64_t* a, int64_t a_stride, int C, int N, const int64_t* ql, const int64_t* qh,
+                   const int64_t* kl, const int64_t* kh, void* stream);
+/* reduce_2q / make_signed / make_unsigned (ntt.cpp:336-376, kern.cu:664-699, 980-995) */
+int ckks_reduce_2q(int64_t* a, int64_t a_stride, int C, int N, const int64_t* _2q, void* stream);
+int ckks_make_signed(int64_t* a, int64_t a_stride, int C, int N, const int64_t* _2q, void* stream);
+int ckks_make_unsigned(int64_t* a, int64_t a_stride, int C, int N, const int64_t* _2q, void* stream);
+/* mont_add / mont_sub (ntt.cpp:378-407, kern.cu:1016-1058): out of place, lazy mod 2q */
+int ckks_mont_add(const int64_t* a, int64_t a_stride, const int64_t* b, int64_t b_stride, int64_t* c,
+                  int64_t c_stride, int C, int N, const int64_t* _2q, void* stream);
+int ckks_mont_sub(const int64_t* a, int64_t a_stride, const int64_t* b, int64_t b_stride, int64_t* c,
+                  int64_t c_stride, int C, int N, const int64_t* _2q, void* stream);
+/* tile_unsigned (ntt.cpp:409-419, kern.cu:997-1014): dst[i][:] = a[:] + q_i */
+int ckks_tile_unsigned(const int64_t* a, int64_t* dst, int64_t dst_stride, int C, int N, const int64_t* _2q,
+                       void* stream);
+
+/* painted psi[C][logN][N/2] (ckks_context.py:336-341) -> compact [C][N]; forward != 0 for psi, 0 for psi^-1 */
+int ckks_compact_twiddles(const int64_t* painted, int64_t* compact, int C, int logN, int forward, void* stream);
+
+/* ---- level 2: fused hot-path operators (additions; engine.py line numbers = src/liberate/fhe/ckks_engine.py) */
+
+/* rescale (engine.py:1026-1038): out[i] = reduce_q( mont(in[i] - r0, scale[i]) + (r0 > round_at) ).
+ * `in` rows are the limbs that survive; r0 is the dropped limb (one row of N). */
+int ckks_rescale(const int64_t* in, int64_t in_stride, const int64_t* r0, int64_t* out, int64_t out_stride, int C,
+                 int N, const int64_t* scale, int64_t round_at, const int64_t* _2q, const int64_t* ql,
+                 const int64_t* qh, const int64_t* kl, const int64_t* kh, void* stream);
+
+/* tensor product (engine.py:1095-1101): d0 = x0*y0, d1 = x0*y1 (+) x1*y0, d2 = x1*y1 (lazy, NTT domain) */
+int ckks_tensor_product(const int64_t* x0, const int64_t* x1, const int64_t* y0, const int64_t* y1, int64_t in_stride,
+                        int64_t* d0, int64_t* d1, int64_t* d2, int64_t out_stride, int C, int N, const int64_t* _2q,
+                        const int64_t* ql, const int64_t* qh, const int64_t* kl, const int64_t* kh, void* stream);
+
+/* Garner mixed-radix digits of one partition (pre_extend, engine.py:654-705).
+ * a: [alpha,N] rows of the partition (plain, as the reference reads them); state: [alpha,N] out (may alias a).
+ * Y_scalar[alpha-1], L_scalar packed row-major upper triangle: entry (i, j) for step i (0..alpha-3) and target
+ * row j (i+2..alpha-1) at  Ltri[i*alpha + j]  (ntt_context.py:336-349).  Per-limb constants of the alpha rows. */
+int ckks_garner_digits(const int64_t* a, int64_t a_stride, int64_t* state, int64_t state_stride, int alpha, int N,
+                       const int64_t* Y_scalar, const int64_t* Ltri, const int64_t* ql, const int64_t* qh,
+                       const int64_t* kl, const int64_t* kh, void* stream);
+
+/* basis extension of one partition's digits to E target limbs (extend, engine.py:707-743):
+ * out[t] = mont(state[0], Rs[t]) (+) mont(state[1], Lenter[0][t]) (+) ...  (lazy mont_add chain, Montgomery form).
+ * Lenter: [(alpha-1)][E] row-major.  Target-limb constants have length E. */
+int ckks_extend(const int64_t* state, int64_t state_stride, int alpha, int64_t* out, int64_t out_stride, int E, int N,
+                const int64_t* Rs, const int64_t* Lenter, const int64_t* _2q, const int64_t* ql, const int64_t* qh,
+                const int64_t* kl, const int64_t* kh, void* stream);
+
+/* evaluation-key inner product (switcher_later_part + the Sigma over parts, engine.py:906-937, 832-840):
+ * acc0[t] (+)= mont(ext[t], ksk0[t]), acc1[t] (+)= mont(ext[t], ksk1[t]); first != 0 overwrites instead. */
+int ckks_ksk_accumulate(const int64_t* ext, int64_t ext_stride, const int64_t* ksk0, const int64_t* ksk1,
+                        int64_t ksk_stride, int64_t* acc0, int64_t* acc1, int64_t acc_stride, int E, int N, int first,
+                        const int64_t* _2q, const int64_t* ql, const int64_t* qh, const int64_t* kl,
+                        const int64_t* kh, void* stream);
+
+/* ModDown (engine.py:851-901): d is [E,N] = ordinary limbs (L rows) then K special rows, all plain in [0,q)
+ * (after intt_exit_reduce).  Runs the K sequential "subtract special limb, multiply by P_j^-1" steps with the
+ * reference's exact lazy semantics, then mont_redc + reduce on the ordinary rows.  PiR: [K][E] row-major
+ * (engine.py:183-216; entries beyond the live rows of a step are ignored).  d is not modified; the
+ * result goes to out; if add != NULL the result is (add + result) reduced to [0,q) (relinearize / switch_key tail,
+ * engine.py:1135-1140, 947-948) written to out.  eff: caller-provided workspace of K*N int64. */
+int ckks_moddown(int64_t* d, int64_t d_stride, int L, int K, int N, const int64_t* Rs, const int64_t* PiR,
+                 const int64_t* add, int64_t add_stride, int64_t* out, int64_t out_stride, int64_t* eff,
+                 const int64_t* _2q, const int64_t* ql, const int64_t* qh, const int64_t* kl, const int64_t* kh,
+                 void* stream);
+
+/* Galois automorphism of coefficient rows (encdec.rotate / conjugate, encdec.py:224-270) fused with
+ * make_unsigned + reduce_2q (engine.py:1196-1200) when canon != 0:
+ * out[i][(g*j) mod N] = +-in[i][j]  (sign = -1 when (g*j mod 2N) >= N), g odd. */
+int ckks_automorphism(const int64_t* in, int64_t in_stride, int64_t* out, int64_t out_stride, int C, int N,
+                      int64_t g, int canon, const int64_t* _2q, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

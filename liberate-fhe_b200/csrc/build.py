@@ -1,0 +1,33 @@
+"""Builds libckks_b200.so in-tree for sm_100a (nvcc cross-compiles without a GPU).
+
+    python liberate-fhe_b200/csrc/build.py [--force] [--verbose]
+"""
+import subprocess
+import sys
+from pathlib import Path
+
+HERE = Path(__file__).resolve().parent
+SOURCES = ["ckks_b200.cu"]
+HEADERS = ["mont.cuh", "ntt_kernels.cuh", "../../include/ckks_b200.h"]
+LIB = HERE / "libckks_b200.so"
+NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+
+def stale():
+    if not LIB.exists():
+        return True
+    t = LIB.stat().st_mtime
+    return any((HERE / f).stat().st_mtime > t for f in SOURCES + HEADERS)
+
+
+def build(force=False, verbose=False):
+    if not force and not stale():
+        return LIB
+    cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", str(LIB)] + [str(HERE / s) for s in SOURCES]
+    subprocess.check_call(cmd)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

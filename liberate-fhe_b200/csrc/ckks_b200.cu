@@ -1,0 +1,566 @@
+// ckks_b200.cu -- kernels + C ABI of libckks_b200.so (see include/ckks_b200.h for the contract and the
+// reference file:line each entry point replaces).  sm_100a only; no torch types anywhere.
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "../../include/ckks_b200.h"
+#include "mont.cuh"
+#include "ntt_kernels.cuh"
+
+using namespace ckks;
+
+#define CKKS_ABI_VERSION 1
+
+namespace {
+
+constexpr int EW_THREADS = 256;
+
+inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+inline int launch_status() { return (int)cudaGetLastError(); }
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+inline bool row_ok(const void* p, long long stride) { return aligned16(p) && (stride % 2 == 0); }
+
+// two coefficients per thread, 128-bit accesses; grid (N/2/EW_THREADS, C)
+__device__ __forceinline__ longlong2 ld2(const int64_t* p) { return *reinterpret_cast<const longlong2*>(p); }
+__device__ __forceinline__ void st2(int64_t* p, longlong2 v) { *reinterpret_cast<longlong2*>(p) = v; }
+
+struct MontPack {
+    const int64_t* _2q;
+    const int64_t* ql;
+    const int64_t* qh;
+    const int64_t* kl;
+    const int64_t* kh;
+};
+__device__ __forceinline__ LimbConst lc(const MontPack& m, int i) { return load_limb_const(m._2q, m.ql, m.qh, m.kl, m.kh, i); }
+
+// ---------------------------------------------------------------------------------------------
+// level-1 elementwise kernels
+// ---------------------------------------------------------------------------------------------
+__global__ void k_mont_mult(const int64_t* __restrict__ a, long long as, const int64_t* __restrict__ b, long long bs,
+                            int64_t* __restrict__ c, long long cs, int N, MontPack m) {
+    const int i = blockIdx.y;
+    const int j = 2 * (blockIdx.x * EW_THREADS + threadIdx.x);
+    if (j >= N) return;
+    const LimbConst k = lc(m, i);
+    const longlong2 x = ld2(a + i * as + j), y = ld2(b + i * bs + j);
+    st2(c + i * cs + j, make_longlong2(mont_mul_ss(x.x, y.x, k.q4, k.k), mont_mul_ss(x.y, y.y, k.q4, k.k)));
+}
+
+__global__ void k_mont_enter(int64_t* __restrict__ a, long long as, const int64_t* __restrict__ Rs, int N, MontPack m) {
+    const int i = blockIdx.y;
+    const int j = 2 * (blockIdx.x * EW_THREADS + threadIdx.x);
+    if (j >= N) return;
+    const LimbConst k = lc(m, i);
+    const int64_t r = Rs[i];
+    longlong2 x = ld2(a + i * as + j);
+    x.x = mont_mul_ss(x.x, r, k.q4, k.k);
+    x.y = mont_mul_ss(x.y, r, k.q4, k.k);
+    st2(a + i * as + j, x);
+}
+
+__global__ void k_mont_redc(int64_t* __restrict__ a, long long as, int N, MontPack m) {
+    const int i = blockIdx.y;
+    const int j = 2 * (blockIdx.x * EW_THREADS + threadIdx.x);
+    if (j >= N) return;
+    const LimbConst k = lc(m, i);
+    longlong2 x = ld2(a + i * as + j);
+    x.x = mont_redc(x.x, k.q4, k.k);
+    x.y = mont_redc(x.y, k.q4, k.k);
+    st2(a + i * as + j, x);
+}
+
+// mode 0 reduce_2q, 1 make_signed, 2 make_unsigned
+template <int MODE>
+__global__ void k_unary(int64_t* __restrict__ a, long long as, int N, const int64_t* __restrict__ _2q) {
+    const int i = blockIdx.y;
+    const int j = 2 * (blockIdx.x * EW_THREADS + threadIdx.x);
+    if (j >= N) return;
+    const int64_t q = _2q[i] >> 1;
+    longlong2 x = ld2(a + i * as + j);
+    if (MODE == 0) { x.x = reduce_q(x.x, q); x.y = reduce_q(x.y, q); }
+    if (MODE == 1) { x.x = make_signed(x.x, q); x.y = make_signed(x.y, q); }
+    if (MODE == 2) { x.x += q; x.y += q; }
+    st2(a + i * as + j, x);
+}
+
+template <bool SUB>
+__global__ void k_addsub(const int64_t* __restrict__ a, long long as, const int64_t* __restrict__ b, long long bs,
+                         int64_t* __restrict__ c, long long cs, int N, const int64_t* __restrict__ _2q) {
+    const int i = blockIdx.y;
+    const int j = 2 * (blockIdx.x * EW_THREADS + threadIdx.x);
+    if (j >= N) return;
+    const int64_t q2 = _2q[i];
+    const longlong2 x = ld2(a + i * as + j), y = ld2(b + i * bs + j);
+    longlong2 r;
+    r.x = SUB ? lazy_sub(x.x, y.x, q2) : lazy_add(x.x, y.x, q2);
+    r.y = SUB ? lazy_sub(x.y, y.y, q2) : lazy_add(x.y, y.y, q2);
+    st2(c + i * cs + j, r);
+}
+
+__global__ void k_tile_unsigned(const int64_t* __restrict__ a, int64_t* __restrict__ dst, long long ds, int N,
+                                const int64_t* __restrict__ _2q) {
+    const int i = blockIdx.y;
+    const int j = 2 * (blockIdx.x * EW_THREADS + threadIdx.x);
+    if (j >= N) return;
+    const int64_t q = _2q[i] >> 1;
+    longlong2 x = ld2(a + j);
+    x.x += q;
+    x.y += q;
+    st2(dst + i * ds + j, x);
+}
+
+// painted psi[C][logN][N/2] -> compact [C][N]  (cctx.py:89-142: block i of stage/level lvl uses one twiddle)
+__global__ void k_compact(const int64_t* __restrict__ painted, int64_t* __restrict__ compact, int logN, int forward) {
+    const int i = blockIdx.y;
+    const int idx = blockIdx.x * EW_THREADS + threadIdx.x;  // compact index in [0, N)
+    const int N = 1 << logN;
+    if (idx >= N) return;
+    int64_t v = 0;
+    if (idx > 0) {
+        const int lg = 31 - __clz(idx);           // idx = 2^lg + blk
+        const int blk = idx - (1 << lg);
+        // forward: stage lg, m = 2^lg blocks of t = N/(2m) butterflies; inverse: level with h = 2^lg, t = N/(2h)
+        const int t = N >> (lg + 1);
+        const int lvl = forward ? lg : (logN - 1 - lg);
+        v = painted[((long long)i * logN + lvl) * (N / 2) + (long long)blk * t];
+    }
+    compact[(long long)i * N + idx] = v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// level-2 fused kernels
+// ---------------------------------------------------------------------------------------------
+__global__ void k_rescale(const int64_t* __restrict__ in, long long is, const int64_t* __restrict__ r0,
+                          int64_t* __restrict__ out, long long os, int N, const int64_t* __restrict__ scale,
+                          int64_t round_at, MontPack m) {
+    const int i = blockIdx.y;
+    const int j = 2 * (blockIdx.x * EW_THREADS + threadIdx.x);
+    if (j >= N) return;
+    const LimbConst k = lc(m, i);
+    const int64_t sc = scale[i], q = (int64_t)(k.q2 >> 1);
+    const longlong2 x = ld2(in + i * is + j), r = ld2(r0 + j);
+    longlong2 o;
+    o.x = reduce_q(mont_mul_ss(x.x - r.x, sc, k.q4, k.k) + (r.x > round_at ? 1 : 0), q);
+    o.y = reduce_q(mont_mul_ss(x.y - r.y, sc, k.q4, k.k) + (r.y > round_at ? 1 : 0), q);
+    st2(out + i * os + j, o);
+}
+
+__global__ void k_tensor(const int64_t* __restrict__ x0, const int64_t* __restrict__ x1, const int64_t* __restrict__ y0,
+                         const int64_t* __restrict__ y1, long long is, int64_t* __restrict__ d0,
+                         int64_t* __restrict__ d1, int64_t* __restrict__ d2, long long os, int N, MontPack m) {
+    const int i = blockIdx.y;
+    const int j = 2 * (blockIdx.x * EW_THREADS + threadIdx.x);
+    if (j >= N) return;
+    const LimbConst k = lc(m, i);
+    const long long o = i * is + j;
+    const longlong2 a0 = ld2(x0 + o), a1 = ld2(x1 + o), b0 = ld2(y0 + o), b1 = ld2(y1 + o);
+    longlong2 r0, r1, r2;
+    r0.x = mont_mul_ss(a0.x, b0.x, k.q4, k.k);
+    r0.y = mont_mul_ss(a0.y, b0.y, k.q4, k.k);
+    r1.x = lazy_add(mont_mul_ss(a0.x, b1.x, k.q4, k.k), mont_mul_ss(a1.x, b0.x, k.q4, k.k), (int64_t)k.q2);
+    r1.y = lazy_add(mont_mul_ss(a0.y, b1.y, k.q4, k.k), mont_mul_ss(a1.y, b0.y, k.q4, k.k), (int64_t)k.q2);
+    r2.x = mont_mul_ss(a1.x, b1.x, k.q4, k.k);
+    r2.y = mont_mul_ss(a1.y, b1.y, k.q4, k.k);
+    const long long oo = i * os + j;
+    st2(d0 + oo, r0);
+    st2(d1 + oo, r1);
+    st2(d2 + oo, r2);
+}
+
+constexpr int MAX_ALPHA = 8;
+
+// one thread per coefficient; the alpha rows of the partition are walked sequentially (engine.py:672-702)
+__global__ void k_garner(const int64_t* __restrict__ a, long long as, int64_t* __restrict__ st, long long ss, int alpha,
+                         int N, const int64_t* __restrict__ Ysc, const int64_t* __restrict__ Ltri, MontPack m) {
+    const int j = blockIdx.x * EW_THREADS + threadIdx.x;
+    if (j >= N) return;
+    int64_t s[MAX_ALPHA], av[MAX_ALPHA];
+#pragma unroll
+    for (int r = 0; r < MAX_ALPHA; ++r)
+        if (r < alpha) av[r] = a[r * as + j];
+#pragma unroll
+    for (int r = 0; r < MAX_ALPHA; ++r) s[r] = av[0];
+#pragma unroll
+    for (int i = 0; i < MAX_ALPHA - 1; ++i) {
+        if (i < alpha - 1) {
+            const LimbConst k = lc(m, i + 1);
+            const int64_t Y = mont_mul_ss(av[i + 1] - s[i + 1], Ysc[i], k.q4, k.k);
+            s[i + 1] = Y;
+#pragma unroll
+            for (int r = i + 2; r < MAX_ALPHA; ++r) {
+                if (r < alpha) {
+                    const LimbConst kr = lc(m, r);
+                    s[r] += mont_mul_ss(Y, Ltri[i * alpha + r], kr.q4, kr.k);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < MAX_ALPHA; ++r)
+        if (r < alpha) st[r * ss + j] = s[r];
+}
+
+// grid (N/2/EW_THREADS, E): target limb t
+__global__ void k_extend(const int64_t* __restrict__ st, long long ss, int alpha, int64_t* __restrict__ out,
+                         long long os, int E, int N, const int64_t* __restrict__ Rs, const int64_t* __restrict__ Lenter,
+                         MontPack m) {
+    const int t = blockIdx.y;
+    const int j = 2 * (blockIdx.x * EW_THREADS + threadIdx.x);
+    if (j >= N) return;
+    const LimbConst k = lc(m, t);
+    const int64_t q2 = (int64_t)k.q2;
+    longlong2 v = ld2(st + j);
+    const int64_t rs = Rs[t];
+    longlong2 acc;
+    acc.x = mont_mul_ss(v.x, rs, k.q4, k.k);
+    acc.y = mont_mul_ss(v.y, rs, k.q4, k.k);
+    for (int i = 0; i < alpha - 1; ++i) {
+        v = ld2(st + (i + 1) * ss + j);
+        const int64_t le = Lenter[(long long)i * E + t];
+        acc.x = lazy_add(acc.x, mont_mul_ss(v.x, le, k.q4, k.k), q2);
+        acc.y = lazy_add(acc.y, mont_mul_ss(v.y, le, k.q4, k.k), q2);
+    }
+    st2(out + t * os + j, acc);
+}
+
+__global__ void k_ksk_acc(const int64_t* __restrict__ ext, long long es, const int64_t* __restrict__ k0,
+                          const int64_t* __restrict__ k1, long long ks, int64_t* __restrict__ a0,
+                          int64_t* __restrict__ a1, long long as, int N, int first, MontPack m) {
+    const int t = blockIdx.y;
+    const int j = 2 * (blockIdx.x * EW_THREADS + threadIdx.x);
+    if (j >= N) return;
+    const LimbConst k = lc(m, t);
+    const int64_t q2 = (int64_t)k.q2;
+    const longlong2 e = ld2(ext + t * es + j), u = ld2(k0 + t * ks + j), v = ld2(k1 + t * ks + j);
+    longlong2 p0, p1;
+    p0.x = mont_mul_ss(e.x, u.x, k.q4, k.k);
+    p0.y = mont_mul_ss(e.y, u.y, k.q4, k.k);
+    p1.x = mont_mul_ss(e.x, v.x, k.q4, k.k);
+    p1.y = mont_mul_ss(e.y, v.y, k.q4, k.k);
+    if (!first) {
+        const longlong2 c0 = ld2(a0 + t * as + j), c1 = ld2(a1 + t * as + j);
+        p0.x = lazy_add(c0.x, p0.x, q2);
+        p0.y = lazy_add(c0.y, p0.y, q2);
+        p1.x = lazy_add(c1.x, p1.x, q2);
+        p1.y = lazy_add(c1.y, p1.y, q2);
+    }
+    st2(a0 + t * as + j, p0);
+    st2(a1 + t * as + j, p1);
+}
+
+// ModDown, part 1: the chain on the K special rows (engine.py:863-890 restricted to rows >= L).
+// eff[i][j] = value of special row E-1-i at the moment step i reads it.  One thread per coefficient.
+__global__ void k_moddown_special(const int64_t* __restrict__ d, long long ds, int L, int K, int N,
+                                  const int64_t* __restrict__ PiR, int64_t* __restrict__ eff, MontPack m) {
+    const int j = blockIdx.x * EW_THREADS + threadIdx.x;
+    if (j >= N) return;
+    const int E = L + K;
+    int64_t s[MAX_ALPHA];
+#pragma unroll
+    for (int p = 0; p < MAX_ALPHA; ++p) {
+        if (p < K) {
+            const int u = E - 1 - p;  // row index
+            const LimbConst k = lc(m, u);
+            const int64_t q2 = (int64_t)k.q2, q = (int64_t)(k.q2 >> 1);
+            int64_t v = d[u * ds + j];
+#pragma unroll
+            for (int i = 0; i < MAX_ALPHA; ++i) {
+                if (i < p) {
+                    v = lazy_sub(v, s[i], q2);
+                    v = mont_mul_ss(v, PiR[(long long)i * E + u], k.q4, k.k);
+                    v = reduce_q(v, q);
+                }
+            }
+            s[p] = v;
+            eff[(long long)p * N + j] = v;
+        }
+    }
+}
+
+// ModDown, part 2: ordinary rows.  grid (N/2/EW_THREADS, L)
+__global__ void k_moddown_ordinary(const int64_t* __restrict__ d, long long ds, int L, int K, int N,
+                                   const int64_t* __restrict__ Rs, const int64_t* __restrict__ PiR,
+                                   const int64_t* __restrict__ eff, const int64_t* __restrict__ add, long long adds,
+                                   int64_t* __restrict__ out, long long os, MontPack m) {
+    const int t = blockIdx.y;
+    const int j = 2 * (blockIdx.x * EW_THREADS + threadIdx.x);
+    if (j >= N) return;
+    const int E = L + K;
+    const LimbConst k = lc(m, t);
+    const int64_t q2 = (int64_t)k.q2, q = (int64_t)(k.q2 >> 1);
+    const int64_t rs = Rs[t];
+    longlong2 v = ld2(d + t * ds + j);
+    v.x = mont_mul_ss(v.x, rs, k.q4, k.k);
+    v.y = mont_mul_ss(v.y, rs, k.q4, k.k);
+    for (int i = 0; i < K; ++i) {
+        const longlong2 p = ld2(eff + (long long)i * N + j);
+        const int64_t pir = PiR[(long long)i * E + t];
+        v.x = reduce_q(mont_mul_ss(lazy_sub(v.x, mont_mul_ss(p.x, rs, k.q4, k.k), q2), pir, k.q4, k.k), q);
+        v.y = reduce_q(mont_mul_ss(lazy_sub(v.y, mont_mul_ss(p.y, rs, k.q4, k.k), q2), pir, k.q4, k.k), q);
+    }
+    v.x = reduce_q(mont_redc(v.x, k.q4, k.k), q);
+    v.y = reduce_q(mont_redc(v.y, k.q4, k.k), q);
+    if (add) {
+        const longlong2 a = ld2(add + t * adds + j);
+        v.x = reduce_q(lazy_add(a.x, v.x, q2), q);
+        v.y = reduce_q(lazy_add(a.y, v.y, q2), q);
+    }
+    st2(out + t * os + j, v);
+}
+
+__global__ void k_automorphism(const int64_t* __restrict__ in, long long is, int64_t* __restrict__ out, long long os,
+                               int N, unsigned g, int canon, const int64_t* __restrict__ _2q) {
+    const int i = blockIdx.y;
+    const unsigned j = blockIdx.x * EW_THREADS + threadIdx.x;
+    if (j >= (unsigned)N) return;
+    const unsigned pj = (g * j) & (2u * N - 1);  // g*j mod 2N (N power of two; 32-bit wrap is harmless)
+    const unsigned dst = pj & (N - 1);
+    int64_t v = in[i * is + j];
+    if (pj >= (unsigned)N) v = -v;
+    if (canon) {
+        const int64_t q = _2q[i] >> 1;
+        v = reduce_q(v + q, q);
+    }
+    out[i * os + dst] = v;
+}
+
+inline dim3 ew_grid(int N, int C) { return dim3((N / 2 + EW_THREADS - 1) / EW_THREADS, C); }
+inline dim3 col_grid(int N) { return dim3((N + EW_THREADS - 1) / EW_THREADS); }
+
+template <int B>
+static int launch_fwd_block(const NttArgs& A, dim3 grid, cudaStream_t st) {
+    ntt_fwd_blockpass<B, true><<<grid, NTT_THREADS, SMEM_BYTES, st>>>(A);
+    return launch_status();
+}
+template <int B>
+static int launch_inv_block(const NttArgs& A, dim3 grid, cudaStream_t st) {
+    ntt_inv_blockpass<B, true><<<grid, NTT_THREADS, SMEM_BYTES, st>>>(A);
+    return launch_status();
+}
+
+}  // namespace
+
+#define CHECK_PTRS(...)                                  \
+    do {                                                 \
+        const void* _p[] = {__VA_ARGS__};                \
+        for (const void* x : _p)                         \
+            if (!x) return CKKS_E_BADARG;                \
+    } while (0)
+
+extern "C" {
+
+int ckks_abi_version(void) { return CKKS_ABI_VERSION; }
+
+int ckks_mont_mult(const int64_t* a, int64_t as, const int64_t* b, int64_t bs, int64_t* c, int64_t cs, int C, int N,
+                   const int64_t* ql, const int64_t* qh, const int64_t* kl, const int64_t* kh, void* stream) {
+    CHECK_PTRS(a, b, c, ql, qh, kl, kh);
+    if (C <= 0 || N <= 0 || (N & 1)) return CKKS_E_BADARG;
+    if (!row_ok(a, as) || !row_ok(b, bs) || !row_ok(c, cs)) return CKKS_E_ALIGN;
+    k_mont_mult<<<ew_grid(N, C), EW_THREADS, 0, S(stream)>>>(a, as, b, bs, c, cs, N, MontPack{nullptr, ql, qh, kl, kh});
+    return launch_status();
+}
+
+int ckks_mont_enter(int64_t* a, int64_t as, const int64_t* Rs, int C, int N, const int64_t* ql, const int64_t* qh,
+                    const int64_t* kl, const int64_t* kh, void* stream) {
+    CHECK_PTRS(a, Rs, ql, qh, kl, kh);
+    if (C <= 0 || N <= 0 || (N & 1)) return CKKS_E_BADARG;
+    if (!row_ok(a, as)) return CKKS_E_ALIGN;
+    k_mont_enter<<<ew_grid(N, C), EW_THREADS, 0, S(stream)>>>(a, as, Rs, N, MontPack{nullptr, ql, qh, kl, kh});
+    return launch_status();
+}
+
+int ckks_mont_redc(int64_t* a, int64_t as, int C, int N, const int64_t* ql, const int64_t* qh, const int64_t* kl,
+                   const int64_t* kh, void* stream) {
+    CHECK_PTRS(a, ql, qh, kl, kh);
+    if (C <= 0 || N <= 0 || (N & 1)) return CKKS_E_BADARG;
+    if (!row_ok(a, as)) return CKKS_E_ALIGN;
+    k_mont_redc<<<ew_grid(N, C), EW_THREADS, 0, S(stream)>>>(a, as, N, MontPack{nullptr, ql, qh, kl, kh});
+    return launch_status();
+}
+
+#define UNARY_IMPL(NAME, MODE)                                                                          \
+    int NAME(int64_t* a, int64_t as, int C, int N, const int64_t* _2q, void* stream) {                  \
+        CHECK_PTRS(a, _2q);                                                                             \
+        if (C <= 0 || N <= 0 || (N & 1)) return CKKS_E_BADARG;                                          \
+        if (!row_ok(a, as)) return CKKS_E_ALIGN;                                                        \
+        k_unary<MODE><<<ew_grid(N, C), EW_THREADS, 0, S(stream)>>>(a, as, N, _2q);                      \
+        return launch_status();                                                                         \
+    }
+UNARY_IMPL(ckks_reduce_2q, 0)
+UNARY_IMPL(ckks_make_signed, 1)
+UNARY_IMPL(ckks_make_unsigned, 2)
+
+int ckks_mont_add(const int64_t* a, int64_t as, const int64_t* b, int64_t bs, int64_t* c, int64_t cs, int C, int N,
+                  const int64_t* _2q, void* stream) {
+    CHECK_PTRS(a, b, c, _2q);
+    if (C <= 0 || N <= 0 || (N & 1)) return CKKS_E_BADARG;
+    if (!row_ok(a, as) || !row_ok(b, bs) || !row_ok(c, cs)) return CKKS_E_ALIGN;
+    k_addsub<false><<<ew_grid(N, C), EW_THREADS, 0, S(stream)>>>(a, as, b, bs, c, cs, N, _2q);
+    return launch_status();
+}
+int ckks_mont_sub(const int64_t* a, int64_t as, const int64_t* b, int64_t bs, int64_t* c, int64_t cs, int C, int N,
+                  const int64_t* _2q, void* stream) {
+    CHECK_PTRS(a, b, c, _2q);
+    if (C <= 0 || N <= 0 || (N & 1)) return CKKS_E_BADARG;
+    if (!row_ok(a, as) || !row_ok(b, bs) || !row_ok(c, cs)) return CKKS_E_ALIGN;
+    k_addsub<true><<<ew_grid(N, C), EW_THREADS, 0, S(stream)>>>(a, as, b, bs, c, cs, N, _2q);
+    return launch_status();
+}
+
+int ckks_tile_unsigned(const int64_t* a, int64_t* dst, int64_t ds, int C, int N, const int64_t* _2q, void* stream) {
+    CHECK_PTRS(a, dst, _2q);
+    if (C <= 0 || N <= 0 || (N & 1)) return CKKS_E_BADARG;
+    if (!aligned16(a) || !row_ok(dst, ds)) return CKKS_E_ALIGN;
+    k_tile_unsigned<<<ew_grid(N, C), EW_THREADS, 0, S(stream)>>>(a, dst, ds, N, _2q);
+    return launch_status();
+}
+
+int ckks_compact_twiddles(const int64_t* painted, int64_t* compact, int C, int logN, int forward, void* stream) {
+    CHECK_PTRS(painted, compact);
+    if (C <= 0 || logN < 1 || logN > 20) return CKKS_E_BADARG;
+    const int N = 1 << logN;
+    k_compact<<<dim3((N + EW_THREADS - 1) / EW_THREADS, C), EW_THREADS, 0, S(stream)>>>(painted, compact, logN, forward);
+    return launch_status();
+}
+
+// ---- NTT -------------------------------------------------------------------------------------------
+int ckks_ntt(int64_t* a, int64_t as, int C, int logN, const int64_t* tw, int64_t tws, const int64_t* Rs,
+             const int64_t* _2q, const int64_t* ql, const int64_t* qh, const int64_t* kl, const int64_t* kh,
+             void* stream) {
+    CHECK_PTRS(a, tw, _2q, ql, qh, kl, kh);
+    if (C <= 0) return CKKS_E_BADARG;
+    if (logN < 12 || logN > 17) return CKKS_E_LOGN;
+    if (!row_ok(a, as) || !row_ok(tw, tws)) return CKKS_E_ALIGN;
+    const int N = 1 << logN;
+    NttArgs A{a, as, tw, tws, _2q, ql, qh, kl, kh, Rs, logN, 0};
+    cudaStream_t st = S(stream);
+    const dim3 grid(N / TILE, C);
+    if (Rs)
+        ntt_fwd_colpass<true, true><<<grid, NTT_THREADS, SMEM_BYTES, st>>>(A);
+    else
+        ntt_fwd_colpass<true, false><<<grid, NTT_THREADS, SMEM_BYTES, st>>>(A);
+    int rc = launch_status();
+    if (rc) return rc;
+    switch (logN - 8) {
+        case 4: return launch_fwd_block<4>(A, grid, st);
+        case 5: return launch_fwd_block<5>(A, grid, st);
+        case 6: return launch_fwd_block<6>(A, grid, st);
+        case 7: return launch_fwd_block<7>(A, grid, st);
+        case 8: return launch_fwd_block<8>(A, grid, st);
+        case 9: return launch_fwd_block<9>(A, grid, st);
+    }
+    return CKKS_E_LOGN;
+}
+
+int ckks_intt(int64_t* a, int64_t as, int C, int logN, const int64_t* tw, int64_t tws, const int64_t* Ninv,
+              const int64_t* _2q, const int64_t* ql, const int64_t* qh, const int64_t* kl, const int64_t* kh,
+              int exit_mode, void* stream) {
+    CHECK_PTRS(a, tw, Ninv, _2q, ql, qh, kl, kh);
+    if (C <= 0 || exit_mode < 0 || exit_mode > 3) return CKKS_E_BADARG;
+    if (logN < 12 || logN > 17) return CKKS_E_LOGN;
+    if (!row_ok(a, as) || !row_ok(tw, tws)) return CKKS_E_ALIGN;
+    const int N = 1 << logN;
+    NttArgs A{a, as, tw, tws, _2q, ql, qh, kl, kh, Ninv, logN, exit_mode};
+    cudaStream_t st = S(stream);
+    const dim3 grid(N / TILE, C);
+    int rc = CKKS_E_LOGN;
+    switch (logN - 8) {
+        case 4: rc = launch_inv_block<4>(A, grid, st); break;
+        case 5: rc = launch_inv_block<5>(A, grid, st); break;
+        case 6: rc = launch_inv_block<6>(A, grid, st); break;
+        case 7: rc = launch_inv_block<7>(A, grid, st); break;
+        case 8: rc = launch_inv_block<8>(A, grid, st); break;
+        case 9: rc = launch_inv_block<9>(A, grid, st); break;
+    }
+    if (rc) return rc;
+    ntt_inv_colpass<true><<<grid, NTT_THREADS, SMEM_BYTES, st>>>(A);
+    return launch_status();
+}
+
+// ---- level 2 -----------------------------------------------------------------------------------------
+int ckks_rescale(const int64_t* in, int64_t is, const int64_t* r0, int64_t* out, int64_t os, int C, int N,
+                 const int64_t* scale, int64_t round_at, const int64_t* _2q, const int64_t* ql, const int64_t* qh,
+                 const int64_t* kl, const int64_t* kh, void* stream) {
+    CHECK_PTRS(in, r0, out, scale, _2q, ql, qh, kl, kh);
+    if (C <= 0 || N <= 0 || (N & 1)) return CKKS_E_BADARG;
+    if (!row_ok(in, is) || !row_ok(out, os) || !aligned16(r0)) return CKKS_E_ALIGN;
+    k_rescale<<<ew_grid(N, C), EW_THREADS, 0, S(stream)>>>(in, is, r0, out, os, N, scale, round_at,
+                                                           MontPack{_2q, ql, qh, kl, kh});
+    return launch_status();
+}
+
+int ckks_tensor_product(const int64_t* x0, const int64_t* x1, const int64_t* y0, const int64_t* y1, int64_t is,
+                        int64_t* d0, int64_t* d1, int64_t* d2, int64_t os, int C, int N, const int64_t* _2q,
+                        const int64_t* ql, const int64_t* qh, const int64_t* kl, const int64_t* kh, void* stream) {
+    CHECK_PTRS(x0, x1, y0, y1, d0, d1, d2, _2q, ql, qh, kl, kh);
+    if (C <= 0 || N <= 0 || (N & 1)) return CKKS_E_BADARG;
+    if (!row_ok(x0, is) || !row_ok(x1, is) || !row_ok(y0, is) || !row_ok(y1, is) || !row_ok(d0, os) ||
+        !row_ok(d1, os) || !row_ok(d2, os))
+        return CKKS_E_ALIGN;
+    k_tensor<<<ew_grid(N, C), EW_THREADS, 0, S(stream)>>>(x0, x1, y0, y1, is, d0, d1, d2, os, N,
+                                                          MontPack{_2q, ql, qh, kl, kh});
+    return launch_status();
+}
+
+int ckks_garner_digits(const int64_t* a, int64_t as, int64_t* state, int64_t ss, int alpha, int N,
+                       const int64_t* Y_scalar, const int64_t* Ltri, const int64_t* ql, const int64_t* qh,
+                       const int64_t* kl, const int64_t* kh, void* stream) {
+    CHECK_PTRS(a, state, ql, qh, kl, kh);
+    if (alpha <= 0 || alpha > MAX_ALPHA || N <= 0) return CKKS_E_BADARG;
+    if (alpha > 1 && !Y_scalar) return CKKS_E_BADARG;
+    if (alpha > 2 && !Ltri) return CKKS_E_BADARG;
+    k_garner<<<col_grid(N), EW_THREADS, 0, S(stream)>>>(a, as, state, ss, alpha, N, Y_scalar, Ltri,
+                                                        MontPack{nullptr, ql, qh, kl, kh});
+    return launch_status();
+}
+
+int ckks_extend(const int64_t* state, int64_t ss, int alpha, int64_t* out, int64_t os, int E, int N, const int64_t* Rs,
+                const int64_t* Lenter, const int64_t* _2q, const int64_t* ql, const int64_t* qh, const int64_t* kl,
+                const int64_t* kh, void* stream) {
+    CHECK_PTRS(state, out, Rs, _2q, ql, qh, kl, kh);
+    if (alpha <= 0 || E <= 0 || N <= 0 || (N & 1)) return CKKS_E_BADARG;
+    if (alpha > 1 && !Lenter) return CKKS_E_BADARG;
+    if (!row_ok(state, ss) || !row_ok(out, os)) return CKKS_E_ALIGN;
+    k_extend<<<ew_grid(N, E), EW_THREADS, 0, S(stream)>>>(state, ss, alpha, out, os, E, N, Rs, Lenter,
+                                                          MontPack{_2q, ql, qh, kl, kh});
+    return launch_status();
+}
+
+int ckks_ksk_accumulate(const int64_t* ext, int64_t es, const int64_t* ksk0, const int64_t* ksk1, int64_t ks,
+                        int64_t* acc0, int64_t* acc1, int64_t as, int E, int N, int first, const int64_t* _2q,
+                        const int64_t* ql, const int64_t* qh, const int64_t* kl, const int64_t* kh, void* stream) {
+    CHECK_PTRS(ext, ksk0, ksk1, acc0, acc1, _2q, ql, qh, kl, kh);
+    if (E <= 0 || N <= 0 || (N & 1)) return CKKS_E_BADARG;
+    if (!row_ok(ext, es) || !row_ok(ksk0, ks) || !row_ok(ksk1, ks) || !row_ok(acc0, as) || !row_ok(acc1, as))
+        return CKKS_E_ALIGN;
+    k_ksk_acc<<<ew_grid(N, E), EW_THREADS, 0, S(stream)>>>(ext, es, ksk0, ksk1, ks, acc0, acc1, as, N, first,
+                                                           MontPack{_2q, ql, qh, kl, kh});
+    return launch_status();
+}
+
+int ckks_moddown(int64_t* d, int64_t ds, int L, int K, int N, const int64_t* Rs, const int64_t* PiR,
+                 const int64_t* add, int64_t adds, int64_t* out, int64_t os, int64_t* eff, const int64_t* _2q,
+                 const int64_t* ql, const int64_t* qh, const int64_t* kl, const int64_t* kh, void* stream) {
+    CHECK_PTRS(d, Rs, PiR, out, eff, _2q, ql, qh, kl, kh);
+    if (L <= 0 || K <= 0 || K > MAX_ALPHA || N <= 0 || (N & 1)) return CKKS_E_BADARG;
+    if (!row_ok(d, ds) || !row_ok(out, os) || (add && !row_ok(add, adds))) return CKKS_E_ALIGN;
+    if (!aligned16(eff)) return CKKS_E_ALIGN;
+    const MontPack m{_2q, ql, qh, kl, kh};
+    k_moddown_special<<<col_grid(N), EW_THREADS, 0, S(stream)>>>(d, ds, L, K, N, PiR, eff, m);
+    int rc = launch_status();
+    if (rc) return rc;
+    k_moddown_ordinary<<<ew_grid(N, L), EW_THREADS, 0, S(stream)>>>(d, ds, L, K, N, Rs, PiR, eff, add, adds, out, os, m);
+    return launch_status();
+}
+
+int ckks_automorphism(const int64_t* in, int64_t is, int64_t* out, int64_t os, int C, int N, int64_t g, int canon,
+                      const int64_t* _2q, void* stream) {
+    CHECK_PTRS(in, out);
+    if (C <= 0 || N <= 0 || (N & (N - 1)) || !(g & 1)) return CKKS_E_BADARG;
+    if (canon && !_2q) return CKKS_E_BADARG;
+    k_automorphism<<<dim3((N + EW_THREADS - 1) / EW_THREADS, C), EW_THREADS, 0, S(stream)>>>(
+        in, is, out, os, N, (unsigned)(g & (2 * (int64_t)N - 1)), canon, _2q);
+    return launch_status();
+}
+
+}  // extern "C"

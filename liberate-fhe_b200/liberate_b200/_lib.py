@@ -1,0 +1,80 @@
+"""ctypes loader for libckks_b200.so (the C ABI declared in include/ckks_b200.h).
+
+There is NO CPU fallback: if the CUDA library cannot be loaded the import fails loudly, and every
+wrapper refuses tensors that are not on a CUDA device.
+"""
+import ctypes
+import shutil
+import sys
+from pathlib import Path
+
+_PKG = Path(__file__).resolve().parent
+_CSRC = _PKG.parent / "csrc"
+_LIBPATH = _CSRC / "libckks_b200.so"
+
+_i64p = ctypes.c_void_p
+_i64 = ctypes.c_int64
+_int = ctypes.c_int
+_vp = ctypes.c_void_p
+
+# name -> argtypes, mirroring include/ckks_b200.h exactly (checked by tests/test_abi.py)
+SIGNATURES = {
+    "ckks_abi_version": [],
+    "ckks_mont_mult": [_i64p, _i64, _i64p, _i64, _i64p, _i64, _int, _int, _i64p, _i64p, _i64p, _i64p, _vp],
+    "ckks_mont_enter": [_i64p, _i64, _i64p, _int, _int, _i64p, _i64p, _i64p, _i64p, _vp],
+    "ckks_ntt": [_i64p, _i64, _int, _int, _i64p, _i64, _i64p, _i64p, _i64p, _i64p, _i64p, _i64p, _vp],
+    "ckks_intt": [_i64p, _i64, _int, _int, _i64p, _i64, _i64p, _i64p, _i64p, _i64p, _i64p, _i64p, _int, _vp],
+    "ckks_mont_redc": [_i64p, _i64, _int, _int, _i64p, _i64p, _i64p, _i64p, _vp],
+    "ckks_reduce_2q": [_i64p, _i64, _int, _int, _i64p, _vp],
+    "ckks_make_signed": [_i64p, _i64, _int, _int, _i64p, _vp],
+    "ckks_make_unsigned": [_i64p, _i64, _int, _int, _i64p, _vp],
+    "ckks_mont_add": [_i64p, _i64, _i64p, _i64, _i64p, _i64, _int, _int, _i64p, _vp],
+    "ckks_mont_sub": [_i64p, _i64, _i64p, _i64, _i64p, _i64, _int, _int, _i64p, _vp],
+    "ckks_tile_unsigned": [_i64p, _i64p, _i64, _int, _int, _i64p, _vp],
+    "ckks_compact_twiddles": [_i64p, _i64p, _int, _int, _int, _vp],
+    "ckks_rescale": [_i64p, _i64, _i64p, _i64p, _i64, _int, _int, _i64p, _i64, _i64p, _i64p, _i64p, _i64p, _i64p, _vp],
+    "ckks_tensor_product": [_i64p, _i64p, _i64p, _i64p, _i64, _i64p, _i64p, _i64p, _i64, _int, _int,
+                            _i64p, _i64p, _i64p, _i64p, _i64p, _vp],
+    "ckks_garner_digits": [_i64p, _i64, _i64p, _i64, _int, _int, _i64p, _i64p, _i64p, _i64p, _i64p, _i64p, _vp],
+    "ckks_extend": [_i64p, _i64, _int, _i64p, _i64, _int, _int, _i64p, _i64p, _i64p, _i64p, _i64p, _i64p, _i64p, _vp],
+    "ckks_ksk_accumulate": [_i64p, _i64, _i64p, _i64p, _i64, _i64p, _i64p, _i64, _int, _int, _int,
+                            _i64p, _i64p, _i64p, _i64p, _i64p, _vp],
+    "ckks_moddown": [_i64p, _i64, _int, _int, _int, _i64p, _i64p, _i64p, _i64, _i64p, _i64, _i64p,
+                     _i64p, _i64p, _i64p, _i64p, _i64p, _vp],
+    "ckks_automorphism": [_i64p, _i64, _i64p, _i64, _int, _int, _i64, _int, _i64p, _vp],
+}
+
+ERRORS = {-1: "CKKS_E_BADARG (null pointer / bad size)", -2: "CKKS_E_LOGN (logN outside [12,17])",
+          -3: "CKKS_E_ALIGN (pointer/stride not 16-byte aligned)"}
+
+
+class CkksLibError(RuntimeError):
+    pass
+
+
+def _load():
+    if not _LIBPATH.exists():
+        if shutil.which("nvcc") is None:
+            raise ImportError(f"{_LIBPATH} is missing and nvcc is not available to build it; "
+                              "liberate_b200 has no CPU fallback")
+        sys.path.insert(0, str(_CSRC))
+        try:
+            import build as _b
+            _b.build()
+        finally:
+            sys.path.pop(0)
+    lib = ctypes.CDLL(str(_LIBPATH))
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError here = header/library mismatch: fail loudly
+        fn.argtypes = argtypes
+        fn.restype = ctypes.c_int
+    return lib
+
+
+lib = _load()
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = ERRORS.get(rc, f"cudaError {rc}")
+        raise CkksLibError(f"{what} failed: {msg}")

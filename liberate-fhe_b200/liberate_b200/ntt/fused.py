@@ -1,0 +1,104 @@
+"""
+fused -- single-device wrappers of the level-2 entry points of libckks_b200.so
+(include/ckks_b200.h): the reference's multi-launch Python sequences for rescale, tensor product,
+Garner ModUp, evaluation-key inner product, ModDown and the Galois automorphism, each as one (or
+two) kernels with the reference's exact per-element integer semantics.
+
+All tensors: int64, CUDA, rows contiguous.  ``mp`` is a "mont pack" (_2q, ql, qh, kl, kh) of 1-D
+per-limb tensors for the rows being processed.
+"""
+import torch
+
+from .._lib import lib, check
+from .ntt_cuda import _rows, _ptr, _stream, _Launch, _vec
+
+
+def rescale(x, r0, scale, round_at, mp):
+    """engine.py:1026-1038.  x: [C,N] surviving limbs, r0: [N] dropped limb -> new [C,N]"""
+    xs = _rows(x, "rescale")
+    out = torch.empty((x.size(0), x.size(1)), dtype=torch.int64, device=x.device)
+    r0 = r0 if r0.is_contiguous() else r0.contiguous()
+    with _Launch(x):
+        check(lib.ckks_rescale(_ptr(x), xs, _ptr(r0), _ptr(out), out.size(1), x.size(0), x.size(1), _ptr(_vec(scale)),
+                               int(round_at), *[_ptr(_vec(t)) for t in mp], _stream(x)), "rescale")
+    return out
+
+
+def tensor_product(x0, x1, y0, y1, mp):
+    """engine.py:1095-1101 -> (d0, d1, d2)"""
+    s = _rows(x0, "tensor_product")
+    for t in (x1, y0, y1):
+        if _rows(t, "tensor_product") != s:
+            raise ValueError("tensor_product: operands must share one row stride")
+    C, N = x0.shape
+    d = torch.empty((3, C, N), dtype=torch.int64, device=x0.device)
+    with _Launch(x0):
+        check(lib.ckks_tensor_product(_ptr(x0), _ptr(x1), _ptr(y0), _ptr(y1), s, _ptr(d[0]), _ptr(d[1]), _ptr(d[2]),
+                                      N, C, N, *[_ptr(_vec(t)) for t in mp], _stream(x0)), "tensor_product")
+    return d[0], d[1], d[2]
+
+
+def garner_digits(a_part, Y_scalar, Ltri, mp4, out=None):
+    """pre_extend, engine.py:654-705.  a_part: [alpha,N] -> state [alpha,N] (plain integers)"""
+    s = _rows(a_part, "garner_digits")
+    alpha, N = a_part.shape
+    if out is None:
+        out = torch.empty((alpha, N), dtype=torch.int64, device=a_part.device)
+    with _Launch(a_part):
+        check(lib.ckks_garner_digits(_ptr(a_part), s, _ptr(out), _rows(out, "garner_digits"), alpha, N,
+                                     _ptr(Y_scalar) if Y_scalar is not None else None,
+                                     _ptr(Ltri) if Ltri is not None else None,
+                                     *[_ptr(_vec(t)) for t in mp4], _stream(a_part)), "garner_digits")
+    return out
+
+
+def extend(state, Rs, Lenter, mp, out=None):
+    """extend, engine.py:707-743.  state [alpha,N] -> [E,N] Montgomery form on the E target limbs"""
+    s = _rows(state, "extend")
+    alpha, N = state.shape
+    E = Rs.numel()
+    if out is None:
+        out = torch.empty((E, N), dtype=torch.int64, device=state.device)
+    with _Launch(state):
+        check(lib.ckks_extend(_ptr(state), s, alpha, _ptr(out), _rows(out, "extend"), E, N, _ptr(_vec(Rs)),
+                              _ptr(Lenter) if Lenter is not None else None,
+                              *[_ptr(_vec(t)) for t in mp], _stream(state)), "extend")
+    return out
+
+
+def ksk_accumulate(ext, ksk0, ksk1, acc0, acc1, first, mp):
+    """engine.py:906-937 + 832-840: acc_i (+)= ext (*) ksk_i"""
+    E, N = ext.shape
+    ks = _rows(ksk0, "ksk_accumulate")
+    if _rows(ksk1, "ksk_accumulate") != ks:
+        raise ValueError("ksk_accumulate: key halves must share one row stride")
+    with _Launch(ext):
+        check(lib.ckks_ksk_accumulate(_ptr(ext), _rows(ext, "ksk"), _ptr(ksk0), _ptr(ksk1), ks, _ptr(acc0), _ptr(acc1),
+                                      _rows(acc0, "ksk"), E, N, 1 if first else 0,
+                                      *[_ptr(_vec(t)) for t in mp], _stream(ext)), "ksk_accumulate")
+
+
+def moddown(d, L, K, Rs, PiR, mp, add=None, eff=None):
+    """engine.py:851-901 (+ the add/reduce tail of relinearize / switch_key) -> new [L,N]"""
+    E, N = d.shape
+    assert E == L + K
+    out = torch.empty((L, N), dtype=torch.int64, device=d.device)
+    if eff is None:
+        eff = torch.empty((K, N), dtype=torch.int64, device=d.device)
+    with _Launch(d):
+        check(lib.ckks_moddown(_ptr(d), _rows(d, "moddown"), L, K, N, _ptr(_vec(Rs)), _ptr(PiR),
+                               _ptr(add) if add is not None else None,
+                               _rows(add, "moddown") if add is not None else 0,
+                               _ptr(out), N, _ptr(eff), *[_ptr(_vec(t)) for t in mp], _stream(d)), "moddown")
+    return out
+
+
+def automorphism(x, g, canon, _2q=None):
+    """encdec.rotate/conjugate (encdec.py:224-270) [+ make_unsigned + reduce_2q, engine.py:1196-1200]"""
+    s = _rows(x, "automorphism")
+    C, N = x.shape
+    out = torch.empty((C, N), dtype=torch.int64, device=x.device)
+    with _Launch(x):
+        check(lib.ckks_automorphism(_ptr(x), s, _ptr(out), N, C, N, int(g), 1 if canon else 0,
+                                    _ptr(_vec(_2q)) if _2q is not None else None, _stream(x)), "automorphism")
+    return out
