@@ -38,39 +38,7 @@ import flows  # noqa: E402
 ENGINE_PARAMS = dict(logN=12, num_scales=6, num_special_primes=2, scale_bits=40, is_secured=False)
 
 
-def sha(t):
-    a = np.ascontiguousarray(t.detach().cpu().numpy())
-    return hashlib.sha256(a.tobytes()).hexdigest()
-
-
-def describe(obj):
-    if isinstance(obj, data_struct):
-        return {"__ds__": dict(include_special=obj.include_special, ntt_state=obj.ntt_state,
-                               montgomery_state=obj.montgomery_state, origin=obj.origin, level=obj.level),
-                "data": describe(obj.data)}
-    if isinstance(obj, (list, tuple)):
-        return [describe(o) for o in obj]
-    if isinstance(obj, torch.Tensor):
-        return {"shape": list(obj.shape), "dtype": str(obj.dtype).replace("torch.", ""), "sha": sha(obj)}
-    if isinstance(obj, np.ndarray):
-        return {"shape": list(obj.shape), "dtype": str(obj.dtype), "sha": hashlib.sha256(np.ascontiguousarray(obj).tobytes()).hexdigest()}
-    raise TypeError(type(obj))
-
-
-class Recorder:
-    def __init__(self):
-        self.digests = {}
-        self.full = {}
-
-    def __call__(self, name, obj):
-        self.digests[name] = describe(obj)
-
-    def fix(self, name, obj):
-        self(name, obj)
-        # keep the full per-device tensors (small) so that the tests can inject them
-        for d, t in enumerate(obj):
-            self.full[f"{name}/{d}"] = t.detach().cpu().numpy()
-        return obj
+from golden_utils import Recorder, describe, sha  # noqa: E402,F401
 
 
 def jsonable(x):

@@ -1,0 +1,90 @@
+"""GPU parity of the ENGINE: liberate_b200.fhe.ckks_engine, driven by the same seeded sampler and the same
+scripted call sequence (tests/flows.py) as the unmodified reference engine was when the golden digests were
+recorded (tests/golden/make_golden.py), must reproduce every key and ciphertext tensor BIT FOR BIT:
+sk, pk, evk, rotation / conjugation keys, encrypt, rescale, cc_mult (triplet incl. lazy representatives),
+relinearize, rotate, conjugate, add/sub, level_up, scalar ops, decrypt -- at every level, for 1, 2 and 3
+logical devices (the reference's limb partitioning; several logical devices may share one physical GPU)."""
+import json
+
+import numpy as np
+import pytest
+import torch
+
+import flows
+from conftest import GOLDEN
+from golden_utils import Checker
+from seeded_rng import SeededCsprng
+
+pytestmark = pytest.mark.gpu
+
+
+def make_engine(D, params):
+    from liberate_b200 import fhe
+    eng = fhe.ckks_engine(devices=["cuda:0"] * D, **params)
+    eng.rng = SeededCsprng(eng.ctx.N, [len(d) for d in eng.ntt.p.d], max(eng.ntt.num_special_primes, 2),
+                           devices=eng.ntt.devices)
+    return eng
+
+
+@pytest.mark.parametrize("D", [1, 2, 3])
+def test_engine_reproduces_reference_tensors(D):
+    g = json.loads((GOLDEN / f"engine_D{D}.json").read_text())
+    full = np.load(GOLDEN / f"engine_D{D}_full.npz")
+    eng = make_engine(D, g["params"])
+    assert [int(x) for x in eng.ctx.q] == g["q"]
+    chk = Checker(g["digests"], full, eng.ntt.devices)
+    objs = flows.hot_path_flow(eng, chk)
+    assert set(chk.seen) == set(g["digests"]), set(g["digests"]) ^ set(chk.seen)
+    assert not chk.failures, chk.failures[:8]
+    # float side: decode of the (bit-identical) ciphertexts agrees with the reference's decode
+    dec = eng.decrode(objs["ct_ab"], objs["sk"])
+    assert np.abs(dec - full["decode_ab"]).max() < 1e-9
+    assert np.abs(dec - full["ma"] * full["mb"]).max() < 1e-6
+
+
+@pytest.mark.parametrize("D", [1, 2, 3])
+def test_engine_constants_match_reference(D):
+    g = json.loads((GOLDEN / f"engine_D{D}.json").read_text())
+    c = json.loads((GOLDEN / f"ntt_consts_D{D}.json").read_text())
+    eng = make_engine(D, g["params"])
+    assert eng.hash == c["hash"]
+    assert eng.ntt.starts == c["starts"] and eng.ntt.stops == c["stops"]
+    assert eng.parts_alloc == c["parts_alloc"] and eng.stor_ids == c["stor_ids"]
+    assert np.allclose(eng.deviations, c["deviations"], rtol=0, atol=0)
+    assert np.allclose(eng.corrections, c["corrections"], rtol=0, atol=0)
+    assert [t.tolist() for t in eng.mont_PR] == c["mont_PR"]
+    assert [t.tolist() for t in eng.final_scalar] == c["final_scalar"]
+    assert [[t.tolist() for t in lvl] for lvl in eng.rescale_scales] == c["rescale_scales"]
+    assert [[[t.tolist() for t in pind] for pind in lvl] for lvl in eng.PiRs] == c["PiRs"]
+    for key, ent in c["parts"].items():
+        dev, rows = key.split(":")
+        item = eng.ntt.parts_pack[int(dev)][tuple(int(r) for r in rows.split(","))]
+        assert (item["Y_host"] or None) == ent["Y_scalar"], key
+        assert (item["L_host"] or None) == ent["L_scalar"], key
+        if ent["Y_scalar"] is not None:
+            assert item["L_enter_host"] == ent["L_enter"], key
+
+
+def test_silver_end_to_end_accuracy():
+    """silver preset (BASELINE.json configs[1]): encrypt -> mult+relin -> rotate -> decrypt accuracy inside the
+    reference's published envelope (cc_mult ~5e-8, rotate ~6e-9; examples/[Example] Evaluators.ipynb)"""
+    from liberate_b200 import fhe
+    eng = fhe.ckks_engine(**{**fhe.params["silver"], "devices": [0]})
+    sk = eng.create_secret_key()
+    pk = eng.create_public_key(sk)
+    evk = eng.create_evk(sk)
+    rotk = eng.create_rotation_key(sk, 1)
+    rng = np.random.default_rng(0)
+    ma = rng.uniform(-1, 1, eng.num_slots) + 1j * rng.uniform(-1, 1, eng.num_slots)
+    mb = rng.uniform(-1, 1, eng.num_slots) + 1j * rng.uniform(-1, 1, eng.num_slots)
+    ca, cb = eng.encorypt(ma, pk), eng.encorypt(mb, pk)
+    assert np.abs(eng.decrode(ca, sk) - ma).max() < 1e-8
+    prod = eng.mult(ca, cb, evk)
+    assert prod.level == 1
+    assert np.abs(eng.decrode(prod, sk) - ma * mb).max() < 5e-7
+    rot = eng.rotate_single(prod, rotk)
+    assert np.abs(eng.decrode(rot, sk) - np.roll(ma * mb, 1)).max() < 5e-7
+    x = prod
+    while x.level < eng.num_levels - 1:
+        x = eng.mult(x, x, evk) if x.level < 3 else eng.mult(x, 1.0)
+    assert x.level == eng.num_levels - 1
