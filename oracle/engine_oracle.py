@@ -128,3 +128,119 @@ def automorphism(x, g, N):
     sign = np.where(pj >= N, -1, 1).astype(np.int64)
     out[:, pj % N] = x * sign[None, :]
     return out
+
+
+# ----------------------------------------------------------------------------------------------------
+# a whole single-device engine hot path assembled from the pieces above
+# ----------------------------------------------------------------------------------------------------
+class OracleEngine:
+    """rescale / cc_mult / relinearize / rotate on ONE device, numpy in, numpy out, following
+    ckks_engine.py:746-1214 for num_devices == 1.  Rows are the device's prime order: scale primes from
+    `level` on, base prime, then the K special primes (rns_partition for one device).  Used as the CPU
+    baseline ("port") by bench.py and as the checker in __graft_entry__.smoke()."""
+
+    def __init__(self, q, logN, K):
+        from .oracle import Params, R
+        self.q = [int(x) for x in q]
+        self.logN, self.N, self.K = logN, 1 << logN, K
+        self.L0 = len(self.q) - K          # ordinary limbs at level 0 (scale primes + base)
+        self.S = self.L0 - 1               # number of scale primes == number of levels
+        self.R = R
+        self.P = Params(self.q, logN)
+        nparts = -(-self.S // K)
+        self.partitions = [list(range(i * K, min((i + 1) * K, self.S))) for i in range(nparts)] + [[self.S]]
+        self._garner = {}
+
+    # rows (global prime indices) alive at `level`
+    def rows(self, level, special=True):
+        r = list(range(level, self.L0))
+        return r + list(range(self.L0, self.L0 + self.K)) if special else r
+
+    def params(self, level, special=True):
+        return self.P.slice(self.rows(level, special))
+
+    def parts(self, level):
+        """live partitions at `level` as lists of global prime indices (partially dropped ones shrink)"""
+        out = []
+        for p in self.partitions:
+            live = [i for i in p if i >= level]
+            if live:
+                out.append(live)
+        return out
+
+    def rescale(self, c, level):
+        """c: [L,N] rows(level, special=False) -> [L-1,N] at level+1 (engine.py:967-1052)"""
+        nxt = self.params(level + 1, special=False)
+        q0 = self.q[level]
+        scale = np.array([pow(q0, -1, qi) * self.R % qi for qi in nxt.q], dtype=np.int64)
+        return rescale_limbs(np.ascontiguousarray(c[1:]), c[0], scale, q0 // 2, nxt)
+
+    def cc_mult(self, a, b, level):
+        """a, b: (c0, c1) at `level` -> triplet (d0, d1, d2) at level+1, NTT + Montgomery (engine.py:1072-1101)"""
+        lv = level + 1
+        P = self.params(lv, special=False)
+        xs = [self.rescale(c, level) for c in (a[0], a[1], b[0], b[1])]
+        for x in xs:
+            C.enter_ntt(x, P.Rs, P.psi, P._2q, *P.mont)
+        return tensor_product(xs[0], xs[1], xs[2], xs[3], P), lv
+
+    def keyswitch(self, a, ksk, level):
+        """a: [L,N] plain rows(level, False); ksk: list over partitions of (k0, k1) each [E0,N] level-0 rows
+        -> (c0, c1) plain [L,N]  (create_switcher, engine.py:746-904, one device)"""
+        PE = self.params(level, special=True)
+        E = len(PE.q)
+        L = E - self.K
+        acc = None
+        for part in self.parts(level):
+            gid = next(i for i, p in enumerate(self.partitions) if part[-1] in p)
+            local = [i - level for i in part]
+            m = [self.q[i] for i in part]
+            key = tuple(part)
+            if key not in self._garner:
+                self._garner[key] = garner_constants(m, self.R)
+            Y, Ls, Lc = self._garner[key]
+            state = pre_extend(np.ascontiguousarray(a[local[0]:local[-1] + 1]), PE.slice(local), Y, Ls)
+            L_enter = [[Lc[i] * PE.R2[t] % PE.q[t] for t in range(E)] for i in range(len(m) - 1)]
+            ext = extend(state, PE, L_enter)
+            C.ntt(ext, PE.psi, PE._2q, *PE.mont)
+            k0, k1 = ksk[gid]
+            acc = ksk_inner(ext, np.ascontiguousarray(k0[level:]), np.ascontiguousarray(k1[level:]), acc, PE)
+        outs = []
+        specials = self.q[-self.K:][::-1]
+        PiR = [[pow(specials[i], -1, PE.q[j]) * self.R % PE.q[j] for j in range(E - i - 1)] for i in range(self.K)]
+        for d in acc:
+            C.intt(d, PE.ipsi, PE.Ninv, PE._2q, *PE.mont, exit_mode=2)
+            outs.append(moddown(d, L, self.K, PiR, PE))
+        return outs
+
+    def relinearize(self, triplet, evk, level):
+        """(d0,d1,d2) NTT+Montgomery at `level` -> (c0,c1) plain (engine.py:1117-1151)"""
+        P = self.params(level, special=False)
+        d = [x.copy() for x in triplet]
+        for x in d:
+            C.intt(x, P.ipsi, P.Ninv, P._2q, *P.mont, exit_mode=2)
+        k0, k1 = self.keyswitch(d[2], evk, level)
+        q = P.qa[:, None]
+        out = []
+        for base, ks in ((d[0], k0), (d[1], k1)):
+            s = base + ks
+            out.append(np.where(s < q, s, s - q))
+        return out
+
+    def mult(self, a, b, evk, level):
+        t, lv = self.cc_mult(a, b, level)
+        return self.relinearize(t, evk, lv), lv
+
+    def rotate(self, ct, rotk, delta, level):
+        """rotate_single (engine.py:1180-1214) for a plain ciphertext"""
+        P = self.params(level, special=False)
+        g = pow(3, delta % self.N, 2 * self.N)
+        q = P.qa[:, None]
+        moved = []
+        for c in ct:
+            r = automorphism(c, g, self.N) + q
+            moved.append(np.where(r < q, r, r - q))
+        k0, k1 = self.keyswitch(moved[1], rotk, level)
+        s = C.mont_add(np.ascontiguousarray(moved[0]), k0, P._2q)
+        C.reduce_2q(s, P._2q)
+        return [s, k1]

@@ -168,6 +168,18 @@ def gen_engine(D):
     (HERE / f"engine_D{D}.json").write_text(json.dumps(dict(params=ENGINE_PARAMS, q=[int(x) for x in eng.ctx.q],
                                                             digests=rec.digests)))
     np.savez_compressed(HERE / f"engine_D{D}_full.npz", **rec.full)
+    if D == 1:
+        # full INPUT tensors of the hot path for the CPU tests of the oracle's own engine restatement
+        # (tests/test_oracle_engine.py); outputs stay digests.
+        T = lambda t: t.numpy()
+        inputs = dict(ct_a0=T(objs["ct_a"].data[0][0]), ct_a1=T(objs["ct_a"].data[1][0]),
+                      ct_b0=T(objs["ct_b"].data[0][0]), ct_b1=T(objs["ct_b"].data[1][0]),
+                      ct_ab0=T(objs["ct_ab"].data[0][0]), ct_ab1=T(objs["ct_ab"].data[1][0]))
+        for name in ("evk", "rotk1"):
+            for i, part in enumerate(objs[name].data):
+                inputs[f"{name}/{i}/0"] = T(part.data[0][0])
+                inputs[f"{name}/{i}/1"] = T(part.data[1][0])
+        np.savez_compressed(HERE / "engine_D1_inputs.npz", **inputs)
 
 
 if __name__ == "__main__":
