@@ -1,0 +1,348 @@
+"""bench.py -- HE mults/sec (ct x ct + relinearize) at logN=16 (gold preset), BASELINE.json's metric.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...      (N > 1: one rank per GPU, NCCL)
+
+A "step" is one engine.mult(ct_a, ct_b, evk) = rescale x2 + 4 NTT + tensor product + 3 iNTT + hybrid key switch
+(ModUp -> beta*E NTTs -> evk inner product -> 2 iNTT -> ModDown) on level-0 gold ciphertexts.
+  value : mults/s with ciphertexts and keys resident in HBM (CUDA events, max over ranks)
+  e2e   : mults/s through the same engine call with the two input ciphertexts in pinned HOST memory and the
+          result read back to host inside the timed region (keys stay resident: they are long-lived operands)
+  roofline : the batched forward NTT of the key switch ([E', N] limbs per call), timed alone with CUDA events;
+          algorithmic bytes = 16 * E' * N per transform against the measured HBM copy peak
+  cpu_baseline / --impl reference : the oracle port (oracle/engine_oracle.OracleEngine, C + OpenMP) doing the same
+          mult on the host cores -- the reference has no CPU implementation of its own.
+N > 1 shards the RNS limbs of ONE multiplication over the ranks (the reference's own partitioning) with one
+all_gather (ModUp digits) and two broadcasts (rescale limbs) per step: total work is fixed -> "strong" scaling.
+Working set (2 ciphertexts + evk ~ 507 MB at gold) exceeds the 126 MB L2, so no explicit L2 flush is needed.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+for p in (ROOT, ROOT / "liberate-fhe_b200"):
+    if str(p) not in sys.path:
+        sys.path.insert(0, str(p))
+
+PRESET = "gold"
+METRIC = "he_mults_per_sec_logN16"
+UNIT = "mult/s"
+
+
+def measured_peak():
+    try:
+        return float(json.loads((ROOT / "MEASURED_PEAKS.json").read_text())["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.lines = []
+        self.proc = None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def __exit__(self, *a):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                pass
+
+    def summary(self):
+        sm, mx, reasons = [], 0, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx = max(mx, float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def gold_params():
+    from liberate_b200.fhe.presets import params
+    return {k: v for k, v in params[PRESET].items() if k != "devices"}
+
+
+# ---------------------------------------------------------------------------------------------------------
+def run_reference(args):
+    """the oracle port of the same mult on the host cores (bounded sample: `steps` whole multiplications)"""
+    import numpy as np
+    from liberate_b200.fhe.context import ckks_context
+    from oracle import oracle as O
+    from oracle.engine_oracle import OracleEngine
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    ctx = ckks_context(**gold_params())
+    K = ctx.num_special_primes
+    eng = OracleEngine(ctx.q, ctx.logN, K)
+    rng = np.random.default_rng(0)
+    L0 = eng.L0
+    q = np.array(ctx.q, dtype=np.int64)[:, None]
+    mk = lambda rows: rng.integers(0, q[rows], (len(rows), eng.N), dtype=np.int64)
+    a = (mk(list(range(L0))), mk(list(range(L0))))
+    b = (mk(list(range(L0))), mk(list(range(L0))))
+    allrows = list(range(L0 + K))
+    evk = [(mk(allrows), mk(allrows)) for _ in eng.partitions]   # random key material: same arithmetic, same bytes
+    # bounded sample: whole multiplications, as many of the requested steps as fit in ~150 s of CPU time
+    t0 = time.perf_counter()
+    for _ in range(min(args.warmup, 1)):
+        eng.mult(a, b, evk, 0)
+    one = max(time.perf_counter() - t0, 1e-3) if args.warmup else 5.0
+    steps = max(1, min(args.steps, int(150.0 / one)))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        eng.mult(a, b, evk, 0)
+    dt = time.perf_counter() - t0
+    v = steps / dt
+    args.steps = steps
+    cores = O.C.num_threads()
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+        "config": {"workload": "gold preset (logN=16, 35 ordinary + 4 special limbs) ct*ct mult + relinearize, level 0"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} whole multiplications by the C/OpenMP oracle port (the reference has no CPU path)"},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def run_reference_gpu(args):
+    """EXTRA arm (not part of the driver contract): the reference's own engine + CUDA kernels, installed under
+    oracle/_ref/site by oracle/build_ref.py --engine, timed on the same box for the same workload."""
+    import numpy as np
+    import torch
+    from oracle import ref_engine
+    if not ref_engine.available():
+        print(json.dumps({"impl": "reference_gpu", "unavailable": "oracle/_ref/site not installed"}))
+        return
+    ref_fhe, cache = ref_engine.load()
+    eng = ref_fhe.ckks_engine(devices=[0], cache_folder=cache, **gold_params())
+    sk = eng.create_secret_key()
+    pk = eng.create_public_key(sk)
+    evk = eng.create_evk(sk)
+    m = eng.example(-1, 1)
+    a, b = eng.encorypt(m, pk), eng.encorypt(m, pk)
+    for _ in range(args.warmup):
+        eng.mult(a, b, evk)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        out = eng.mult(a, b, evk)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    err = float(np.abs(eng.decrode(out, sk) - m * m).max())
+    print(json.dumps({"impl": "reference_gpu", "metric": METRIC, "value": 1e3 / ms, "unit": UNIT, "n_gpus": 1,
+                      "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+                      "dtype": "int64", "data": "synthetic", "decrypt_error": err,
+                      "config": {"workload": "gold preset ct*ct mult + relinearize, level-0 inputs; the reference's own "
+                                             "ckks_engine + ntt_cuda kernels compiled for sm_100 (unmodified sources)"}}))
+
+
+# ---------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import numpy as np
+    import torch
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    import liberate_b200
+    from liberate_b200 import fhe
+    from liberate_b200._lib import lib, check
+    from liberate_b200.csprng import Csprng
+
+    params = gold_params()
+    if world > 1:
+        eng = fhe.ckks_engine(devices=[f"cuda:{local_rank}"] * world, distributed=True, **params)
+    else:
+        eng = fhe.ckks_engine(devices=[local_rank], **params)
+    # identical sampler state on every rank so that the replicated channels agree
+    eng.rng = Csprng(eng.ctx.N, [len(d) for d in eng.ntt.p.d], max(eng.ntt.num_special_primes, 2),
+                     devices=eng.ntt.devices, local_ids=eng.local_ids, seed=20260925)
+    sk = eng.create_secret_key()
+    pk = eng.create_public_key(sk)
+    evk = eng.create_evk(sk)
+    rs = np.random.default_rng(1)
+    ma = rs.uniform(-1, 1, eng.num_slots) + 1j * rs.uniform(-1, 1, eng.num_slots)
+    mb = rs.uniform(-1, 1, eng.num_slots) + 1j * rs.uniform(-1, 1, eng.num_slots)
+    ct_a, ct_b = eng.encorypt(ma, pk), eng.encorypt(mb, pk)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def reduce_max(ms):
+        if dist is None:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0 = lib.launches
+        e0.record()
+        for _ in range(steps):
+            out = fn()
+        e1.record()
+        barrier()
+        return reduce_max(e0.elapsed_time(e1)) / steps, (lib.launches - n0) // steps, out
+
+    with ClockSampler(local_rank) as clk:
+        ms, launches, prod = timed(lambda: eng.mult(ct_a, ct_b, evk), args.steps, args.warmup)
+    clocks = clk.summary()
+
+    # correctness guard inside the bench: the product decrypts to ma*mb
+    if rank == 0 and world == 1:
+        err = float(np.abs(eng.decrode(prod, sk) - ma * mb).max())
+        assert err < 1e-6, f"bench product does not decrypt: {err}"
+
+    # ---- e2e: host-resident operands, result back to host ----------------------------------------------
+    def pinned(ct):
+        return [[t.cpu().pin_memory() if t is not None else None for t in poly] for poly in ct.data]
+
+    ha, hb = pinned(ct_a), pinned(ct_b)
+    out_host = [[torch.empty_like(t, device="cpu").pin_memory() if t is not None else None for t in poly]
+                for poly in prod.data]
+    h2d = sum(t.numel() * 8 for h in (ha, hb) for poly in h for t in poly if t is not None)
+    d2h = sum(t.numel() * 8 for poly in out_host for t in poly if t is not None)
+    dev = torch.device(f"cuda:{local_rank}")
+
+    def e2e_step():
+        da = [[t.to(dev, non_blocking=True) if t is not None else None for t in poly] for poly in ha]
+        db = [[t.to(dev, non_blocking=True) if t is not None else None for t in poly] for poly in hb]
+        r = eng.mult(ct_a._replace(data=da), ct_b._replace(data=db), evk)
+        for poly, hp in zip(r.data, out_host):
+            for t, h in zip(poly, hp):
+                if t is not None:
+                    h.copy_(t, non_blocking=True)
+        return r
+
+    ms_e2e, _, _ = timed(e2e_step, max(3, args.steps // 2), 3)
+
+    # ---- roofline of the dominant kernel pair: the key switch's batched forward NTT ----------------------
+    peak, peak_kind = measured_peak()
+    d0 = eng.local_ids[0]
+    level = 1
+    pack = eng.ntt.pack5(level, d0, -2)
+    E, N, logN = pack[0].numel(), eng.ctx.N, eng.ctx.logN
+    start = eng.ntt.starts[level][d0]
+    tw = eng.ntt.psi[d0][start:]
+    nbuf = max(2, int((320 << 20) // (E * N * 8)) + 1)
+    bufs = [torch.randint(0, 1 << 40, (E, N), dtype=torch.int64, device=dev) for _ in range(nbuf)]
+    st = torch.cuda.current_stream().cuda_stream
+    P = lambda t: t.data_ptr()
+
+    def ntt_call(i=[0]):
+        b = bufs[i[0] % nbuf]
+        i[0] += 1
+        check(lib.ckks_ntt(P(b), N, E, logN, P(tw), tw.stride(0), None, *[P(x) for x in pack], st), "ntt")
+
+    ms_ntt, _, _ = timed(ntt_call, 40, 5)
+    achieved = 16.0 * E * N / (ms_ntt * 1e-3) / 1e9
+
+    line = {
+        "metric": METRIC, "value": 1e3 / ms, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int64",
+        "data": "synthetic",
+        "config": {"workload": "gold preset (logN=16, 35 ordinary + 4 special limbs) ct*ct mult + relinearize, level-0 inputs",
+                   "parallelism": f"rns-limb-shard{world}", "l2": "working set 507 MB > 126 MB L2, no flush needed",
+                   "arithmetic": "bit-exact reference semantics (62-bit-buffer Montgomery, lazy [0,2q))"},
+        "clocks": clocks,
+        "e2e": {"value": 1e3 / ms_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": launches,
+        "roofline": {"bound": "hbm", "kernel": "ntt_fwd_colpass + ntt_fwd_blockpass (one batched forward NTT)",
+                     "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "limbs_per_launch": E, "ms_per_launch": ms_ntt},
+    }
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(eng, ct_a, ct_b, evk, prod)
+    if rank == 0:
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def cpu_baseline(eng, ct_a, ct_b, evk, prod):
+    """one whole multiplication by the oracle port on the host cores, on the SAME operands (also checks the GPU
+    result bit for bit)"""
+    import numpy as np
+    from oracle import oracle as O
+    from oracle.engine_oracle import OracleEngine
+    n = lambda t: t.cpu().numpy()
+    orc = OracleEngine(eng.ctx.q, eng.ctx.logN, eng.ctx.num_special_primes)
+    a = (n(ct_a.data[0][0]), n(ct_a.data[1][0]))
+    b = (n(ct_b.data[0][0]), n(ct_b.data[1][0]))
+    keys = [(n(p.data[0][0]), n(p.data[1][0])) for p in evk.data]
+    t0 = time.perf_counter()
+    out, _ = orc.mult(a, b, keys, 0)
+    dt = time.perf_counter() - t0
+    exact = bool((out[0] == n(prod.data[0][0])).all() and (out[1] == n(prod.data[1][0])).all())
+    return {"value": 1.0 / dt, "unit": UNIT, "cores": O.C.num_threads(), "kind": "port",
+            "sample": "1 whole gold multiplication by the C/OpenMP oracle port on the same operands",
+            "gpu_result_bit_exact": exact}
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference_gpu"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    elif args.impl == "reference_gpu":
+        run_reference_gpu(args)
+    else:
+        run_ours(args)

@@ -75,12 +75,28 @@ int ckks_tile_unsigned(const int64_t* a, int64_t* dst, int64_t dst_stride, int C
 /* painted psi[C][logN][N/2] (ckks_context.py:336-341) -> compact [C][N]; forward != 0 for psi, 0 for psi^-1 */
 int ckks_compact_twiddles(const int64_t* painted, int64_t* compact, int C, int logN, int forward, void* stream);
 
+/* ---- canonical-output ("fast") transforms for the fused path (additions) ----------------
+ * Congruent to ntt/enter_ntt resp. intt* but with CANONICAL output: ckks_ntt_fast == {[x scal], ntt, reduce to [0,q)},
+ * ckks_intt_fast == {intt stages, x scal, reduce to [0,q) or centred}.  Plain (non-Montgomery) twiddle tables:
+ * tw_u64 [period][N] of {w, floor(w 2^64/q)} and tw_f64 [period][N] doubles (built by ckks_fast_tables from the
+ * canonical plain table).  Row r uses the constants of limb r % period (batched key-switch extension).
+ * Inputs: forward [0, 2q) (any |x| < 2^51 for primes < 2^42); inverse [0, 2q).  scal/scal_sh: per-limb plain
+ * multiplier s and floor(s 2^64/q) (forward: optional, applied on load; inverse: required, e.g. N^-1 R^-1). */
+int ckks_fast_tables(const int64_t* plain, const int64_t* q, void* tw_u64, double* tw_f64, int C, int N, void* stream);
+int ckks_ntt_fast(int64_t* a, int64_t a_stride, int rows, int period, int logN, const void* tw_u64,
+                  const double* tw_f64, const int64_t* q, const int64_t* scal, const uint64_t* scal_sh,
+                  int force_int, void* stream);
+int ckks_intt_fast(int64_t* a, int64_t a_stride, int rows, int period, int logN, const void* tw_u64,
+                   const double* tw_f64, const int64_t* q, const int64_t* scal, const uint64_t* scal_sh,
+                   int centred, int force_int, void* stream);
+
 /* ---- level 2: fused hot-path operators (additions; engine.py line numbers = src/liberate/fhe/ckks_engine.py) */
 
 /* rescale (engine.py:1026-1038): out[i] = reduce_q( mont(in[i] - r0, scale[i]) + (r0 > round_at) ).
- * `in` rows are the limbs that survive; r0 is the dropped limb (one row of N). */
+ * `in` rows are the limbs that survive; r0 is the dropped limb (one row of N).  canon != 0 additionally maps the
+ * (congruent) slightly negative representatives the reference leaves here into [0,q) -- fused path only. */
 int ckks_rescale(const int64_t* in, int64_t in_stride, const int64_t* r0, int64_t* out, int64_t out_stride, int C,
-                 int N, const int64_t* scale, int64_t round_at, const int64_t* _2q, const int64_t* ql,
+                 int N, const int64_t* scale, int64_t round_at, int canon, const int64_t* _2q, const int64_t* ql,
                  const int64_t* qh, const int64_t* kl, const int64_t* kh, void* stream);
 
 /* tensor product (engine.py:1095-1101): d0 = x0*y0, d1 = x0*y1 (+) x1*y0, d2 = x1*y1 (lazy, NTT domain) */
@@ -98,10 +114,11 @@ int ckks_garner_digits(const int64_t* a, int64_t a_stride, int64_t* state, int64
 
 /* basis extension of one partition's digits to E target limbs (extend, engine.py:707-743):
  * out[t] = mont(state[0], Rs[t]) (+) mont(state[1], Lenter[0][t]) (+) ...  (lazy mont_add chain, Montgomery form).
- * Lenter: [(alpha-1)][E] row-major.  Target-limb constants have length E. */
+ * Lenter: [(alpha-1)][E] row-major.  Target-limb constants have length E.  canon != 0: result shifted into
+ * [0, 2q) when the lazy chain ends below zero (fused path only). */
 int ckks_extend(const int64_t* state, int64_t state_stride, int alpha, int64_t* out, int64_t out_stride, int E, int N,
-                const int64_t* Rs, const int64_t* Lenter, const int64_t* _2q, const int64_t* ql, const int64_t* qh,
-                const int64_t* kl, const int64_t* kh, void* stream);
+                const int64_t* Rs, const int64_t* Lenter, int canon, const int64_t* _2q, const int64_t* ql,
+                const int64_t* qh, const int64_t* kl, const int64_t* kh, void* stream);
 
 /* evaluation-key inner product (switcher_later_part + the Sigma over parts, engine.py:906-937, 832-840):
  * acc0[t] (+)= mont(ext[t], ksk0[t]), acc1[t] (+)= mont(ext[t], ksk1[t]); first != 0 overwrites instead. */
@@ -109,6 +126,14 @@ int ckks_ksk_accumulate(const int64_t* ext, int64_t ext_stride, const int64_t* k
                         int64_t ksk_stride, int64_t* acc0, int64_t* acc1, int64_t acc_stride, int E, int N, int first,
                         const int64_t* _2q, const int64_t* ql, const int64_t* qh, const int64_t* kl,
                         const int64_t* kh, void* stream);
+
+/* the same inner product over ALL `parts` partitions in one pass (ext: [parts*E rows]; k0_ptrs/k1_ptrs: device
+ * arrays of `parts` pointers to row 0 of each partition's key half, rows ksk_stride apart).  Congruent to the
+ * running sum above (same Montgomery products, same summation order). */
+int ckks_ksk_inner(const int64_t* ext, int64_t ext_stride, int parts, const int64_t* const* k0_ptrs,
+                   const int64_t* const* k1_ptrs, int64_t ksk_stride, int64_t* acc0, int64_t* acc1, int64_t acc_stride,
+                   int E, int N, const int64_t* _2q, const int64_t* ql, const int64_t* qh, const int64_t* kl,
+                   const int64_t* kh, void* stream);
 
 /* ModDown (engine.py:851-901): d is [E,N] = ordinary limbs (L rows) then K special rows, all plain in [0,q)
  * (after intt_exit_reduce).  Runs the K sequential "subtract special limb, multiply by P_j^-1" steps with the

@@ -6,6 +6,7 @@
 #include "../../include/ckks_b200.h"
 #include "mont.cuh"
 #include "ntt_kernels.cuh"
+#include "ntt_fast.cuh"
 
 using namespace ckks;
 
@@ -132,7 +133,7 @@ __global__ void k_compact(const int64_t* __restrict__ painted, int64_t* __restri
 // ---------------------------------------------------------------------------------------------
 __global__ void k_rescale(const int64_t* __restrict__ in, long long is, const int64_t* __restrict__ r0,
                           int64_t* __restrict__ out, long long os, int N, const int64_t* __restrict__ scale,
-                          int64_t round_at, MontPack m) {
+                          int64_t round_at, int canon, MontPack m) {
     const int i = blockIdx.y;
     const int j = 2 * (blockIdx.x * EW_THREADS + threadIdx.x);
     if (j >= N) return;
@@ -142,6 +143,10 @@ __global__ void k_rescale(const int64_t* __restrict__ in, long long is, const in
     longlong2 o;
     o.x = reduce_q(mont_mul_ss(x.x - r.x, sc, k.q4, k.k) + (r.x > round_at ? 1 : 0), q);
     o.y = reduce_q(mont_mul_ss(x.y - r.y, sc, k.q4, k.k) + (r.y > round_at ? 1 : 0), q);
+    if (canon) {  // the reference leaves slightly negative representatives here; the fused path wants [0,q)
+        o.x += (o.x < 0) ? q : 0;
+        o.y += (o.y < 0) ? q : 0;
+    }
     st2(out + i * os + j, o);
 }
 
@@ -203,7 +208,7 @@ __global__ void k_garner(const int64_t* __restrict__ a, long long as, int64_t* _
 // grid (N/2/EW_THREADS, E): target limb t
 __global__ void k_extend(const int64_t* __restrict__ st, long long ss, int alpha, int64_t* __restrict__ out,
                          long long os, int E, int N, const int64_t* __restrict__ Rs, const int64_t* __restrict__ Lenter,
-                         MontPack m) {
+                         int canon, MontPack m) {
     const int t = blockIdx.y;
     const int j = 2 * (blockIdx.x * EW_THREADS + threadIdx.x);
     if (j >= N) return;
@@ -220,7 +225,34 @@ __global__ void k_extend(const int64_t* __restrict__ st, long long ss, int alpha
         acc.x = lazy_add(acc.x, mont_mul_ss(v.x, le, k.q4, k.k), q2);
         acc.y = lazy_add(acc.y, mont_mul_ss(v.y, le, k.q4, k.k), q2);
     }
+    if (canon) {  // lazy chain can end slightly below zero (signed digits); bring into [0, 2q)
+        acc.x += (acc.x < 0) ? q2 : 0;
+        acc.y += (acc.y < 0) ? q2 : 0;
+    }
     st2(out + t * os + j, acc);
+}
+
+// evaluation-key inner product over ALL parts in one pass: acc_i[t] = (+)_p mont(ext[p][t], key_i[p][t])
+// ext: [parts*E rows]; key pointers: device arrays of `parts` row-0 pointers (row stride ks).
+__global__ void k_ksk_inner(const int64_t* __restrict__ ext, long long es, int parts, const int64_t* const* __restrict__ k0p,
+                            const int64_t* const* __restrict__ k1p, long long ks, int64_t* __restrict__ a0,
+                            int64_t* __restrict__ a1, long long as, int E, int N, MontPack m) {
+    const int t = blockIdx.y;
+    const int j = 2 * (blockIdx.x * EW_THREADS + threadIdx.x);
+    if (j >= N) return;
+    const LimbConst k = lc(m, t);
+    const int64_t q2 = (int64_t)k.q2;
+    longlong2 s0 = make_longlong2(0, 0), s1 = make_longlong2(0, 0);
+    for (int p = 0; p < parts; ++p) {
+        const longlong2 e = ld2(ext + ((long long)p * E + t) * es + j);
+        const longlong2 u = ld2(k0p[p] + t * ks + j), v = ld2(k1p[p] + t * ks + j);
+        s0.x = lazy_add(s0.x, mont_mul_ss(e.x, u.x, k.q4, k.k), q2);
+        s0.y = lazy_add(s0.y, mont_mul_ss(e.y, u.y, k.q4, k.k), q2);
+        s1.x = lazy_add(s1.x, mont_mul_ss(e.x, v.x, k.q4, k.k), q2);
+        s1.y = lazy_add(s1.y, mont_mul_ss(e.y, v.y, k.q4, k.k), q2);
+    }
+    st2(a0 + t * as + j, s0);
+    st2(a1 + t * as + j, s1);
 }
 
 __global__ void k_ksk_acc(const int64_t* __restrict__ ext, long long es, const int64_t* __restrict__ k0,
@@ -338,6 +370,16 @@ static int launch_inv_block(const NttArgs& A, dim3 grid, cudaStream_t st) {
     return launch_status();
 }
 
+template <int B>
+static int launch_fast_fwd_block(const FastArgs& F, dim3 grid, cudaStream_t st) {
+    fast_fwd_blockpass<B><<<grid, NTT_THREADS, SMEM_BYTES, st>>>(F);
+    return launch_status();
+}
+template <int B>
+static int launch_fast_inv_block(const FastArgs& F, dim3 grid, cudaStream_t st) {
+    fast_inv_blockpass<B><<<grid, NTT_THREADS, SMEM_BYTES, st>>>(F);
+    return launch_status();
+}
 }  // namespace
 
 #define CHECK_PTRS(...)                                  \
@@ -477,14 +519,73 @@ int ckks_intt(int64_t* a, int64_t as, int C, int logN, const int64_t* tw, int64_
     return launch_status();
 }
 
+// ---- canonical-output fast transforms --------------------------------------------------------------------
+int ckks_fast_tables(const int64_t* plain, const int64_t* q, void* tw_u64, double* tw_f64, int C, int N, void* stream) {
+    CHECK_PTRS(plain, q, tw_u64);
+    if (C <= 0 || N <= 0) return CKKS_E_BADARG;
+    fast_tables_kernel<<<dim3((N + 255) / 256, C), 256, 0, S(stream)>>>(plain, q, reinterpret_cast<ulonglong2*>(tw_u64),
+                                                                        tw_f64, N);
+    return launch_status();
+}
+
+int ckks_ntt_fast(int64_t* a, int64_t as, int rows, int period, int logN, const void* tw_u64, const double* tw_f64,
+                  const int64_t* q, const int64_t* scal, const uint64_t* scal_sh, int force_int, void* stream) {
+    CHECK_PTRS(a, tw_u64, q);
+    if (rows <= 0 || period <= 0 || (scal && !scal_sh)) return CKKS_E_BADARG;
+    if (!force_int && !tw_f64) return CKKS_E_BADARG;
+    if (logN < 12 || logN > 17) return CKKS_E_LOGN;
+    if (!row_ok(a, as) || !aligned16(tw_u64) || (tw_f64 && !aligned16(tw_f64))) return CKKS_E_ALIGN;
+    FastArgs F{a, as, reinterpret_cast<const ulonglong2*>(tw_u64), tw_f64, q, scal, scal_sh, period, logN, 0, force_int};
+    cudaStream_t st = S(stream);
+    const dim3 grid((1 << logN) / TILE, rows);
+    fast_fwd_colpass<0><<<grid, NTT_THREADS, SMEM_BYTES, st>>>(F);
+    int rc = launch_status();
+    if (rc) return rc;
+    F.scal = nullptr;
+    switch (logN - 8) {
+        case 4: return launch_fast_fwd_block<4>(F, grid, st);
+        case 5: return launch_fast_fwd_block<5>(F, grid, st);
+        case 6: return launch_fast_fwd_block<6>(F, grid, st);
+        case 7: return launch_fast_fwd_block<7>(F, grid, st);
+        case 8: return launch_fast_fwd_block<8>(F, grid, st);
+        case 9: return launch_fast_fwd_block<9>(F, grid, st);
+    }
+    return CKKS_E_LOGN;
+}
+
+int ckks_intt_fast(int64_t* a, int64_t as, int rows, int period, int logN, const void* tw_u64, const double* tw_f64,
+                   const int64_t* q, const int64_t* scal, const uint64_t* scal_sh, int centred, int force_int,
+                   void* stream) {
+    CHECK_PTRS(a, tw_u64, q, scal, scal_sh);
+    if (rows <= 0 || period <= 0) return CKKS_E_BADARG;
+    if (!force_int && !tw_f64) return CKKS_E_BADARG;
+    if (logN < 12 || logN > 17) return CKKS_E_LOGN;
+    if (!row_ok(a, as) || !aligned16(tw_u64) || (tw_f64 && !aligned16(tw_f64))) return CKKS_E_ALIGN;
+    FastArgs F{a, as, reinterpret_cast<const ulonglong2*>(tw_u64), tw_f64, q, scal, scal_sh, period, logN, centred, force_int};
+    cudaStream_t st = S(stream);
+    const dim3 grid((1 << logN) / TILE, rows);
+    int rc = CKKS_E_LOGN;
+    switch (logN - 8) {
+        case 4: rc = launch_fast_inv_block<4>(F, grid, st); break;
+        case 5: rc = launch_fast_inv_block<5>(F, grid, st); break;
+        case 6: rc = launch_fast_inv_block<6>(F, grid, st); break;
+        case 7: rc = launch_fast_inv_block<7>(F, grid, st); break;
+        case 8: rc = launch_fast_inv_block<8>(F, grid, st); break;
+        case 9: rc = launch_fast_inv_block<9>(F, grid, st); break;
+    }
+    if (rc) return rc;
+    fast_inv_colpass<0><<<grid, NTT_THREADS, SMEM_BYTES, st>>>(F);
+    return launch_status();
+}
+
 // ---- level 2 -----------------------------------------------------------------------------------------
 int ckks_rescale(const int64_t* in, int64_t is, const int64_t* r0, int64_t* out, int64_t os, int C, int N,
-                 const int64_t* scale, int64_t round_at, const int64_t* _2q, const int64_t* ql, const int64_t* qh,
-                 const int64_t* kl, const int64_t* kh, void* stream) {
+                 const int64_t* scale, int64_t round_at, int canon, const int64_t* _2q, const int64_t* ql,
+                 const int64_t* qh, const int64_t* kl, const int64_t* kh, void* stream) {
     CHECK_PTRS(in, r0, out, scale, _2q, ql, qh, kl, kh);
     if (C <= 0 || N <= 0 || (N & 1)) return CKKS_E_BADARG;
     if (!row_ok(in, is) || !row_ok(out, os) || !aligned16(r0)) return CKKS_E_ALIGN;
-    k_rescale<<<ew_grid(N, C), EW_THREADS, 0, S(stream)>>>(in, is, r0, out, os, N, scale, round_at,
+    k_rescale<<<ew_grid(N, C), EW_THREADS, 0, S(stream)>>>(in, is, r0, out, os, N, scale, round_at, canon,
                                                            MontPack{_2q, ql, qh, kl, kh});
     return launch_status();
 }
@@ -515,13 +616,13 @@ int ckks_garner_digits(const int64_t* a, int64_t as, int64_t* state, int64_t ss,
 }
 
 int ckks_extend(const int64_t* state, int64_t ss, int alpha, int64_t* out, int64_t os, int E, int N, const int64_t* Rs,
-                const int64_t* Lenter, const int64_t* _2q, const int64_t* ql, const int64_t* qh, const int64_t* kl,
-                const int64_t* kh, void* stream) {
+                const int64_t* Lenter, int canon, const int64_t* _2q, const int64_t* ql, const int64_t* qh,
+                const int64_t* kl, const int64_t* kh, void* stream) {
     CHECK_PTRS(state, out, Rs, _2q, ql, qh, kl, kh);
     if (alpha <= 0 || E <= 0 || N <= 0 || (N & 1)) return CKKS_E_BADARG;
     if (alpha > 1 && !Lenter) return CKKS_E_BADARG;
     if (!row_ok(state, ss) || !row_ok(out, os)) return CKKS_E_ALIGN;
-    k_extend<<<ew_grid(N, E), EW_THREADS, 0, S(stream)>>>(state, ss, alpha, out, os, E, N, Rs, Lenter,
+    k_extend<<<ew_grid(N, E), EW_THREADS, 0, S(stream)>>>(state, ss, alpha, out, os, E, N, Rs, Lenter, canon,
                                                           MontPack{_2q, ql, qh, kl, kh});
     return launch_status();
 }
@@ -535,6 +636,18 @@ int ckks_ksk_accumulate(const int64_t* ext, int64_t es, const int64_t* ksk0, con
         return CKKS_E_ALIGN;
     k_ksk_acc<<<ew_grid(N, E), EW_THREADS, 0, S(stream)>>>(ext, es, ksk0, ksk1, ks, acc0, acc1, as, N, first,
                                                            MontPack{_2q, ql, qh, kl, kh});
+    return launch_status();
+}
+
+int ckks_ksk_inner(const int64_t* ext, int64_t es, int parts, const int64_t* const* k0_ptrs,
+                   const int64_t* const* k1_ptrs, int64_t ks, int64_t* acc0, int64_t* acc1, int64_t as, int E, int N,
+                   const int64_t* _2q, const int64_t* ql, const int64_t* qh, const int64_t* kl, const int64_t* kh,
+                   void* stream) {
+    CHECK_PTRS(ext, k0_ptrs, k1_ptrs, acc0, acc1, _2q, ql, qh, kl, kh);
+    if (E <= 0 || parts <= 0 || N <= 0 || (N & 1)) return CKKS_E_BADARG;
+    if (!row_ok(ext, es) || (ks & 1) || !row_ok(acc0, as) || !row_ok(acc1, as)) return CKKS_E_ALIGN;
+    k_ksk_inner<<<ew_grid(N, E), EW_THREADS, 0, S(stream)>>>(ext, es, parts, k0_ptrs, k1_ptrs, ks, acc0, acc1, as, E, N,
+                                                             MontPack{_2q, ql, qh, kl, kh});
     return launch_status();
 }
 

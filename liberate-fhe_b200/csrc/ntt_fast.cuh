@@ -1,0 +1,454 @@
+// ntt_fast.cuh -- canonical-output ("fast") batched NTT / iNTT for the fused hot path, sm_100a (B200).
+//
+// Same two-pass / radix-16-in-registers structure and index algebra as ntt_kernels.cuh, but the butterflies no
+// longer reproduce the reference's lazy representatives: outputs are CANONICAL ([0,q), optionally centred),
+// which is all the fused mult / rotate path needs (every reference sequence on that path ends in reduce_2q;
+// DESIGN.md section 6).  That freedom is spent on the instruction mix the B200 actually has
+// (profiles/r01_pipe_microbench.txt: 4 issue slots/clk/SM; IMAD 2/clk, FP64 1.8/clk, IMAD+DFMA co-issue 3.8/clk):
+//
+//   * scale primes (q < 2^42, 34 of 39 limbs at gold): FP64 ERROR-FREE butterflies.  A coefficient (|v| < 2^51) lives
+//     in a double; v*w is formed exactly as p + e = (v*w rounded, fma residual), the quotient by a magic-constant
+//     rint(p/q), and r = fma(-c, q, p) + e is the exact integer v*w - c*q with |r| < 0.54 q.  8 FP64-pipe
+//     instructions per butterfly, no carries, no conditional corrections, on a pipe the integer kernels leave idle.
+//   * 60-bit primes (base + special): Shoup/Harvey lazy butterflies on 64-bit integers, twiddle w with
+//     w' = floor(w 2^64 / q): t = umulhi(v, w'), r = v*w - t*q in [0, 2q); one conditional correction per butterfly.
+//
+// Twiddles are PLAIN (non-Montgomery) powers of psi: the transform is linear, so Montgomery-form data stay in
+// Montgomery form.  Tables: shoup[C][N] = {w, w'} (16 B) and dbl[C][N] (8 B, small primes only).
+#pragma once
+#include "ntt_kernels.cuh"
+
+namespace ckks {
+
+constexpr double F64_MAGIC = 6755399441055744.0;      // 1.5 * 2^52: x + MAGIC - MAGIC == rint(x) for |x| < 2^51
+constexpr uint64_t SMALL_PRIME_LIMIT = 1ull << 42;
+
+// ------------------------------------------------------------------------------------------------------------
+// FP64 arithmetic
+// ------------------------------------------------------------------------------------------------------------
+struct F64C {
+    double q, qinv;
+};
+__device__ __forceinline__ double f64_mulmod(double v, double w, const F64C& c) {
+    const double p = __dmul_rn(v, w);
+    const double e = __fma_rn(v, w, -p);
+    const double m = __dadd_rn(__fma_rn(p, c.qinv, F64_MAGIC), -F64_MAGIC);
+    return __dadd_rn(__fma_rn(-m, c.q, p), e);
+}
+__device__ __forceinline__ double f64_reduce(double v, const F64C& c) {   // -> |r| <= q/2 (+1)
+    const double m = __dadd_rn(__fma_rn(v, c.qinv, F64_MAGIC), -F64_MAGIC);
+    return __fma_rn(-m, c.q, v);
+}
+// |x| < 2^51 integer <-> double without the slow conversion pipe
+__device__ __forceinline__ double i2d(int64_t x) {
+    const uint64_t t = (uint64_t)(x + (1ll << 51)) | 0x4330000000000000ull;
+    return __dadd_rn(__longlong_as_double((long long)t), -(4503599627370496.0 + 2251799813685248.0));
+}
+__device__ __forceinline__ int64_t d2i(double v) {
+    const uint64_t t = (uint64_t)__double_as_longlong(__dadd_rn(v, 4503599627370496.0 + 2251799813685248.0));
+    return (int64_t)(t & 0x000FFFFFFFFFFFFFull) - (1ll << 51);
+}
+
+struct ArithF64 {
+    using T = double;
+    using TW = double;
+    using C = F64C;
+    static __device__ __forceinline__ T load(int64_t x) { return i2d(x); }
+    static __device__ __forceinline__ int64_t store_lazy(T v, const C& c) { return d2i(f64_reduce(v, c)); }
+    static __device__ __forceinline__ int64_t store_canon(T v, const C& c, bool centred) {
+        double r = f64_reduce(v, c);
+        if (!centred) r = (r < 0.0) ? __dadd_rn(r, c.q) : r;
+        return d2i(r);
+    }
+    static __device__ __forceinline__ T mul(T v, TW w, const C& c) { return f64_mulmod(v, w, c); }
+    static __device__ __forceinline__ void ct(T& U, T& V, TW w, const C& c) {
+        const T r = f64_mulmod(V, w, c);
+        V = __dadd_rn(U, -r);
+        U = __dadd_rn(U, r);
+    }
+    static __device__ __forceinline__ void gs(T& U, T& V, TW w, const C& c) {
+        const T t = __dadd_rn(U, -V);
+        U = __dadd_rn(U, V);
+        V = f64_mulmod(t, w, c);
+    }
+    // magnitudes double along the sum outputs of GS stages: re-centre once per radix-16 round
+    static __device__ __forceinline__ void tame(T& v, const C& c) { v = f64_reduce(v, c); }
+    template <int RUN>
+    static __device__ __forceinline__ void load_tw(TW (&w)[8], const TW* __restrict__ p) {
+        if (RUN == 1) {
+            w[0] = __ldg(p);
+        } else {
+#pragma unroll
+            for (int g = 0; g < RUN; g += 2) {
+                const double2 v = __ldg(reinterpret_cast<const double2*>(p + g));
+                w[g] = v.x;
+                w[g + 1] = v.y;
+            }
+        }
+    }
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// 64-bit integer Shoup / Harvey arithmetic (any q < 2^62; values kept in [0, 4q) forward, [0, 2q) inverse)
+// ------------------------------------------------------------------------------------------------------------
+struct U64C {
+    uint64_t q, q2;
+};
+__device__ __forceinline__ uint64_t shoup_mul(uint64_t v, uint64_t w, uint64_t wp, uint64_t q) {
+    const uint64_t t = __umul64hi(v, wp);
+    return v * w - t * q;   // in [0, 2q) for any v < 2^64
+}
+struct ArithU64 {
+    using T = uint64_t;
+    using TW = ulonglong2;   // {w, w'}
+    using C = U64C;
+    static __device__ __forceinline__ T load(int64_t x) { return (uint64_t)x; }   // expects [0, 4q)
+    static __device__ __forceinline__ int64_t store_lazy(T v, const C& c) { return (int64_t)v; }
+    static __device__ __forceinline__ int64_t store_canon(T v, const C& c, bool centred) {
+        v = (v >= c.q2) ? v - c.q2 : v;
+        v = (v >= c.q2) ? v - c.q2 : v;           // [0,4q) or even [0,6q) -> [0,2q)
+        v = (v >= c.q) ? v - c.q : v;
+        int64_t r = (int64_t)v;
+        if (centred) r = (r > (int64_t)(c.q >> 1)) ? r - (int64_t)c.q : r;
+        return r;
+    }
+    static __device__ __forceinline__ T mul(T v, TW w, const C& c) { return shoup_mul(v, w.x, w.y, c.q); }
+    static __device__ __forceinline__ void ct(T& U, T& V, TW w, const C& c) {
+        const T u = (U >= c.q2) ? U - c.q2 : U;
+        const T t = shoup_mul(V, w.x, w.y, c.q);
+        U = u + t;
+        V = u - t + c.q2;
+    }
+    static __device__ __forceinline__ void gs(T& U, T& V, TW w, const C& c) {
+        const T s = U + V;
+        const T d = U - V + c.q2;
+        U = (s >= c.q2) ? s - c.q2 : s;
+        V = shoup_mul(d, w.x, w.y, c.q);
+    }
+    static __device__ __forceinline__ void tame(T& v, const C& c) {}
+    template <int RUN>
+    static __device__ __forceinline__ void load_tw(TW (&w)[8], const TW* __restrict__ p) {
+#pragma unroll
+        for (int g = 0; g < RUN; ++g) w[g] = __ldg(p + g);
+    }
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// rounds
+// ------------------------------------------------------------------------------------------------------------
+template <class A, int FIRST>
+__device__ __forceinline__ void fast_fwd_round(typename A::T (&e)[16], const typename A::TW* __restrict__ W, int s0,
+                                               unsigned pre, const typename A::C& c) {
+#pragma unroll
+    for (int i = FIRST; i < 4; ++i) {
+        const int d = 8 >> i;
+        const typename A::TW* wp = W + ((1u << (s0 + i)) + (pre << i));
+        typename A::TW w[8];
+        if (i == 0) A::template load_tw<1>(w, wp);
+        if (i == 1) A::template load_tw<2>(w, wp);
+        if (i == 2) A::template load_tw<4>(w, wp);
+        if (i == 3) A::template load_tw<8>(w, wp);
+#pragma unroll
+        for (int k = 0; k < 16; ++k)
+            if (!(k & d)) A::ct(e[k], e[k + d], w[k >> (4 - i)], c);
+    }
+}
+template <class A, int NST>
+__device__ __forceinline__ void fast_inv_round(typename A::T (&e)[16], const typename A::TW* __restrict__ W, int s0,
+                                               unsigned pre, const typename A::C& c) {
+#pragma unroll
+    for (int i = 0; i < NST; ++i) {
+        const int d = 1 << i;
+        const int ip = 3 - i;
+        const typename A::TW* wp = W + ((1u << (s0 + ip)) + (pre << ip));
+        typename A::TW w[8];
+        if (ip == 0) A::template load_tw<1>(w, wp);
+        if (ip == 1) A::template load_tw<2>(w, wp);
+        if (ip == 2) A::template load_tw<4>(w, wp);
+        if (ip == 3) A::template load_tw<8>(w, wp);
+#pragma unroll
+        for (int k = 0; k < 16; ++k)
+            if (!(k & d)) A::gs(e[k], e[k + d], w[k >> (i + 1)], c);
+    }
+#pragma unroll
+    for (int k = 0; k < 16; ++k) A::tame(e[k], c);
+}
+
+// shared-memory exchange on the raw 64-bit patterns (double and uint64 share the slot layout)
+template <class T>
+__device__ __forceinline__ void smx_store(int64_t* sm, const T (&e)[16], int tau, int p) {
+    int64_t r[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) r[k] = *reinterpret_cast<const int64_t*>(&e[k]);
+    sm_store_field(sm, r, tau, p);
+}
+template <class T>
+__device__ __forceinline__ void smx_load(const int64_t* sm, T (&e)[16], int tau, int p) {
+    int64_t r[16];
+    sm_load_field(sm, r, tau, p);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) e[k] = *reinterpret_cast<const T*>(&r[k]);
+}
+
+struct FastArgs {
+    int64_t* a;                 // [rows] in place
+    long long a_stride;
+    const ulonglong2* tw_u64;   // [period][N] {w, w'} plain twiddles (psi for forward, psi^-1 for inverse)
+    const double* tw_f64;       // [period][N] the same values as doubles (only read for small primes)
+    const int64_t* q;           // [period]
+    const int64_t* scal;        // [period] optional per-limb plain multiplier (forward: on load; inverse: at the end)
+    const uint64_t* scal_sh;    // [period] its Shoup companion floor(s 2^64 / q)
+    int period;                 // constants / twiddles of row r are those of limb r % period
+    int logN;
+    int centred;                // inverse only: output in (-q/2, q/2] instead of [0, q)
+    int force_int;              // 1: use the integer path for every limb (pipe balancing / testing)
+};
+
+template <class A>
+__device__ __forceinline__ typename A::C make_const(uint64_t q);
+template <>
+__device__ __forceinline__ F64C make_const<ArithF64>(uint64_t q) {
+    return F64C{(double)q, 1.0 / (double)q};
+}
+template <>
+__device__ __forceinline__ U64C make_const<ArithU64>(uint64_t q) {
+    return U64C{q, q << 1};
+}
+template <class A>
+__device__ __forceinline__ const typename A::TW* tw_row(const FastArgs& F, int limb);
+template <>
+__device__ __forceinline__ const double* tw_row<ArithF64>(const FastArgs& F, int limb) {
+    return F.tw_f64 + ((long long)limb << F.logN);
+}
+template <>
+__device__ __forceinline__ const ulonglong2* tw_row<ArithU64>(const FastArgs& F, int limb) {
+    return F.tw_u64 + ((long long)limb << F.logN);
+}
+template <class A>
+__device__ __forceinline__ typename A::TW scalar_tw(const FastArgs& F, int limb);
+template <>
+__device__ __forceinline__ double scalar_tw<ArithF64>(const FastArgs& F, int limb) {
+    return (double)F.scal[limb];
+}
+template <>
+__device__ __forceinline__ ulonglong2 scalar_tw<ArithU64>(const FastArgs& F, int limb) {
+    return make_ulonglong2((uint64_t)F.scal[limb], F.scal_sh[limb]);
+}
+
+// ---- forward pass A (column pass, stages 0..7) -------------------------------------------------------------
+template <class A>
+__device__ __forceinline__ void fast_fwd_col_body(const FastArgs& F, int64_t* sm, int limb) {
+    using T = typename A::T;
+    const int tau = threadIdx.x;
+    const int b = F.logN - 8;
+    const typename A::C c = make_const<A>((uint64_t)F.q[limb]);
+    int64_t* __restrict__ row0 = F.a + (long long)blockIdx.y * F.a_stride + (long long)blockIdx.x * 16;
+    const typename A::TW* __restrict__ W = tw_row<A>(F, limb);
+    T e[16];
+    {
+        const int r0 = tau >> 4, col = tau & 15;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) e[k] = A::load(row0[((long long)(r0 + 16 * k) << b) + col]);
+        if (F.scal) {
+            const typename A::TW s = scalar_tw<A>(F, limb);
+#pragma unroll
+            for (int k = 0; k < 16; ++k) e[k] = A::mul(e[k], s, c);
+        }
+        fast_fwd_round<A, 0>(e, W, 0, 0u, c);
+        smx_store(sm, e, tau, 8);
+    }
+    __syncthreads();
+    {
+        smx_load(sm, e, tau, 4);
+        const int hi = tau >> 4, col = tau & 15;
+        fast_fwd_round<A, 0>(e, W, 4, (unsigned)hi, c);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) row0[((long long)(hi * 16 + k) << b) + col] = A::store_lazy(e[k], c);
+    }
+}
+
+template <int DUMMY>
+__global__ void __launch_bounds__(NTT_THREADS) fast_fwd_colpass(const FastArgs F) {
+    extern __shared__ __align__(16) int64_t sm[];
+    const int limb = blockIdx.y % F.period;
+    if (!F.force_int && (uint64_t)F.q[limb] < SMALL_PRIME_LIMIT)
+        fast_fwd_col_body<ArithF64>(F, sm, limb);
+    else
+        fast_fwd_col_body<ArithU64>(F, sm, limb);
+}
+
+// ---- forward pass B (block pass, stages 8..logN-1), canonical [0,q) out --------------------------------------
+template <class A, int B>
+__device__ __forceinline__ void fast_fwd_block_body(const FastArgs& F, int64_t* sm, int limb) {
+    using T = typename A::T;
+    const int tau = threadIdx.x;
+    const unsigned chunk = blockIdx.x;
+    constexpr int logN = B + 8;
+    const typename A::C c = make_const<A>((uint64_t)F.q[limb]);
+    int64_t* __restrict__ g = F.a + (long long)blockIdx.y * F.a_stride + (long long)chunk * TILE;
+    const typename A::TW* __restrict__ W = tw_row<A>(F, limb);
+    T e[16];
+    constexpr int P1 = B - 4;
+    {
+        const int zb = zbase(tau, P1);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) e[k] = A::load(g[zb | (k << P1)]);
+        fast_fwd_round<A, 0>(e, W, logN - 4 - P1, (chunk << (8 - P1)) | (unsigned)(tau >> P1), c);
+    }
+    if constexpr (B >= 8) {
+        constexpr int P2 = B - 8;
+        smx_store(sm, e, tau, P1);
+        __syncthreads();
+        smx_load(sm, e, tau, P2);
+        fast_fwd_round<A, 0>(e, W, logN - 4 - P2, (chunk << (8 - P2)) | (unsigned)(tau >> P2), c);
+        if constexpr (B == 9) {
+            __syncthreads();
+            smx_store(sm, e, tau, P2);
+            __syncthreads();
+            smx_load(sm, e, tau, 0);
+            fast_fwd_round<A, 3>(e, W, logN - 4, (chunk << 8) | (unsigned)tau, c);
+        }
+        __syncthreads();
+    } else if constexpr (B > 4) {
+        smx_store(sm, e, tau, P1);
+        __syncthreads();
+        smx_load(sm, e, tau, 0);
+        fast_fwd_round<A, 8 - B>(e, W, logN - 4, (chunk << 8) | (unsigned)tau, c);
+        __syncthreads();
+    }
+    {   // canonical values back through shared memory for coalesced 128-bit stores
+        int64_t r[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) r[k] = A::store_canon(e[k], c, false);
+        sm_store_field(sm, r, tau, 0);
+    }
+    __syncthreads();
+    sm_to_global(sm, g, tau);
+}
+
+template <int B>
+__global__ void __launch_bounds__(NTT_THREADS) fast_fwd_blockpass(const FastArgs F) {
+    extern __shared__ __align__(16) int64_t sm[];
+    const int limb = blockIdx.y % F.period;
+    if (!F.force_int && (uint64_t)F.q[limb] < SMALL_PRIME_LIMIT)
+        fast_fwd_block_body<ArithF64, B>(F, sm, limb);
+    else
+        fast_fwd_block_body<ArithU64, B>(F, sm, limb);
+}
+
+// ---- inverse pass B' (levels 0..B-1) ---------------------------------------------------------------------------
+template <class A, int B>
+__device__ __forceinline__ void fast_inv_block_body(const FastArgs& F, int64_t* sm, int limb) {
+    using T = typename A::T;
+    const int tau = threadIdx.x;
+    const unsigned chunk = blockIdx.x;
+    constexpr int logN = B + 8;
+    const typename A::C c = make_const<A>((uint64_t)F.q[limb]);
+    int64_t* __restrict__ g = F.a + (long long)blockIdx.y * F.a_stride + (long long)chunk * TILE;
+    const typename A::TW* __restrict__ W = tw_row<A>(F, limb);
+    T e[16];
+    global_to_sm(sm, g, tau);
+    __syncthreads();
+    {
+        int64_t r[16];
+        sm_load_field(sm, r, tau, 0);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) e[k] = A::load(r[k]);
+    }
+    fast_inv_round<A, 4>(e, W, logN - 4, (chunk << 8) | (unsigned)tau, c);
+    if constexpr (B == 4) {
+        int64_t r[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) r[k] = A::store_lazy(e[k], c);
+        __syncthreads();
+        sm_store_field(sm, r, tau, 0);
+        __syncthreads();
+        sm_to_global(sm, g, tau);
+    } else {
+        __syncthreads();
+        smx_store(sm, e, tau, 0);
+        __syncthreads();
+        smx_load(sm, e, tau, 4);
+        constexpr int NST = (B >= 8) ? 4 : B - 4;
+        fast_inv_round<A, NST>(e, W, logN - 8, (chunk << 4) | (unsigned)(tau >> 4), c);
+        if constexpr (B == 9) {
+            __syncthreads();
+            smx_store(sm, e, tau, 4);
+            __syncthreads();
+            smx_load(sm, e, tau, 8);
+            fast_inv_round<A, 1>(e, W, logN - 12, chunk, c);
+            const int zb = zbase(tau, 8);
+#pragma unroll
+            for (int k = 0; k < 16; ++k) g[zb | (k << 8)] = A::store_lazy(e[k], c);
+        } else {
+            const int zb = zbase(tau, 4);
+#pragma unroll
+            for (int k = 0; k < 16; ++k) g[zb | (k << 4)] = A::store_lazy(e[k], c);
+        }
+    }
+}
+
+template <int B>
+__global__ void __launch_bounds__(NTT_THREADS) fast_inv_blockpass(const FastArgs F) {
+    extern __shared__ __align__(16) int64_t sm[];
+    const int limb = blockIdx.y % F.period;
+    if (!F.force_int && (uint64_t)F.q[limb] < SMALL_PRIME_LIMIT)
+        fast_inv_block_body<ArithF64, B>(F, sm, limb);
+    else
+        fast_inv_block_body<ArithU64, B>(F, sm, limb);
+}
+
+// ---- inverse pass A' (levels b..logN-1), x scalar, canonical out ---------------------------------------------
+template <class A>
+__device__ __forceinline__ void fast_inv_col_body(const FastArgs& F, int64_t* sm, int limb) {
+    using T = typename A::T;
+    const int tau = threadIdx.x;
+    const int b = F.logN - 8;
+    const typename A::C c = make_const<A>((uint64_t)F.q[limb]);
+    int64_t* __restrict__ row0 = F.a + (long long)blockIdx.y * F.a_stride + (long long)blockIdx.x * 16;
+    const typename A::TW* __restrict__ W = tw_row<A>(F, limb);
+    T e[16];
+    {
+        const int hi = tau >> 4, col = tau & 15;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) e[k] = A::load(row0[((long long)(hi * 16 + k) << b) + col]);
+        fast_inv_round<A, 4>(e, W, 4, (unsigned)hi, c);
+        smx_store(sm, e, tau, 4);
+    }
+    __syncthreads();
+    {
+        smx_load(sm, e, tau, 8);
+        fast_inv_round<A, 4>(e, W, 0, 0u, c);
+        const typename A::TW s = scalar_tw<A>(F, limb);
+        const int r0 = tau >> 4, col = tau & 15;
+#pragma unroll
+        for (int k = 0; k < 16; ++k)
+            row0[((long long)(r0 + 16 * k) << b) + col] = A::store_canon(A::mul(e[k], s, c), c, F.centred != 0);
+    }
+}
+
+template <int DUMMY>
+__global__ void __launch_bounds__(NTT_THREADS) fast_inv_colpass(const FastArgs F) {
+    extern __shared__ __align__(16) int64_t sm[];
+    const int limb = blockIdx.y % F.period;
+    if (!F.force_int && (uint64_t)F.q[limb] < SMALL_PRIME_LIMIT)
+        fast_inv_col_body<ArithF64>(F, sm, limb);
+    else
+        fast_inv_col_body<ArithU64>(F, sm, limb);
+}
+
+// ---- table construction ----------------------------------------------------------------------------------------
+// plain canonical twiddles [C][N] -> {w, floor(w 2^64 / q)} and double(w)
+__global__ void fast_tables_kernel(const int64_t* __restrict__ plain, const int64_t* __restrict__ q,
+                                   ulonglong2* __restrict__ sh, double* __restrict__ dbl, int N) {
+    const int i = blockIdx.y;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= N) return;
+    const uint64_t w = (uint64_t)plain[(long long)i * N + j];
+    const unsigned __int128 num = ((unsigned __int128)w) << 64;
+    const uint64_t wp = (uint64_t)(num / (unsigned __int128)(uint64_t)q[i]);
+    sh[(long long)i * N + j] = make_ulonglong2(w, wp);
+    if (dbl) dbl[(long long)i * N + j] = (double)w;
+}
+
+}  // namespace ckks

@@ -32,11 +32,15 @@ SIGNATURES = {
     "ckks_mont_sub": [_i64p, _i64, _i64p, _i64, _i64p, _i64, _int, _int, _i64p, _vp],
     "ckks_tile_unsigned": [_i64p, _i64p, _i64, _int, _int, _i64p, _vp],
     "ckks_compact_twiddles": [_i64p, _i64p, _int, _int, _int, _vp],
-    "ckks_rescale": [_i64p, _i64, _i64p, _i64p, _i64, _int, _int, _i64p, _i64, _i64p, _i64p, _i64p, _i64p, _i64p, _vp],
+    "ckks_fast_tables": [_i64p, _i64p, _vp, _vp, _int, _int, _vp],
+    "ckks_ntt_fast": [_i64p, _i64, _int, _int, _int, _vp, _vp, _i64p, _i64p, _i64p, _int, _vp],
+    "ckks_intt_fast": [_i64p, _i64, _int, _int, _int, _vp, _vp, _i64p, _i64p, _i64p, _int, _int, _vp],
+    "ckks_rescale": [_i64p, _i64, _i64p, _i64p, _i64, _int, _int, _i64p, _i64, _int, _i64p, _i64p, _i64p, _i64p, _i64p, _vp],
     "ckks_tensor_product": [_i64p, _i64p, _i64p, _i64p, _i64, _i64p, _i64p, _i64p, _i64, _int, _int,
                             _i64p, _i64p, _i64p, _i64p, _i64p, _vp],
     "ckks_garner_digits": [_i64p, _i64, _i64p, _i64, _int, _int, _i64p, _i64p, _i64p, _i64p, _i64p, _i64p, _vp],
-    "ckks_extend": [_i64p, _i64, _int, _i64p, _i64, _int, _int, _i64p, _i64p, _i64p, _i64p, _i64p, _i64p, _i64p, _vp],
+    "ckks_extend": [_i64p, _i64, _int, _i64p, _i64, _int, _int, _i64p, _i64p, _int, _i64p, _i64p, _i64p, _i64p, _i64p, _vp],
+    "ckks_ksk_inner": [_i64p, _i64, _int, _vp, _vp, _i64, _i64p, _i64p, _i64, _int, _int, _i64p, _i64p, _i64p, _i64p, _i64p, _vp],
     "ckks_ksk_accumulate": [_i64p, _i64, _i64p, _i64p, _i64, _i64p, _i64p, _i64, _int, _int, _int,
                             _i64p, _i64p, _i64p, _i64p, _i64p, _vp],
     "ckks_moddown": [_i64p, _i64, _int, _int, _int, _i64p, _i64p, _i64p, _i64, _i64p, _i64, _i64p,
@@ -71,7 +75,28 @@ def _load():
     return lib
 
 
-lib = _load()
+# kernels launched per entry point (for bench.py's gpu_launches accounting)
+KERNELS_PER_CALL = {"ckks_abi_version": 0, "ckks_ntt": 2, "ckks_intt": 2, "ckks_moddown": 2, "ckks_ntt_fast": 2,
+                    "ckks_intt_fast": 2}
+
+
+class _Counted:
+    """the loaded library with a launch counter: lib.<entry>(...) -> int status"""
+
+    def __init__(self, cdll):
+        self._cdll = cdll
+        self.launches = 0
+        for name in SIGNATURES:
+            setattr(self, name, self._wrap(getattr(cdll, name), KERNELS_PER_CALL.get(name, 1)))
+
+    def _wrap(self, fn, n):
+        def call(*args):
+            self.launches += n
+            return fn(*args)
+        return call
+
+
+lib = _Counted(_load())
 
 
 def check(rc, what):

@@ -49,7 +49,10 @@ def _live(xs):
 class ckks_engine:
     @errors.log_error
     def __init__(self, devices: list[int] = None, verbose: bool = False, bias_guard: bool = True,
-                 norm: str = "forward", distributed: bool = False, rng=None, **ctx_params):
+                 norm: str = "forward", distributed: bool = False, rng=None, fast: bool = True, **ctx_params):
+        # fast=True: mult(relin=True) / rotate use the canonical-output transforms (FP64 + Shoup butterflies);
+        # results are bit-identical either way, only invisible intermediate representatives differ
+        self.fast = fast
         self.bias_guard = bias_guard
         self.norm = norm
         self.version = VERSION
@@ -167,6 +170,7 @@ class ckks_engine:
                 per_p.append(per_dev)
             self.PiRs.append(per_p)
         self._PiR_dense = {}
+        self._ptr_cache = {}
 
         P = math.prod(c.q[-K:])
         self.mont_PR = [self._t([P * c.R % c.q[i] for i in p.destination_arrays[0][dev]], dev) if self._local(dev) else None
@@ -529,7 +533,25 @@ class ckks_engine:
         return fused.extend(state, self.ntt.Rs[tgt][start:], self.ntt.lenter(level, device_id, part_id, tgt),
                             self.ntt.pack5(level, tgt, -2))
 
-    def create_switcher(self, a: list[torch.Tensor], ksk: data_struct, level, exit_ntt=False, add=None) -> tuple:
+    def _key_pointers(self, ksk, level, dst, owners):
+        """device arrays of the row-0 pointers of every partition's key halves at this level (cached per key)"""
+        ck = ("kptr", id(ksk.data), level, dst)
+        hit = self._ptr_cache.get(ck)
+        if hit is None or hit[0] is not ksk.data:
+            start = self.ntt.starts[level][dst]
+            p0, p1 = [], []
+            for sid in sorted(owners):
+                src, part_id, _alpha = owners[sid]
+                kd = ksk.data[self.parts_alloc[level][src][part_id]].data
+                p0.append(kd[0][dst][start:].data_ptr())
+                p1.append(kd[1][dst][start:].data_ptr())
+            stride = ksk.data[0].data[0][dst].stride(0)
+            hit = (ksk.data, self._t(p0, dst), self._t(p1, dst), stride)
+            self._ptr_cache[ck] = hit
+        return hit[1], hit[2], hit[3]
+
+    def create_switcher(self, a: list[torch.Tensor], ksk: data_struct, level, exit_ntt=False, add=None,
+                        fast=False) -> tuple:
         """ModUp -> NTT -> evk inner product -> iNTT -> ModDown (:746-904).
         add = (list_or_None, list_or_None): polynomials added to the two outputs and reduced to [0,q)
         (the tails of relinearize :1135-1140 and switch_key :947-948), fused into the ModDown kernel."""
@@ -551,14 +573,28 @@ class ckks_engine:
             E = pack[0].numel()
             acc0 = torch.empty((E, self.ctx.N), dtype=torch.int64, device=ntt.devices[dst])
             acc1 = torch.empty_like(acc0)
-            for n, sid in enumerate(sorted(owners)):
-                src, part_id, _alpha = owners[sid]
-                ext = self.extend(delivered[dst][sid], src, level, part_id, dst)
-                ntt.ntt([ext], level, dst, -2)
-                key_part = ksk.data[self.parts_alloc[level][src][part_id]].data
-                fused.ksk_accumulate(ext, key_part[0][dst][start:], key_part[1][dst][start:], acc0, acc1, n == 0, pack)
-            ntt.intt_exit_reduce([acc0], level, dst, -2)
-            ntt.intt_exit_reduce([acc1], level, dst, -2)
+            if fast:
+                # all partitions extended into one [parts*E, N] block, ONE batched canonical NTT, ONE inner-product pass
+                sids = sorted(owners)
+                ext_all = torch.empty((len(sids) * E, self.ctx.N), dtype=torch.int64, device=ntt.devices[dst])
+                for n, sid in enumerate(sids):
+                    src, part_id, _alpha = owners[sid]
+                    fused.extend(delivered[dst][sid], ntt.Rs[dst][start:], ntt.lenter(level, src, part_id, dst), pack,
+                                 out=ext_all[n * E:(n + 1) * E], canon=True)
+                ntt.ntt_fast(ext_all, level, dst, -2, batched=True)
+                k0p, k1p, kstride = self._key_pointers(ksk, level, dst, owners)
+                fused.ksk_inner(ext_all, len(sids), k0p, k1p, kstride, acc0, acc1, pack)
+                ntt.intt_fast(acc0, level, dst, -2)
+                ntt.intt_fast(acc1, level, dst, -2)
+            else:
+                for n, sid in enumerate(sorted(owners)):
+                    src, part_id, _alpha = owners[sid]
+                    ext = self.extend(delivered[dst][sid], src, level, part_id, dst)
+                    ntt.ntt([ext], level, dst, -2)
+                    key_part = ksk.data[self.parts_alloc[level][src][part_id]].data
+                    fused.ksk_accumulate(ext, key_part[0][dst][start:], key_part[1][dst][start:], acc0, acc1, n == 0, pack)
+                ntt.intt_exit_reduce([acc0], level, dst, -2)
+                ntt.intt_exit_reduce([acc1], level, dst, -2)
             Rs = ntt.Rs[dst][start:]
             PiR = self._moddown_table(level, dst)
             eff = torch.empty((K, self.ctx.N), dtype=torch.int64, device=ntt.devices[dst])
@@ -572,14 +608,15 @@ class ckks_engine:
         if ct.origin != types.origins["ct"]:
             raise errors.NotMatchType(origin=ct.origin, to=types.origins["ct"])
         level = ct.level
-        new0, d1 = self.create_switcher(ct.data[1], ksk, level, exit_ntt=ct.ntt_state, add=(ct.data[0], None))
+        new0, d1 = self.create_switcher(ct.data[1], ksk, level, exit_ntt=ct.ntt_state, add=(ct.data[0], None),
+                                        fast=self.fast)
         return self._ct((new0, d1), level, "ct", include_special=ct.include_special, ntt_state=ct.ntt_state,
                         montgomery_state=ct.montgomery_state)
 
     # -----------------------------------------------------------------------------------------------
     # multiplication (:967-1151)
     # -----------------------------------------------------------------------------------------------
-    def rescale(self, ct: data_struct, exact_rounding=True) -> data_struct:
+    def rescale(self, ct: data_struct, exact_rounding=True, _canon=False) -> data_struct:
         if ct.origin != types.origins["ct"]:
             raise errors.NotMatchType(origin=ct.origin, to=types.origins["ct"])
         level = ct.level
@@ -603,7 +640,7 @@ class ckks_engine:
                     continue
                 x = ct.data[c][dev][1:] if dev == src else ct.data[c][dev]
                 out[dev] = fused.rescale(x, r0[dev], self.rescale_scales[level][dev], round_at,
-                                         self.ntt.pack5(nxt, dev, -1))
+                                         self.ntt.pack5(nxt, dev, -1), canon=_canon)
             new.append(out)
         return self._ct((new[0], new[1]), nxt, "ct")
 
@@ -612,22 +649,28 @@ class ckks_engine:
             raise errors.NotMatchType(origin=a.origin, to=types.origins["sk"])
         if b.origin != types.origins["ct"]:
             raise errors.NotMatchType(origin=b.origin, to=types.origins["sk"])
-        x = self.rescale(a)
-        y = self.rescale(b)
+        fast = self.fast and relin
+        x = self.rescale(a, _canon=fast)
+        y = self.rescale(b, _canon=fast)
         level = x.level
         x0, x1 = x.data
         y0, y1 = y.data
         for t in (x0, x1, y0, y1):
-            self.ntt.enter_ntt(t, level)
+            if fast:
+                for dev, v in enumerate(t):
+                    if v is not None:
+                        self.ntt.ntt_fast(v, level, dev, -1, enter=True)
+            else:
+                self.ntt.enter_ntt(t, level)
         d0, d1, d2 = [None] * len(x0), [None] * len(x0), [None] * len(x0)
         for dev in range(len(x0)):
             if x0[dev] is not None:
                 d0[dev], d1[dev], d2[dev] = fused.tensor_product(x0[dev], x1[dev], y0[dev], y1[dev],
                                                                  self.ntt.pack5(level, dev, -1))
         ctt = self._ct((d0, d1, d2), level, "ctt", ntt_state=True, montgomery_state=True)
-        return self.relinearize(ct_triplet=ctt, evk=evk) if relin else ctt
+        return self.relinearize(ct_triplet=ctt, evk=evk, _fast=fast) if relin else ctt
 
-    def relinearize(self, ct_triplet: data_struct, evk: data_struct) -> data_struct:
+    def relinearize(self, ct_triplet: data_struct, evk: data_struct, _fast=False) -> data_struct:
         if ct_triplet.origin != types.origins["ctt"]:
             raise errors.NotMatchType(origin=ct_triplet.origin, to=types.origins["ctt"])
         if not ct_triplet.ntt_state or not ct_triplet.montgomery_state:
@@ -635,10 +678,14 @@ class ckks_engine:
         d0, d1, d2 = ct_triplet.data
         level = ct_triplet.level
         # the reference transforms the triplet in place (:1127-1129); so do we
-        self.ntt.intt_exit_reduce(d0, level)
-        self.ntt.intt_exit_reduce(d1, level)
-        self.ntt.intt_exit_reduce(d2, level)
-        c0, c1 = self.create_switcher(d2, evk, level, add=(d0, d1))
+        for d in (d0, d1, d2):
+            if _fast:   # only for triplets produced by the fused path (values known to lie in [0, 2q))
+                for dev, v in enumerate(d):
+                    if v is not None:
+                        self.ntt.intt_fast(v, level, dev, -1)
+            else:
+                self.ntt.intt_exit_reduce(d, level)
+        c0, c1 = self.create_switcher(d2, evk, level, add=(d0, d1), fast=self.fast)
         return self._ct((c0, c1), level, "ct")
 
     # -----------------------------------------------------------------------------------------------

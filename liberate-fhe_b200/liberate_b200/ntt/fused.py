@@ -13,14 +13,14 @@ from .._lib import lib, check
 from .ntt_cuda import _rows, _ptr, _stream, _Launch, _vec
 
 
-def rescale(x, r0, scale, round_at, mp):
+def rescale(x, r0, scale, round_at, mp, canon=False):
     """engine.py:1026-1038.  x: [C,N] surviving limbs, r0: [N] dropped limb -> new [C,N]"""
     xs = _rows(x, "rescale")
     out = torch.empty((x.size(0), x.size(1)), dtype=torch.int64, device=x.device)
     r0 = r0 if r0.is_contiguous() else r0.contiguous()
     with _Launch(x):
         check(lib.ckks_rescale(_ptr(x), xs, _ptr(r0), _ptr(out), out.size(1), x.size(0), x.size(1), _ptr(_vec(scale)),
-                               int(round_at), *[_ptr(_vec(t)) for t in mp], _stream(x)), "rescale")
+                               int(round_at), 1 if canon else 0, *[_ptr(_vec(t)) for t in mp], _stream(x)), "rescale")
     return out
 
 
@@ -52,7 +52,7 @@ def garner_digits(a_part, Y_scalar, Ltri, mp4, out=None):
     return out
 
 
-def extend(state, Rs, Lenter, mp, out=None):
+def extend(state, Rs, Lenter, mp, out=None, canon=False):
     """extend, engine.py:707-743.  state [alpha,N] -> [E,N] Montgomery form on the E target limbs"""
     s = _rows(state, "extend")
     alpha, N = state.shape
@@ -61,7 +61,7 @@ def extend(state, Rs, Lenter, mp, out=None):
         out = torch.empty((E, N), dtype=torch.int64, device=state.device)
     with _Launch(state):
         check(lib.ckks_extend(_ptr(state), s, alpha, _ptr(out), _rows(out, "extend"), E, N, _ptr(_vec(Rs)),
-                              _ptr(Lenter) if Lenter is not None else None,
+                              _ptr(Lenter) if Lenter is not None else None, 1 if canon else 0,
                               *[_ptr(_vec(t)) for t in mp], _stream(state)), "extend")
     return out
 
@@ -102,3 +102,46 @@ def automorphism(x, g, canon, _2q=None):
         check(lib.ckks_automorphism(_ptr(x), s, _ptr(out), N, C, N, int(g), 1 if canon else 0,
                                     _ptr(_vec(_2q)) if _2q is not None else None, _stream(x)), "automorphism")
     return out
+
+
+def fast_tables(plain, q):
+    """plain canonical twiddles [C,N] -> (shoup [C,N,2] as int64 {w, floor(w 2^64/q)}, dbl [C,N] float64)"""
+    C, N = plain.shape
+    sh = torch.empty((C, N, 2), dtype=torch.int64, device=plain.device)
+    dbl = torch.empty((C, N), dtype=torch.float64, device=plain.device)
+    with _Launch(plain):
+        check(lib.ckks_fast_tables(_ptr(plain), _ptr(_vec(q)), _ptr(sh), _ptr(dbl), C, N, _stream(plain)), "fast_tables")
+    return sh, dbl
+
+
+def ntt_fast(x, tw_u64, tw_f64, q, scal=None, scal_sh=None, period=None, force_int=False):
+    """canonical-output forward NTT in place: x [rows,N] in [0,2q) -> NTT(x * scal) in [0,q)"""
+    s = _rows(x, "ntt_fast")
+    rows, N = x.shape
+    logN = int(N).bit_length() - 1
+    with _Launch(x):
+        check(lib.ckks_ntt_fast(_ptr(x), s, rows, period or rows, logN, _ptr(tw_u64), _ptr(tw_f64), _ptr(_vec(q)),
+                                _ptr(scal) if scal is not None else None,
+                                _ptr(scal_sh) if scal_sh is not None else None, 1 if force_int else 0, _stream(x)),
+              "ntt_fast")
+
+
+def intt_fast(x, tw_u64, tw_f64, q, scal, scal_sh, centred=False, period=None, force_int=False):
+    """canonical-output inverse NTT in place: x [rows,N] in [0,2q) -> iNTT(x) * scal in [0,q) (or centred)"""
+    s = _rows(x, "intt_fast")
+    rows, N = x.shape
+    logN = int(N).bit_length() - 1
+    with _Launch(x):
+        check(lib.ckks_intt_fast(_ptr(x), s, rows, period or rows, logN, _ptr(tw_u64), _ptr(tw_f64), _ptr(_vec(q)),
+                                 _ptr(scal), _ptr(scal_sh), 1 if centred else 0, 1 if force_int else 0, _stream(x)),
+              "intt_fast")
+
+
+def ksk_inner(ext_all, parts, k0_ptrs, k1_ptrs, ksk_stride, acc0, acc1, mp):
+    """one-pass evaluation-key inner product over all partitions; ext_all: [parts*E, N]; k*_ptrs: int64 device
+    tensors holding `parts` raw row-0 pointers of the key halves"""
+    E, N = acc0.shape
+    with _Launch(ext_all):
+        check(lib.ckks_ksk_inner(_ptr(ext_all), _rows(ext_all, "ksk_inner"), parts, _ptr(k0_ptrs), _ptr(k1_ptrs),
+                                 ksk_stride, _ptr(acc0), _ptr(acc1), _rows(acc0, "ksk_inner"), E, N,
+                                 *[_ptr(_vec(t)) for t in mp], _stream(ext_all)), "ksk_inner")

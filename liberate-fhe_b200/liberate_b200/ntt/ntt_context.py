@@ -23,7 +23,7 @@ import numpy as np
 import torch
 
 from ..fhe.presets import errors
-from . import ntt_cuda
+from . import fused, ntt_cuda
 from .rns_partition import rns_partition
 
 
@@ -80,10 +80,27 @@ class ntt_context:
         self.Ninv = self.partition_variable([(ni * R) % q for ni, q in zip(c.N_inv, c.q)])
         self.mont_pack0 = [self.ql, self.qh, self.kl, self.kh]
         fwd, inv = c.psi_stage_factors()
-        self.psi = [self._grow_twiddles(d, fwd) if self.is_local(d) else None for d in range(self.num_devices)]
-        self.ipsi = [self._grow_twiddles(d, inv) if self.is_local(d) else None for d in range(self.num_devices)]
+        # plain-twiddle tables of the canonical-output fast transforms: ({w, floor(w 2^64/q)} [rows,N,2], double [rows,N])
+        self.tw_fast_fwd = [None] * self.num_devices
+        self.tw_fast_inv = [None] * self.num_devices
+        self.psi = [self._grow_twiddles(d, fwd, self.tw_fast_fwd) if self.is_local(d) else None
+                    for d in range(self.num_devices)]
+        self.ipsi = [self._grow_twiddles(d, inv, self.tw_fast_inv) if self.is_local(d) else None
+                     for d in range(self.num_devices)]
+        # per-limb plain scalars of the fast transforms with their Shoup companions (uint64 bit patterns)
+        Rinv = [pow(R, -1, q) for q in c.q]
+        self.fs_R = self._fast_scalar([R % q for q in c.q])                                   # "enter": x R
+        self.fs_exit = self._fast_scalar([ni * ri % q for ni, ri, q in zip(c.N_inv, Rinv, c.q)])  # x N^-1 R^-1
+        self.fs_ninv = self._fast_scalar(list(c.N_inv))                                        # x N^-1
 
-    def _grow_twiddles(self, dev, factors):
+    def _fast_scalar(self, values):
+        def pattern(v, q):
+            w = (v << 64) // q
+            return w - (1 << 64) if w >= (1 << 63) else w
+        sh = [pattern(v, q) for v, q in zip(values, self.ctx.q)]
+        return self.partition_variable(values), self.partition_variable(sh)
+
+    def _grow_twiddles(self, dev, factors, fast_store):
         """compact bit-reversed power table [limbs, N] in Montgomery form for device ``dev``.
         table[m + i] = table[i] * w^(N/2m), m = 2^s (see ckks_context.psi_stage_factors)."""
         c = self.ctx
@@ -110,6 +127,7 @@ class ntt_context:
         # canonical plain values, then the reference's own Montgomery entry (nctx.py:115-130)
         ntt_cuda.mont_redc([T], *mont)
         ntt_cuda.reduce_2q([T], [self._2q[dev]])
+        fast_store[dev] = fused.fast_tables(T, self.q[dev])
         ntt_cuda.mont_enter([T], [self.Rs[dev]], *mont)
         return T
 
@@ -202,6 +220,23 @@ class ntt_context:
         """(_2q, ql, qh, kl, kh) row slices of one device, for the fused single-device operators"""
         (_, a, b), = self.rows(lvl, dev, part)
         return [t[dev][a:b] for t in (self._2q, self.ql, self.qh, self.kl, self.kh)]
+
+    # ---------------------------------------------------------------------------------------------
+    # canonical-output fast transforms on one device's tensor (fused path; DESIGN.md section 6)
+    # ---------------------------------------------------------------------------------------------
+    def ntt_fast(self, x, lvl, dev, part=-1, enter=False, batched=False):
+        """x: [rows, N] (or [parts*rows, N] with batched=True) in [0,2q) -> canonical NTT(x [* R])"""
+        (_, a, b), = self.rows(lvl, dev, part)
+        sh, dbl = self.tw_fast_fwd[dev]
+        sc = (self.fs_R[0][dev][a:b], self.fs_R[1][dev][a:b]) if enter else (None, None)
+        fused.ntt_fast(x, sh[a:b], dbl[a:b], self.q[dev][a:b], sc[0], sc[1], period=(b - a) if batched else None)
+
+    def intt_fast(self, x, lvl, dev, part=-1, exit=True, centred=False):
+        """x: [rows, N] in [0,2q) -> canonical iNTT(x) * N^-1 [* R^-1]  (== intt_exit_reduce / intt + reduce)"""
+        (_, a, b), = self.rows(lvl, dev, part)
+        sh, dbl = self.tw_fast_inv[dev]
+        sc = self.fs_exit if exit else self.fs_ninv
+        fused.intt_fast(x, sh[a:b], dbl[a:b], self.q[dev][a:b], sc[0][dev][a:b], sc[1][dev][a:b], centred=centred)
 
     @staticmethod
     def _live(a):

@@ -37,5 +37,54 @@ def build(verbose=False):
     return so
 
 
+def build_engine(verbose=False):
+    """"installs" the whole reference package for the GPU-side comparison rows (bench.py --impl reference_gpu,
+    tests/test_gpu_vs_reference_engine.py): the four csprng extensions are compiled UNMODIFIED from
+    /root/reference/src/liberate/csprng, and the reference's Python files + prime tables are copied into
+    oracle/_ref/site/liberate -- the same thing ``pip install --target`` would do.  Everything stays under the
+    git-ignored oracle/_ref/; nothing of it enters the repository."""
+    import shutil
+    src_pkg = REF.parent
+    if not src_pkg.exists():
+        print("reference sources not present; nothing to install")
+        return None
+    site = OUT / "site"
+    pkg = site / "liberate"
+    if (pkg / ".complete").exists():
+        return site
+    build(verbose)
+    os.environ.setdefault("TORCH_CUDA_ARCH_LIST", "10.0")
+    os.environ.setdefault("MAX_JOBS", "4")
+    from torch.utils.cpp_extension import load
+    cs = src_pkg / "csprng"
+    exts = {"chacha20_cuda": ["chacha20.cpp", "chacha20_cuda_kernel.cu"],
+            "randint_cuda": ["randint.cpp", "randint_cuda_kernel.cu"],
+            "discrete_gaussian_cuda": ["discrete_gaussian.cpp", "discrete_gaussian_cuda_kernel.cu"],
+            "randround_cuda": ["randround.cpp", "randround_cuda_kernel.cu"]}
+    for name, srcs in exts.items():
+        bdir = OUT / f"build_{name}"
+        bdir.mkdir(exist_ok=True)
+        if not (bdir / f"{name}.so").exists():
+            load(name=name, sources=[str(cs / s) for s in srcs], extra_cuda_cflags=["-O3"],
+                 build_directory=str(bdir), is_python_module=False, verbose=verbose)
+    if pkg.exists():
+        shutil.rmtree(pkg)
+    shutil.copytree(src_pkg, pkg, ignore=shutil.ignore_patterns("*.cu", "*.cpp", "*.h", "__pycache__", "tests"))
+    for name in exts:
+        shutil.copy(OUT / f"build_{name}" / f"{name}.so", pkg / "csprng" / f"{name}.so")
+    shutil.copy(OUT / "ntt_cuda_ref.so", pkg / "ntt" / "ntt_cuda_ref.so")
+    # liberate/ntt/__init__.py does ``from . import ntt_cuda``: forward that name to the compiled module
+    (pkg / "ntt" / "ntt_cuda.py").write_text(
+        "import importlib.util, pathlib, sys\n"
+        "_p = pathlib.Path(__file__).with_name('ntt_cuda_ref.so')\n"
+        "_s = importlib.util.spec_from_file_location('ntt_cuda_ref', _p)\n"
+        "_m = importlib.util.module_from_spec(_s); _s.loader.exec_module(_m)\n"
+        "globals().update({k: getattr(_m, k) for k in dir(_m) if not k.startswith('_')})\n")
+    (pkg / ".complete").write_text("ok")
+    return site
+
+
 if __name__ == "__main__":
     print(build(verbose="-v" in sys.argv))
+    if "--engine" in sys.argv:
+        print(build_engine(verbose="-v" in sys.argv))

@@ -49,8 +49,21 @@ def run(logN, L, iters, pool_bytes=320 << 20):
     def inv(b):
         check(lib.ckks_intt(P(b), N, L, logN, P(tw), N, P(c["Rs"]), P(c["_2q"]), P(c["ql"]), P(c["qh"]), P(c["kl"]), P(c["kh"]), 2, st), "intt")
 
+    # canonical-output fast transforms (FP64 butterflies for q < 2^42, Shoup for the 60-bit primes)
+    twu = torch.randint(0, 1 << 40, (L, N, 2), dtype=torch.int64, device="cuda", generator=g)
+    twd = torch.randint(0, 1 << 40, (L, N), dtype=torch.int64, device="cuda", generator=g).double()
+    qd = torch.tensor(q, dtype=torch.int64, device="cuda")
+    sc = c["Rs"]
+
+    def ffwd(b, fi=0):
+        check(lib.ckks_ntt_fast(P(b), N, L, L, logN, P(twu), P(twd), P(qd), None, None, fi, st), "ntt_fast")
+
+    def finv(b, fi=0):
+        check(lib.ckks_intt_fast(P(b), N, L, L, logN, P(twu), P(twd), P(qd), P(sc), P(sc), 0, fi, st), "intt_fast")
+
     out = {}
-    for name, fn in (("fwd", fwd), ("inv_exit_reduce", inv)):
+    for name, fn in (("fwd", fwd), ("inv_exit_reduce", inv), ("fast_fwd", ffwd), ("fast_inv", finv),
+                     ("fast_fwd_int", lambda b: ffwd(b, 1)), ("fast_inv_int", lambda b: finv(b, 1))):
         for i in range(3):
             fn(bufs[i % nbuf])
         torch.cuda.synchronize()
@@ -69,10 +82,10 @@ if __name__ == "__main__":
     quick = "--quick" in sys.argv
     res = []
     for logN in ([16] if quick else [14, 15, 16, 17]):
-        for L in ([32] if quick else [1, 2, 4, 8, 16, 32, 60]):
+        for L in ([36] if quick else [1, 4, 16, 36, 60]):
             r = run(logN, L, iters=20 if quick else 50)
             res.append(dict(logN=logN, L=L, **r))
             print(logN, L, {k: (round(v["gbps"], 1), round(v["limb_ntt_us"], 3)) for k, v in r.items()}, flush=True)
     out = ROOT / "gpurun_out"
     out.mkdir(exist_ok=True)
-    (out / "ntt_sweep.json").write_text(json.dumps(dict(when=time.time(), results=res), indent=1))
+    (out / ("ntt_sweep_quick.json" if quick else "ntt_sweep.json")).write_text(json.dumps(dict(when=time.time(), results=res), indent=1))

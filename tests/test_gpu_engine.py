@@ -18,19 +18,22 @@ from seeded_rng import SeededCsprng
 pytestmark = pytest.mark.gpu
 
 
-def make_engine(D, params):
+def make_engine(D, params, fast=True):
     from liberate_b200 import fhe
-    eng = fhe.ckks_engine(devices=["cuda:0"] * D, **params)
+    eng = fhe.ckks_engine(devices=["cuda:0"] * D, fast=fast, **params)
     eng.rng = SeededCsprng(eng.ctx.N, [len(d) for d in eng.ntt.p.d], max(eng.ntt.num_special_primes, 2),
                            devices=eng.ntt.devices)
     return eng
 
 
+@pytest.mark.parametrize("fast", [True, False], ids=["fused-fast", "faithful"])
 @pytest.mark.parametrize("D", [1, 2, 3])
-def test_engine_reproduces_reference_tensors(D):
+def test_engine_reproduces_reference_tensors(D, fast):
+    """fast=True routes mult+relin / rotate through the canonical-output FP64 + Shoup transforms and the batched
+    key switch; fast=False through the lazy-representative-faithful kernels.  Both must hit the same digests."""
     g = json.loads((GOLDEN / f"engine_D{D}.json").read_text())
     full = np.load(GOLDEN / f"engine_D{D}_full.npz")
-    eng = make_engine(D, g["params"])
+    eng = make_engine(D, g["params"], fast)
     assert [int(x) for x in eng.ctx.q] == g["q"]
     chk = Checker(g["digests"], full, eng.ntt.devices)
     objs = flows.hot_path_flow(eng, chk)

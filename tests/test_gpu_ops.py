@@ -218,3 +218,58 @@ def test_fused_keyswitch_pieces_bit_exact(logN, alpha, K):
         ref2 = np.where(ref2 < qcol[:Lr], ref2, ref2 - qcol[:Lr])
         got = fused.automorphism(T(xin), g, True, t["_2q"][:Lr])
         assert eq(got, ref2), "automorphism+canon"
+
+
+@pytest.mark.parametrize("logN", [12, 13, 14, 15, 16, 17])
+@pytest.mark.parametrize("force_int", [False, True])
+def test_fast_transforms_equal_reference_sequences_after_reduction(logN, force_int):
+    """ckks_ntt_fast == {enter_ntt; reduce_2q}, ckks_intt_fast == intt_exit_reduce[_signed] (canonical outputs):
+    FP64 error-free butterflies for the scale primes, Shoup/Harvey for the 60-bit primes."""
+    from liberate_b200.ntt import fused
+    P = O.Params(primes_for(logN, 3, 2), logN)
+    t = packs(P)
+    C, N = len(P.q), P.N
+    rng = np.random.default_rng(300 + logN)
+    q = np.array(P.q, dtype=np.int64)
+    R = O.R
+    sh_f, dbl_f = fused.fast_tables(T(P.psi_plain), t["_2q"] // 2)
+    sh_i, dbl_i = fused.fast_tables(T(P.ipsi_plain), t["_2q"] // 2)
+    qd = T(q)
+
+    def shoup(s):
+        out = []
+        for v, m in zip(s, q):
+            w = (int(v) << 64) // int(m)
+            out.append(w - (1 << 64) if w >= (1 << 63) else w)   # uint64 bit pattern as int64
+        return np.array(out, dtype=np.int64)
+
+    # forward with enter (x R): input lazy [0, 2q)
+    a = rng.integers(0, 2 * q[:, None], (C, N), dtype=np.int64)
+    Rp = np.array([R % int(m) for m in q], dtype=np.int64)
+    x = T(a)
+    fused.ntt_fast(x, sh_f, dbl_f, qd, T(Rp), T(shoup(Rp)), force_int=force_int)
+    ref = a.copy()
+    O.C.enter_ntt(ref, P.Rs, P.psi, P._2q, *P.mont)
+    O.C.reduce_2q(ref, P._2q)
+    assert eq(x, ref), "ntt_fast(enter)"
+    # forward without scalar
+    x = T(a)
+    fused.ntt_fast(x, sh_f, dbl_f, qd, force_int=force_int)
+    ref2 = a.copy()
+    O.C.ntt(ref2, P.psi, P._2q, *P.mont)
+    O.C.reduce_2q(ref2, P._2q)
+    assert eq(x, ref2), "ntt_fast"
+    # inverse with the exit chain folded into one scalar: N^-1 R^-1
+    lazy = a.copy()
+    O.C.ntt(lazy, P.psi, P._2q, *P.mont)            # lazy NTT-domain input in [0, 2q)
+    ex = np.array([pow(N, -1, int(m)) * pow(R, -1, int(m)) % int(m) for m in q], dtype=np.int64)
+    for centred, mode in ((False, 2), (True, 3)):
+        y = T(lazy)
+        fused.intt_fast(y, sh_i, dbl_i, qd, T(ex), T(shoup(ex)), centred=centred, force_int=force_int)
+        r = lazy.copy()
+        O.C.intt(r, P.ipsi, P.Ninv, P._2q, *P.mont, exit_mode=mode)
+        assert eq(y, r), f"intt_fast centred={centred}"
+    # batched rows: 2 x C rows share the C limbs' constants (period = C)
+    big = T(np.concatenate([a, a]))
+    fused.ntt_fast(big, sh_f, dbl_f, qd, period=C, force_int=force_int)
+    assert eq(big[:C], ref2) and eq(big[C:], ref2), "batched period"
