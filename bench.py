@@ -235,9 +235,13 @@ def run_ours(args):
         barrier()
         return reduce_max(e0.elapsed_time(e1)) / steps, (lib.launches - n0) // steps, out
 
-    with ClockSampler(local_rank) as clk:
-        ms, launches, prod = timed(lambda: eng.mult(ct_a, ct_b, evk), args.steps, args.warmup)
-    clocks = clk.summary()
+    clk = ClockSampler(local_rank).__enter__()      # sampled across the whole measured part of the run
+    time.sleep(0.3)
+    if args.profile_range:
+        torch.cuda.profiler.start()
+    ms, launches, prod = timed(lambda: eng.mult(ct_a, ct_b, evk), args.steps, args.warmup)
+    if args.profile_range:
+        torch.cuda.profiler.stop()
 
     # correctness guard inside the bench: the product decrypts to ma*mb
     if rank == 0 and world == 1:
@@ -287,6 +291,8 @@ def run_ours(args):
 
     ms_ntt, _, _ = timed(ntt_call, 40, 5)
     achieved = 16.0 * E * N / (ms_ntt * 1e-3) / 1e9
+    clk.__exit__()
+    clocks = clk.summary()
 
     line = {
         "metric": METRIC, "value": 1e3 / ms, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -339,6 +345,7 @@ if __name__ == "__main__":
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference_gpu"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-range", action="store_true", help="cudaProfilerStart/Stop around the timed steps (ncu --profile-from-start off)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -152,6 +152,44 @@ int ckks_moddown(int64_t* d, int64_t d_stride, int L, int K, int N, const int64_
 int ckks_automorphism(const int64_t* in, int64_t in_stride, int64_t* out, int64_t out_stride, int C, int N,
                       int64_t g, int canon, const int64_t* _2q, void* stream);
 
+/* ---- level 3: fused executor -- one C call runs a whole stage of the hot path (all kernels on `stream`) -------
+ * ckks_level_t describes one (level, device): every pointer is a DEVICE pointer the caller keeps alive.
+ * Rows = the device's limbs live at this level: L ordinary rows then K special rows (E = L + K). */
+typedef struct {
+    int32_t logN, L, K, nparts, nlocal, _pad;
+    const int64_t *q, *_2q, *ql, *qh, *kl, *kh, *Rs;          /* [E] per-row constants                          */
+    const void* twf_u64; const double* twf_f64;               /* fast forward tables of the E rows              */
+    const void* twi_u64; const double* twi_f64;               /* fast inverse tables                            */
+    const int64_t *sR, *sR_sh, *sExit, *sExit_sh;             /* [E] plain scalars R and N^-1 R^-1 (+ Shoup)    */
+    const int64_t* PiR;                                       /* [K][E] ModDown table                           */
+    const int32_t* part_alpha;                                /* [nparts] rows of every partition (storage order) */
+    const int64_t* const* Lenter;                             /* [nparts] -> [(alpha-1)][E]                     */
+    const int32_t *loc_row0, *loc_alpha;                      /* [nlocal] partitions whose digits this device makes */
+    const int64_t* const* loc_Y; const int64_t* const* loc_Ltri;
+    const int64_t* rescale_scale; int64_t round_at;           /* rescale INTO this level: [L] multipliers       */
+} ckks_level_t;
+
+/* rescale x4 -> batched enter+NTT -> tensor product -> batched iNTT+exit -> Garner digits of d2
+ * (cc_mult + the first half of relinearize, engine.py:1072-1129, 654-705).  a0..b1: the rows that survive the rescale
+ * ([L][N], in_stride); r0*: the dropped limb of each polynomial ([N], on this device).  x: workspace [4][L][N];
+ * d: out [3][L][N] plain canonical d0,d1,d2; digits: out [L][N] (rows of the local partitions). */
+int ckks_exec_tensor_stage(const ckks_level_t* lv, const int64_t* a0, const int64_t* a1, const int64_t* b0,
+                           const int64_t* b1, int64_t in_stride, const int64_t* r0a0, const int64_t* r0a1,
+                           const int64_t* r0b0, const int64_t* r0b1, int64_t* x, int64_t* d, int64_t* digits,
+                           void* stream);
+/* Garner digits of the local partitions of a [L][N] polynomial (pre_extend for every partition, one launch) */
+int ckks_exec_digits(const ckks_level_t* lv, const int64_t* a, int64_t a_stride, int64_t* digits, int64_t d_stride,
+                     void* stream);
+/* extend (all partitions) -> batched NTT -> evk inner product -> batched iNTT+exit -> ModDown (+add, reduce)
+ * (create_switcher engine.py:812-904 + the relinearize / switch_key tails).  digit_ptrs: device [nparts] pointers to
+ * each partition's [alpha][N] digit block (rows digit_stride apart) -- local or received from a peer;
+ * ws: ckks_exec_keyswitch_ws_elems(...) int64 elements. */
+int ckks_exec_keyswitch_stage(const ckks_level_t* lv, const int64_t* const* digit_ptrs, int64_t digit_stride,
+                              const int64_t* const* k0_ptrs, const int64_t* const* k1_ptrs, int64_t ksk_stride,
+                              const int64_t* add0, const int64_t* add1, int64_t add_stride, int64_t* out0,
+                              int64_t* out1, int64_t out_stride, int64_t* ws, void* stream);
+int64_t ckks_exec_keyswitch_ws_elems(int L, int K, int nparts, int N);
+
 #ifdef __cplusplus
 }
 #endif

@@ -356,6 +356,71 @@ __global__ void k_automorphism(const int64_t* __restrict__ in, long long is, int
     out[i * os + dst] = v;
 }
 
+// all local partitions in one launch: grid (N/EW_THREADS, nlocal); partition p covers rows [row0[p], row0[p]+alpha[p])
+__global__ void k_garner_batched(const int64_t* __restrict__ a, long long as, int64_t* __restrict__ st, long long ss, int N,
+                                 const int32_t* __restrict__ row0, const int32_t* __restrict__ alphas,
+                                 const int64_t* const* __restrict__ Yp, const int64_t* const* __restrict__ Lp, MontPack m) {
+    const int p = blockIdx.y;
+    const int j = blockIdx.x * EW_THREADS + threadIdx.x;
+    if (j >= N) return;
+    const int r0 = row0[p], alpha = alphas[p];
+    const int64_t* __restrict__ Ysc = Yp[p];
+    const int64_t* __restrict__ Ltri = Lp[p];
+    int64_t s[MAX_ALPHA], av[MAX_ALPHA];
+#pragma unroll
+    for (int r = 0; r < MAX_ALPHA; ++r)
+        if (r < alpha) av[r] = a[(long long)(r0 + r) * as + j];
+#pragma unroll
+    for (int r = 0; r < MAX_ALPHA; ++r) s[r] = av[0];
+#pragma unroll
+    for (int i = 0; i < MAX_ALPHA - 1; ++i) {
+        if (i < alpha - 1) {
+            const LimbConst k = lc(m, r0 + i + 1);
+            const int64_t Y = mont_mul_ss(av[i + 1] - s[i + 1], Ysc[i], k.q4, k.k);
+            s[i + 1] = Y;
+#pragma unroll
+            for (int r = i + 2; r < MAX_ALPHA; ++r) {
+                if (r < alpha) {
+                    const LimbConst kr = lc(m, r0 + r);
+                    s[r] += mont_mul_ss(Y, Ltri[i * alpha + r], kr.q4, kr.k);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < MAX_ALPHA; ++r)
+        if (r < alpha) st[(long long)(r0 + r) * ss + j] = s[r];
+}
+
+// every partition extended to the E target rows in one launch: grid (N/2/EW_THREADS, nparts*E), canonicalised to [0,2q)
+__global__ void k_extend_batched(const int64_t* const* __restrict__ states, long long ss, const int32_t* __restrict__ alphas,
+                                 int64_t* __restrict__ out, long long os, int E, int N, const int64_t* __restrict__ Rs,
+                                 const int64_t* const* __restrict__ Lenters, MontPack m) {
+    const int row = blockIdx.y;
+    const int p = row / E, t = row - p * E;
+    const int j = 2 * (blockIdx.x * EW_THREADS + threadIdx.x);
+    if (j >= N) return;
+    const LimbConst k = lc(m, t);
+    const int64_t q2 = (int64_t)k.q2;
+    const int64_t* __restrict__ st = states[p];
+    const int64_t* __restrict__ Lenter = Lenters[p];
+    const int alpha = alphas[p];
+    longlong2 v = ld2(st + j);
+    const int64_t rs = Rs[t];
+    longlong2 acc;
+    acc.x = mont_mul_ss(v.x, rs, k.q4, k.k);
+    acc.y = mont_mul_ss(v.y, rs, k.q4, k.k);
+    for (int i = 0; i < alpha - 1; ++i) {
+        v = ld2(st + (long long)(i + 1) * ss + j);
+        const int64_t le = Lenter[(long long)i * E + t];
+        acc.x = lazy_add(acc.x, mont_mul_ss(v.x, le, k.q4, k.k), q2);
+        acc.y = lazy_add(acc.y, mont_mul_ss(v.y, le, k.q4, k.k), q2);
+    }
+    acc.x += (acc.x < 0) ? q2 : 0;
+    acc.y += (acc.y < 0) ? q2 : 0;
+    st2(out + (long long)row * os + j, acc);
+}
+
 inline dim3 ew_grid(int N, int C) { return dim3((N / 2 + EW_THREADS - 1) / EW_THREADS, C); }
 inline dim3 col_grid(int N) { return dim3((N + EW_THREADS - 1) / EW_THREADS); }
 
@@ -664,6 +729,72 @@ int ckks_moddown(int64_t* d, int64_t ds, int L, int K, int N, const int64_t* Rs,
     if (rc) return rc;
     k_moddown_ordinary<<<ew_grid(N, L), EW_THREADS, 0, S(stream)>>>(d, ds, L, K, N, Rs, PiR, eff, add, adds, out, os, m);
     return launch_status();
+}
+
+// ---- level 3: the fused executor (one C call = a whole stage of the hot path) ------------------------------
+#define RC(x)              \
+    do {                   \
+        int _rc = (x);     \
+        if (_rc) return _rc; \
+    } while (0)
+
+int ckks_exec_digits(const ckks_level_t* lv, const int64_t* a, int64_t as, int64_t* digits, int64_t ds, void* stream) {
+    CHECK_PTRS(lv, a, digits);
+    if (lv->nlocal <= 0) return 0;
+    const int N = 1 << lv->logN;
+    k_garner_batched<<<dim3((N + EW_THREADS - 1) / EW_THREADS, lv->nlocal), EW_THREADS, 0, S(stream)>>>(
+        a, as, digits, ds, N, lv->loc_row0, lv->loc_alpha, lv->loc_Y, lv->loc_Ltri,
+        MontPack{nullptr, lv->ql, lv->qh, lv->kl, lv->kh});
+    return launch_status();
+}
+
+int ckks_exec_tensor_stage(const ckks_level_t* lv, const int64_t* a0, const int64_t* a1, const int64_t* b0,
+                           const int64_t* b1, int64_t in_stride, const int64_t* r0a0, const int64_t* r0a1,
+                           const int64_t* r0b0, const int64_t* r0b1, int64_t* x, int64_t* d, int64_t* digits,
+                           void* stream) {
+    CHECK_PTRS(lv, a0, a1, b0, b1, r0a0, r0a1, r0b0, r0b1, x, d, digits);
+    const int L = lv->L, N = 1 << lv->logN;
+    const long long LN = (long long)L * N;
+    const int64_t* in[4] = {a0, a1, b0, b1};
+    const int64_t* r0[4] = {r0a0, r0a1, r0b0, r0b1};
+    for (int c = 0; c < 4; ++c)
+        RC(ckks_rescale(in[c], in_stride, r0[c], x + c * LN, N, L, N, lv->rescale_scale, lv->round_at, 1, lv->_2q, lv->ql,
+                        lv->qh, lv->kl, lv->kh, stream));
+    RC(ckks_ntt_fast(x, N, 4 * L, L, lv->logN, lv->twf_u64, lv->twf_f64, lv->q, lv->sR, (const uint64_t*)lv->sR_sh, 0, stream));
+    RC(ckks_tensor_product(x, x + LN, x + 2 * LN, x + 3 * LN, N, d, d + LN, d + 2 * LN, N, L, N, lv->_2q, lv->ql, lv->qh,
+                           lv->kl, lv->kh, stream));
+    RC(ckks_intt_fast(d, N, 3 * L, L, lv->logN, lv->twi_u64, lv->twi_f64, lv->q, lv->sExit, (const uint64_t*)lv->sExit_sh, 0, 0,
+                      stream));
+    return ckks_exec_digits(lv, d + 2 * LN, N, digits, N, stream);
+}
+
+int ckks_exec_keyswitch_stage(const ckks_level_t* lv, const int64_t* const* digit_ptrs, int64_t digit_stride,
+                              const int64_t* const* k0_ptrs, const int64_t* const* k1_ptrs, int64_t ksk_stride,
+                              const int64_t* add0, const int64_t* add1, int64_t add_stride, int64_t* out0,
+                              int64_t* out1, int64_t out_stride, int64_t* ws, void* stream) {
+    CHECK_PTRS(lv, digit_ptrs, k0_ptrs, k1_ptrs, out0, out1, ws);
+    const int L = lv->L, K = lv->K, E = L + K, P = lv->nparts, N = 1 << lv->logN;
+    int64_t* ext = ws;                                  // [P*E][N]
+    int64_t* acc = ext + (long long)P * E * N;          // [2E][N]
+    int64_t* eff = acc + 2ll * E * N;                   // [K][N]
+    const MontPack m{lv->_2q, lv->ql, lv->qh, lv->kl, lv->kh};
+    k_extend_batched<<<ew_grid(N, P * E), EW_THREADS, 0, S(stream)>>>(digit_ptrs, digit_stride, lv->part_alpha, ext, N, E, N,
+                                                                      lv->Rs, lv->Lenter, m);
+    RC(launch_status());
+    RC(ckks_ntt_fast(ext, N, P * E, E, lv->logN, lv->twf_u64, lv->twf_f64, lv->q, nullptr, nullptr, 0, stream));
+    RC(ckks_ksk_inner(ext, N, P, k0_ptrs, k1_ptrs, ksk_stride, acc, acc + (long long)E * N, N, E, N, lv->_2q, lv->ql, lv->qh,
+                      lv->kl, lv->kh, stream));
+    RC(ckks_intt_fast(acc, N, 2 * E, E, lv->logN, lv->twi_u64, lv->twi_f64, lv->q, lv->sExit, (const uint64_t*)lv->sExit_sh, 0, 0,
+                      stream));
+    RC(ckks_moddown(acc, N, L, K, N, lv->Rs, lv->PiR, add0, add_stride, out0, out_stride, eff, lv->_2q, lv->ql, lv->qh,
+                    lv->kl, lv->kh, stream));
+    return ckks_moddown(acc + (long long)E * N, N, L, K, N, lv->Rs, lv->PiR, add1, add_stride, out1, out_stride, eff, lv->_2q,
+                        lv->ql, lv->qh, lv->kl, lv->kh, stream);
+}
+
+int64_t ckks_exec_keyswitch_ws_elems(int L, int K, int nparts, int N) {
+    const long long E = L + K;
+    return ((long long)nparts * E + 2 * E + K) * N;
 }
 
 int ckks_automorphism(const int64_t* in, int64_t is, int64_t* out, int64_t os, int C, int N, int64_t g, int canon,

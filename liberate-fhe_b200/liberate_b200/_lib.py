@@ -46,7 +46,12 @@ SIGNATURES = {
     "ckks_moddown": [_i64p, _i64, _int, _int, _int, _i64p, _i64p, _i64p, _i64, _i64p, _i64, _i64p,
                      _i64p, _i64p, _i64p, _i64p, _i64p, _vp],
     "ckks_automorphism": [_i64p, _i64, _i64p, _i64, _int, _int, _i64, _int, _i64p, _vp],
+    "ckks_exec_tensor_stage": [_vp, _i64p, _i64p, _i64p, _i64p, _i64, _i64p, _i64p, _i64p, _i64p, _i64p, _i64p, _i64p, _vp],
+    "ckks_exec_digits": [_vp, _i64p, _i64, _i64p, _i64, _vp],
+    "ckks_exec_keyswitch_stage": [_vp, _vp, _i64, _vp, _vp, _i64, _i64p, _i64p, _i64, _i64p, _i64p, _i64, _i64p, _vp],
+    "ckks_exec_keyswitch_ws_elems": [_int, _int, _int, _int],
 }
+RESTYPES = {"ckks_exec_keyswitch_ws_elems": ctypes.c_int64}
 
 ERRORS = {-1: "CKKS_E_BADARG (null pointer / bad size)", -2: "CKKS_E_LOGN (logN outside [12,17])",
           -3: "CKKS_E_ALIGN (pointer/stride not 16-byte aligned)"}
@@ -71,13 +76,14 @@ def _load():
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError here = header/library mismatch: fail loudly
         fn.argtypes = argtypes
-        fn.restype = ctypes.c_int
+        fn.restype = RESTYPES.get(name, ctypes.c_int)
     return lib
 
 
 # kernels launched per entry point (for bench.py's gpu_launches accounting)
 KERNELS_PER_CALL = {"ckks_abi_version": 0, "ckks_ntt": 2, "ckks_intt": 2, "ckks_moddown": 2, "ckks_ntt_fast": 2,
-                    "ckks_intt_fast": 2}
+                    "ckks_intt_fast": 2, "ckks_exec_tensor_stage": 10, "ckks_exec_keyswitch_stage": 10,
+                    "ckks_exec_keyswitch_ws_elems": 0}
 
 
 class _Counted:

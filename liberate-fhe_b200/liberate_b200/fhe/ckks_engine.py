@@ -34,6 +34,7 @@ import torch
 from ..csprng import Csprng
 from ..ntt import fused, ntt_cuda
 from ..ntt.ntt_context import ntt_context
+from . import executor
 from .comm import DistComm, LocalComm
 from .context.ckks_context import ckks_context
 from .data_struct import data_struct
@@ -53,6 +54,7 @@ class ckks_engine:
         # fast=True: mult(relin=True) / rotate use the canonical-output transforms (FP64 + Shoup butterflies);
         # results are bit-identical either way, only invisible intermediate representatives differ
         self.fast = fast
+        self.use_executor = True     # fast path through the C executor (False: same kernels, Python orchestration)
         self.bias_guard = bias_guard
         self.norm = norm
         self.version = VERSION
@@ -171,10 +173,70 @@ class ckks_engine:
             self.PiRs.append(per_p)
         self._PiR_dense = {}
         self._ptr_cache = {}
+        self._plans = {}
+        self._ws = {}
 
         P = math.prod(c.q[-K:])
         self.mont_PR = [self._t([P * c.R % c.q[i] for i in p.destination_arrays[0][dev]], dev) if self._local(dev) else None
                         for dev in range(self.ntt.num_devices)]
+
+    def _workspace(self, dev):
+        ws = self._ws.get(dev)
+        if ws is None:
+            ws = self._ws[dev] = executor.Workspace(self.ntt.devices[dev])
+        return ws
+
+    def _plan(self, level, dev):
+        plan = self._plans.get((level, dev))
+        if plan is None:
+            plan = self._plans[(level, dev)] = executor.LevelPlan(self, level, dev)
+        return plan
+
+    def _deliver_digits(self, plans, level):
+        """every local destination device gets a {sid: [alpha,N] block} map with CONSTANT addresses:
+        own partitions in place, peers' partitions in persistent receive buffers (LocalComm: GPU->GPU copy;
+        DistComm: ONE all_gather into a persistent buffer)."""
+        N = self.ctx.N
+        out = {}
+        if isinstance(self.comm, LocalComm):
+            for dst, plan in plans.items():
+                blocks = {}
+                for sid in plan.sids:
+                    src, _pid, alpha = plan.owners[sid]
+                    state = plans[src].local_state(sid)
+                    if src == dst or self.ntt.devices[src] == self.ntt.devices[dst]:
+                        blocks[sid] = state
+                    else:
+                        buf = plan.peer.get(sid)
+                        if buf is None:
+                            buf = plan.peer[sid] = torch.empty((alpha, N), dtype=torch.int64, device=self.ntt.devices[dst])
+                        buf.copy_(state, non_blocking=True)
+                        blocks[sid] = buf
+                out[dst] = blocks
+            return out
+        (dst, plan), = plans.items()
+        world = self.comm.world
+        rows_of = [0] * world
+        for sid in plan.sids:
+            rows_of[plan.owners[sid][0]] += plan.owners[sid][2]
+        width = max(max(rows_of), 1)
+        if "gather" not in plan.peer:
+            plan.peer["mine"] = torch.zeros((width, N), dtype=torch.int64, device=self.ntt.devices[dst])
+            plan.peer["gather"] = torch.empty((world, width, N), dtype=torch.int64, device=self.ntt.devices[dst])
+        mine, gathered = plan.peer["mine"], plan.peer["gather"]
+        r = 0
+        for sid in plan.local_sids:
+            st = plan.local_state(sid)
+            mine[r:r + st.size(0)].copy_(st)
+            r += st.size(0)
+        self.comm.dist.all_gather_into_tensor(gathered.view(-1, N), mine, group=self.comm.group)
+        cursor = [0] * world
+        blocks = {}
+        for sid in plan.sids:
+            src, _pid, alpha = plan.owners[sid]
+            blocks[sid] = gathered[src, cursor[src]:cursor[src] + alpha]
+            cursor[src] += alpha
+        return {dst: blocks}
 
     def _moddown_table(self, level, dev):
         """[K, E] row-major table of P_j^-1 * R for the rows of `dev` live at `level` (zero where a row is dead)"""
@@ -555,6 +617,8 @@ class ckks_engine:
         """ModUp -> NTT -> evk inner product -> iNTT -> ModDown (:746-904).
         add = (list_or_None, list_or_None): polynomials added to the two outputs and reduced to [0,q)
         (the tails of relinearize :1135-1140 and switch_key :947-948), fused into the ModDown kernel."""
+        if fast and self.use_executor and not exit_ntt:
+            return self._keyswitch_fused(a, ksk, level, add)
         ntt, K = self.ntt, self.ntt.num_special_primes
         n_dev = self.len_devices[level]
         owners = self._part_owners(level)
@@ -604,6 +668,55 @@ class ckks_engine:
             out1[dst] = fused.moddown(acc1, E - K, K, Rs, PiR, pack, add=add1, eff=eff)
         return out0, out1
 
+    def _keyswitch_fused(self, a, ksk, level, add=None):
+        """create_switcher through the C executor: digits (1 launch) -> exchange -> one keyswitch stage call"""
+        n_dev = self.len_devices[level]
+        plans = {d: self._plan(level, d) for d in range(n_dev) if self._local(d)}
+        for d, plan in plans.items():
+            executor.digits_stage(plan, a[d])
+        blocks = self._deliver_digits(plans, level)
+        out0, out1 = [None] * n_dev, [None] * n_dev
+        for d, plan in plans.items():
+            dev = self.ntt.devices[d]
+            out0[d] = torch.empty((plan.L, plan.N), dtype=torch.int64, device=dev)
+            out1[d] = torch.empty((plan.L, plan.N), dtype=torch.int64, device=dev)
+            k0p, k1p, ks = plan.key_pointer_tables(self, ksk)
+            add0 = add[0][d] if add is not None and add[0] is not None else None
+            add1 = add[1][d] if add is not None and add[1] is not None else None
+            executor.keyswitch_stage(plan, plan.digit_pointer_table(blocks[d]), k0p, k1p, ks, add0, add1, out0[d], out1[d])
+        return out0, out1
+
+    def _mult_fused(self, a, b, evk):
+        """cc_mult + relinearize through the C executor: 2 calls per device instead of ~50 operator calls"""
+        level = a.level
+        nxt = level + 1
+        if nxt >= self.num_levels:
+            raise errors.MaximumLevelError(level=level, level_max=self.num_levels)
+        src = self.ntt.p.rescaler_loc[level]
+        n_before, n_after = self.len_devices[level], self.len_devices[nxt]
+        polys = (a.data[0], a.data[1], b.data[0], b.data[1])
+        r0 = []
+        for poly in polys:
+            if isinstance(self.comm, LocalComm):
+                r0.append(self.comm.bcast(poly[src][0], src, range(n_before)))
+            else:
+                r0.append(self.comm.bcast(poly[src][0] if self._local(src) else None, src, range(n_before),
+                                          shape=(self.ctx.N,)))
+        plans = {d: self._plan(nxt, d) for d in range(n_after) if self._local(d)}
+        for d, plan in plans.items():
+            rows = [p[d][1:] if d == src else p[d] for p in polys]
+            executor.tensor_stage(plan, rows, [r[d] for r in r0])
+        blocks = self._deliver_digits(plans, nxt)
+        out0, out1 = [None] * n_after, [None] * n_after
+        for d, plan in plans.items():
+            dev = self.ntt.devices[d]
+            out0[d] = torch.empty((plan.L, plan.N), dtype=torch.int64, device=dev)
+            out1[d] = torch.empty((plan.L, plan.N), dtype=torch.int64, device=dev)
+            k0p, k1p, ks = plan.key_pointer_tables(self, evk)
+            executor.keyswitch_stage(plan, plan.digit_pointer_table(blocks[d]), k0p, k1p, ks, plan.d[0], plan.d[1],
+                                     out0[d], out1[d])
+        return self._ct((out0, out1), nxt, "ct")
+
     def switch_key(self, ct: data_struct, ksk: data_struct) -> data_struct:
         if ct.origin != types.origins["ct"]:
             raise errors.NotMatchType(origin=ct.origin, to=types.origins["ct"])
@@ -650,6 +763,8 @@ class ckks_engine:
         if b.origin != types.origins["ct"]:
             raise errors.NotMatchType(origin=b.origin, to=types.origins["sk"])
         fast = self.fast and relin
+        if fast and self.use_executor:
+            return self._mult_fused(a, b, evk)
         x = self.rescale(a, _canon=fast)
         y = self.rescale(b, _canon=fast)
         level = x.level

@@ -1,0 +1,167 @@
+"""
+executor -- host side of the level-3 C ABI (include/ckks_b200.h: ckks_exec_tensor_stage / ckks_exec_digits /
+ckks_exec_keyswitch_stage).  One ctypes call launches a whole stage of the hot path (10-12 kernels), so the Python
+cost of a ct x ct multiplication drops from ~50 operator calls to 2.
+
+A ``LevelPlan`` is the (level, device) descriptor the C side reads: row constants, fast-transform tables, Garner /
+ModDown tables, partition bookkeeping -- all device pointers into tensors owned by ntt_context / the engine, plus
+PERSISTENT workspaces (so that every pointer the kernels see is constant from call to call: nothing is allocated
+and no pointer table is uploaded on the hot path).
+"""
+import ctypes
+
+import torch
+
+from .._lib import check, lib
+
+_vp = ctypes.c_void_p
+
+
+class LevelT(ctypes.Structure):
+    _fields_ = [("logN", ctypes.c_int32), ("L", ctypes.c_int32), ("K", ctypes.c_int32), ("nparts", ctypes.c_int32),
+                ("nlocal", ctypes.c_int32), ("_pad", ctypes.c_int32),
+                ("q", _vp), ("_2q", _vp), ("ql", _vp), ("qh", _vp), ("kl", _vp), ("kh", _vp), ("Rs", _vp),
+                ("twf_u64", _vp), ("twf_f64", _vp), ("twi_u64", _vp), ("twi_f64", _vp),
+                ("sR", _vp), ("sR_sh", _vp), ("sExit", _vp), ("sExit_sh", _vp),
+                ("PiR", _vp), ("part_alpha", _vp), ("Lenter", _vp),
+                ("loc_row0", _vp), ("loc_alpha", _vp), ("loc_Y", _vp), ("loc_Ltri", _vp),
+                ("rescale_scale", _vp), ("round_at", ctypes.c_int64)]
+
+
+def _p(t):
+    return t.data_ptr() if t is not None else None
+
+
+class Workspace:
+    """per-device scratch, sized once for the largest level in use and then sliced (constant addresses)"""
+
+    def __init__(self, device):
+        self.device = device
+        self.buf = {}
+
+    def get(self, name, elems):
+        t = self.buf.get(name)
+        if t is None or t.numel() < elems:
+            t = torch.empty(elems, dtype=torch.int64, device=self.device)
+            self.buf[name] = t
+        return t[:elems]
+
+
+class LevelPlan:
+    def __init__(self, eng, level, dev):
+        ntt = eng.ntt
+        self.level, self.dev = level, dev
+        device = ntt.devices[dev]
+        N = eng.ctx.N
+        K = ntt.num_special_primes
+        (_, a, b), = ntt.rows(level, dev, -2)
+        E = b - a
+        self.L, self.K, self.E, self.N = E - K, K, E, N
+        keep = []                      # tensors the descriptor points into
+
+        def hold(t):
+            keep.append(t)
+            return t
+
+        owners = eng._part_owners(level)
+        self.sids = sorted(owners)
+        self.owners = owners
+        i32 = lambda v: hold(torch.tensor(v, dtype=torch.int32, device=device))
+        i64 = lambda v: hold(torch.tensor(v, dtype=torch.int64, device=device))
+        part_alpha = i32([owners[s][2] for s in self.sids])
+        lenter = [ntt.lenter(level, owners[s][0], owners[s][1], dev) for s in self.sids]
+        keep.extend(t for t in lenter if t is not None)
+        lenter_ptrs = i64([_p(t) or 0 for t in lenter])
+        local = [(s, owners[s]) for s in self.sids if owners[s][0] == dev]
+        self.local_sids = [s for s, _ in local]
+        g = [ntt.garner(level, dev, o[1]) for _, o in local]
+        self.loc_row0 = [ntt.p.parts[level][dev][o[1]][0] for _, o in local]
+        self.loc_alpha = [o[2] for _, o in local]
+        loc_row0 = i32(self.loc_row0 or [0])
+        loc_alpha = i32(self.loc_alpha or [0])
+        loc_Y = i64([_p(x["Y_scalar"]) or 0 for x in g] or [0])
+        loc_L = i64([_p(x["Ltri"]) or 0 for x in g] or [0])
+
+        sh_f, dbl_f = ntt.tw_fast_fwd[dev]
+        sh_i, dbl_i = ntt.tw_fast_inv[dev]
+        sl = slice(a, b)
+        T = lambda t: hold(t[dev][sl])
+        d = LevelT()
+        d.logN, d.L, d.K, d.nparts, d.nlocal = eng.ctx.logN, self.L, K, len(self.sids), len(local)
+        d.q, d._2q, d.ql, d.qh, d.kl, d.kh, d.Rs = (_p(T(x)) for x in (ntt.q, ntt._2q, ntt.ql, ntt.qh, ntt.kl, ntt.kh, ntt.Rs))
+        d.twf_u64, d.twf_f64 = _p(hold(sh_f[sl])), _p(hold(dbl_f[sl]))
+        d.twi_u64, d.twi_f64 = _p(hold(sh_i[sl])), _p(hold(dbl_i[sl]))
+        d.sR, d.sR_sh = _p(T(ntt.fs_R[0])), _p(T(ntt.fs_R[1]))
+        d.sExit, d.sExit_sh = _p(T(ntt.fs_exit[0])), _p(T(ntt.fs_exit[1]))
+        d.PiR = _p(hold(eng._moddown_table(level, dev)))
+        d.part_alpha, d.Lenter = _p(part_alpha), _p(lenter_ptrs)
+        d.loc_row0, d.loc_alpha, d.loc_Y, d.loc_Ltri = _p(loc_row0), _p(loc_alpha), _p(loc_Y), _p(loc_L)
+        if level > 0 and dev < len(eng.rescale_scales[level - 1]):
+            d.rescale_scale = _p(hold(eng.rescale_scales[level - 1][dev]))
+            src = ntt.p.rescaler_loc[level - 1]
+            d.round_at = eng.ctx.q[ntt.p.destination_arrays[level - 1][src][0]] // 2
+        self.desc = d
+        self.ref = ctypes.byref(d)
+        self._keep = keep
+
+        # persistent buffers (constant addresses): tensor-stage scratch, digits, key-switch scratch
+        ws = eng._workspace(dev)
+        L = self.L
+        self.x = ws.get("x", 4 * L * N).view(4, L, N)
+        self.d = ws.get("d", 3 * L * N).view(3, L, N)
+        self.digits = ws.get("digits", max(L, 1) * N).view(max(L, 1), N)
+        self.ks_ws = ws.get("ks", int(lib.ckks_exec_keyswitch_ws_elems(L, K, len(self.sids), N)))
+        self.peer = {}                 # sid -> persistent copy of a remote partition's digits on this device
+        self._digit_ptrs = None
+        self._key_ptrs = {}
+
+    def local_state(self, sid):
+        i = self.local_sids.index(sid)
+        r0, al = self.loc_row0[i], self.loc_alpha[i]
+        return self.digits[r0:r0 + al]
+
+    def digit_pointer_table(self, blocks):
+        """blocks: {sid: [alpha,N] tensor with CONSTANT address}; uploaded once"""
+        if self._digit_ptrs is None:
+            self._digit_ptrs = torch.tensor([blocks[s].data_ptr() for s in self.sids], dtype=torch.int64,
+                                            device=self.x.device)
+            self._blocks = blocks
+        return self._digit_ptrs
+
+    def key_pointer_tables(self, eng, ksk):
+        hit = self._key_ptrs.get(id(ksk.data))
+        if hit is None or hit[0] is not ksk.data:
+            start = eng.ntt.starts[self.level][self.dev]
+            p0, p1 = [], []
+            for s in self.sids:
+                src, part_id, _alpha = self.owners[s]
+                kd = ksk.data[eng.parts_alloc[self.level][src][part_id]].data
+                p0.append(kd[0][self.dev][start:].data_ptr())
+                p1.append(kd[1][self.dev][start:].data_ptr())
+            dev = self.x.device
+            hit = (ksk.data, torch.tensor(p0, dtype=torch.int64, device=dev),
+                   torch.tensor(p1, dtype=torch.int64, device=dev), ksk.data[0].data[0][self.dev].stride(0))
+            self._key_ptrs[id(ksk.data)] = hit
+        return hit[1], hit[2], hit[3]
+
+
+def _stream(t):
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def tensor_stage(plan, polys, r0s):
+    """polys: 4 tensors [L,N] (rows surviving the rescale, common row stride); r0s: 4 tensors [N] on this device"""
+    s = polys[0].stride(0)
+    check(lib.ckks_exec_tensor_stage(plan.ref, *[_p(t) for t in polys], s, *[_p(t) for t in r0s], _p(plan.x), _p(plan.d),
+                                     _p(plan.digits), _stream(plan.x)), "exec_tensor_stage")
+
+
+def digits_stage(plan, a):
+    check(lib.ckks_exec_digits(plan.ref, _p(a), a.stride(0), _p(plan.digits), plan.N, _stream(a)), "exec_digits")
+
+
+def keyswitch_stage(plan, digit_ptrs, k0p, k1p, kstride, add0, add1, out0, out1):
+    add = add0 if add0 is not None else add1
+    check(lib.ckks_exec_keyswitch_stage(plan.ref, _p(digit_ptrs), plan.N, _p(k0p), _p(k1p), kstride, _p(add0), _p(add1),
+                                        add.stride(0) if add is not None else 0, _p(out0), _p(out1), plan.N,
+                                        _p(plan.ks_ws), _stream(out0)), "exec_keyswitch_stage")

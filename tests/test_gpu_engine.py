@@ -18,22 +18,24 @@ from seeded_rng import SeededCsprng
 pytestmark = pytest.mark.gpu
 
 
-def make_engine(D, params, fast=True):
+def make_engine(D, params, mode="executor"):
     from liberate_b200 import fhe
-    eng = fhe.ckks_engine(devices=["cuda:0"] * D, fast=fast, **params)
+    eng = fhe.ckks_engine(devices=["cuda:0"] * D, fast=(mode != "faithful"), **params)
+    eng.use_executor = (mode == "executor")
     eng.rng = SeededCsprng(eng.ctx.N, [len(d) for d in eng.ntt.p.d], max(eng.ntt.num_special_primes, 2),
                            devices=eng.ntt.devices)
     return eng
 
 
-@pytest.mark.parametrize("fast", [True, False], ids=["fused-fast", "faithful"])
+@pytest.mark.parametrize("mode", ["executor", "fast-python", "faithful"])
 @pytest.mark.parametrize("D", [1, 2, 3])
-def test_engine_reproduces_reference_tensors(D, fast):
-    """fast=True routes mult+relin / rotate through the canonical-output FP64 + Shoup transforms and the batched
-    key switch; fast=False through the lazy-representative-faithful kernels.  Both must hit the same digests."""
+def test_engine_reproduces_reference_tensors(D, mode):
+    """executor: mult+relin / rotate through the C executor (canonical-output FP64 + Shoup transforms, batched key
+    switch, 2 C calls per mult); fast-python: the same kernels orchestrated from Python; faithful: the
+    lazy-representative-faithful kernels.  All three must hit the same digests."""
     g = json.loads((GOLDEN / f"engine_D{D}.json").read_text())
     full = np.load(GOLDEN / f"engine_D{D}_full.npz")
-    eng = make_engine(D, g["params"], fast)
+    eng = make_engine(D, g["params"], mode)
     assert [int(x) for x in eng.ctx.q] == g["q"]
     chk = Checker(g["digests"], full, eng.ntt.devices)
     objs = flows.hot_path_flow(eng, chk)
