@@ -272,25 +272,23 @@ def run_ours(args):
     ms_e2e, _, _ = timed(e2e_step, max(3, args.steps // 2), 3)
 
     # ---- roofline of the dominant kernel pair: the key switch's batched forward NTT ----------------------
+    # (fast_fwd_colpass + fast_fwd_blockpass over all partitions' extended limbs: [parts*E, N] rows per launch)
     peak, peak_kind = measured_peak()
     d0 = eng.local_ids[0]
     level = 1
-    pack = eng.ntt.pack5(level, d0, -2)
-    E, N, logN = pack[0].numel(), eng.ctx.N, eng.ctx.logN
-    start = eng.ntt.starts[level][d0]
-    tw = eng.ntt.psi[d0][start:]
-    nbuf = max(2, int((320 << 20) // (E * N * 8)) + 1)
-    bufs = [torch.randint(0, 1 << 40, (E, N), dtype=torch.int64, device=dev) for _ in range(nbuf)]
+    plan = eng._plan(level, d0)
+    E, N, logN, parts = plan.E, eng.ctx.N, eng.ctx.logN, len(plan.sids)
+    rows = parts * E
+    buf = torch.randint(0, 1 << 40, (rows, N), dtype=torch.int64, device=dev)   # 200 MB at gold: > L2
     st = torch.cuda.current_stream().cuda_stream
-    P = lambda t: t.data_ptr()
+    dsc = plan.desc
 
-    def ntt_call(i=[0]):
-        b = bufs[i[0] % nbuf]
-        i[0] += 1
-        check(lib.ckks_ntt(P(b), N, E, logN, P(tw), tw.stride(0), None, *[P(x) for x in pack], st), "ntt")
+    def ntt_call():
+        check(lib.ckks_ntt_fast(buf.data_ptr(), N, rows, E, logN, dsc.twf_u64, dsc.twf_f64, dsc.q, None, None, 0, st),
+              "ntt_fast")
 
-    ms_ntt, _, _ = timed(ntt_call, 40, 5)
-    achieved = 16.0 * E * N / (ms_ntt * 1e-3) / 1e9
+    ms_ntt, _, _ = timed(ntt_call, 20, 3)
+    achieved = 16.0 * rows * N / (ms_ntt * 1e-3) / 1e9
     clk.__exit__()
     clocks = clk.summary()
 
@@ -300,13 +298,14 @@ def run_ours(args):
         "data": "synthetic",
         "config": {"workload": "gold preset (logN=16, 35 ordinary + 4 special limbs) ct*ct mult + relinearize, level-0 inputs",
                    "parallelism": f"rns-limb-shard{world}", "l2": "working set 507 MB > 126 MB L2, no flush needed",
-                   "arithmetic": "bit-exact reference semantics (62-bit-buffer Montgomery, lazy [0,2q))"},
+                   "arithmetic": "results bit-identical to the reference; FP64 error-free + Shoup butterflies inside the fused path"},
         "clocks": clocks,
         "e2e": {"value": 1e3 / ms_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": launches,
-        "roofline": {"bound": "hbm", "kernel": "ntt_fwd_colpass + ntt_fwd_blockpass (one batched forward NTT)",
+        "roofline": {"bound": "hbm", "kernel": "fast_fwd_colpass + fast_fwd_blockpass (the key switch's batched forward NTT)",
                      "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "limbs_per_launch": E, "ms_per_launch": ms_ntt},
+                     "traffic": None, "limbs_per_launch": rows, "ms_per_launch": ms_ntt,
+                     "note": "algorithmic bytes = 16 B per coefficient per transform (SURVEY 8d); instruction-issue bound, see DESIGN.md 6"},
     }
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
