@@ -437,12 +437,14 @@ static int launch_inv_block(const NttArgs& A, dim3 grid, cudaStream_t st) {
 
 template <int B>
 static int launch_fast_fwd_block(const FastArgs& F, dim3 grid, cudaStream_t st) {
-    fast_fwd_blockpass<B><<<grid, NTT_THREADS, SMEM_BYTES, st>>>(F);
+    cudaFuncSetAttribute(fast_fwd_blockpass<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, FAST_SMEM_BYTES);
+    fast_fwd_blockpass<B><<<grid, NTT_THREADS, FAST_SMEM_BYTES, st>>>(F);
     return launch_status();
 }
 template <int B>
 static int launch_fast_inv_block(const FastArgs& F, dim3 grid, cudaStream_t st) {
-    fast_inv_blockpass<B><<<grid, NTT_THREADS, SMEM_BYTES, st>>>(F);
+    cudaFuncSetAttribute(fast_inv_blockpass<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, FAST_SMEM_BYTES);
+    fast_inv_blockpass<B><<<grid, NTT_THREADS, FAST_SMEM_BYTES, st>>>(F);
     return launch_status();
 }
 }  // namespace
@@ -603,7 +605,8 @@ int ckks_ntt_fast(int64_t* a, int64_t as, int rows, int period, int logN, const 
     FastArgs F{a, as, reinterpret_cast<const ulonglong2*>(tw_u64), tw_f64, q, scal, scal_sh, period, logN, 0, force_int};
     cudaStream_t st = S(stream);
     const dim3 grid((1 << logN) / TILE, rows);
-    fast_fwd_colpass<0><<<grid, NTT_THREADS, SMEM_BYTES, st>>>(F);
+    cudaFuncSetAttribute(fast_fwd_colpass<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, FAST_SMEM_BYTES);
+    fast_fwd_colpass<0><<<grid, NTT_THREADS, FAST_SMEM_BYTES, st>>>(F);
     int rc = launch_status();
     if (rc) return rc;
     F.scal = nullptr;
@@ -639,7 +642,8 @@ int ckks_intt_fast(int64_t* a, int64_t as, int rows, int period, int logN, const
         case 9: rc = launch_fast_inv_block<9>(F, grid, st); break;
     }
     if (rc) return rc;
-    fast_inv_colpass<0><<<grid, NTT_THREADS, SMEM_BYTES, st>>>(F);
+    cudaFuncSetAttribute(fast_inv_colpass<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, FAST_SMEM_BYTES);
+    fast_inv_colpass<0><<<grid, NTT_THREADS, FAST_SMEM_BYTES, st>>>(F);
     return launch_status();
 }
 

@@ -73,14 +73,14 @@ struct ArithF64 {
     }
     // magnitudes double along the sum outputs of GS stages: re-centre once per radix-16 round
     static __device__ __forceinline__ void tame(T& v, const C& c) { v = f64_reduce(v, c); }
-    template <int RUN>
+    template <int RUN, bool SMEM>
     static __device__ __forceinline__ void load_tw(TW (&w)[8], const TW* __restrict__ p) {
         if (RUN == 1) {
-            w[0] = __ldg(p);
+            w[0] = SMEM ? *p : __ldg(p);
         } else {
 #pragma unroll
             for (int g = 0; g < RUN; g += 2) {
-                const double2 v = __ldg(reinterpret_cast<const double2*>(p + g));
+                const double2 v = SMEM ? *reinterpret_cast<const double2*>(p + g) : __ldg(reinterpret_cast<const double2*>(p + g));
                 w[g] = v.x;
                 w[g + 1] = v.y;
             }
@@ -126,46 +126,93 @@ struct ArithU64 {
         V = shoup_mul(d, w.x, w.y, c.q);
     }
     static __device__ __forceinline__ void tame(T& v, const C& c) {}
-    template <int RUN>
+    template <int RUN, bool SMEM>
     static __device__ __forceinline__ void load_tw(TW (&w)[8], const TW* __restrict__ p) {
 #pragma unroll
-        for (int g = 0; g < RUN; ++g) w[g] = __ldg(p + g);
+        for (int g = 0; g < RUN; ++g) w[g] = SMEM ? p[g] : __ldg(p + g);
     }
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// TMA (cp.async.bulk) staging of a CTA's twiddles into shared memory, completion on an mbarrier
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, unsigned bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned phase) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(phase)
+        : "memory");
+}
+
+// where a round's twiddles come from: the global table (index 2^s + ...) or the CTA's staged copy in shared memory
+template <class TW>
+struct TwGlobal {
+    const TW* W;
+    int s0;
+    unsigned pre;
+    static constexpr bool SMEM = false;
+    __device__ __forceinline__ const TW* run(int i) const { return W + ((1u << (s0 + i)) + (pre << i)); }
+};
+template <class TW>
+struct TwShared {
+    const TW* const* stage;   // stage[j] = shared-memory array of pass-local stage j
+    int j0;                   // pass-local stage of i == 0
+    unsigned pre;             // CTA-local index bits above the field
+    static constexpr bool SMEM = true;
+    __device__ __forceinline__ const TW* run(int i) const { return stage[j0 + i] + (pre << i); }
 };
 
 // ------------------------------------------------------------------------------------------------------------
 // rounds
 // ------------------------------------------------------------------------------------------------------------
-template <class A, int FIRST>
-__device__ __forceinline__ void fast_fwd_round(typename A::T (&e)[16], const typename A::TW* __restrict__ W, int s0,
-                                               unsigned pre, const typename A::C& c) {
+template <class A, int FIRST, class SRC>
+__device__ __forceinline__ void fast_fwd_round(typename A::T (&e)[16], const SRC& src, const typename A::C& c) {
 #pragma unroll
     for (int i = FIRST; i < 4; ++i) {
         const int d = 8 >> i;
-        const typename A::TW* wp = W + ((1u << (s0 + i)) + (pre << i));
+        const typename A::TW* wp = src.run(i);
         typename A::TW w[8];
-        if (i == 0) A::template load_tw<1>(w, wp);
-        if (i == 1) A::template load_tw<2>(w, wp);
-        if (i == 2) A::template load_tw<4>(w, wp);
-        if (i == 3) A::template load_tw<8>(w, wp);
+        if (i == 0) A::template load_tw<1, SRC::SMEM>(w, wp);
+        if (i == 1) A::template load_tw<2, SRC::SMEM>(w, wp);
+        if (i == 2) A::template load_tw<4, SRC::SMEM>(w, wp);
+        if (i == 3) A::template load_tw<8, SRC::SMEM>(w, wp);
 #pragma unroll
         for (int k = 0; k < 16; ++k)
             if (!(k & d)) A::ct(e[k], e[k + d], w[k >> (4 - i)], c);
     }
 }
-template <class A, int NST>
-__device__ __forceinline__ void fast_inv_round(typename A::T (&e)[16], const typename A::TW* __restrict__ W, int s0,
-                                               unsigned pre, const typename A::C& c) {
+template <class A, int NST, class SRC>
+__device__ __forceinline__ void fast_inv_round(typename A::T (&e)[16], const SRC& src, const typename A::C& c) {
 #pragma unroll
     for (int i = 0; i < NST; ++i) {
         const int d = 1 << i;
         const int ip = 3 - i;
-        const typename A::TW* wp = W + ((1u << (s0 + ip)) + (pre << ip));
+        const typename A::TW* wp = src.run(ip);
         typename A::TW w[8];
-        if (ip == 0) A::template load_tw<1>(w, wp);
-        if (ip == 1) A::template load_tw<2>(w, wp);
-        if (ip == 2) A::template load_tw<4>(w, wp);
-        if (ip == 3) A::template load_tw<8>(w, wp);
+        if (ip == 0) A::template load_tw<1, SRC::SMEM>(w, wp);
+        if (ip == 1) A::template load_tw<2, SRC::SMEM>(w, wp);
+        if (ip == 2) A::template load_tw<4, SRC::SMEM>(w, wp);
+        if (ip == 3) A::template load_tw<8, SRC::SMEM>(w, wp);
 #pragma unroll
         for (int k = 0; k < 16; ++k)
             if (!(k & d)) A::gs(e[k], e[k + d], w[k >> (i + 1)], c);
@@ -235,33 +282,95 @@ __device__ __forceinline__ ulonglong2 scalar_tw<ArithU64>(const FastArgs& F, int
     return make_ulonglong2((uint64_t)F.scal[limb], F.scal_sh[limb]);
 }
 
+// shared memory of the fast kernels: [data tile | staged twiddles (F64 path) | mbarrier]
+constexpr int FAST_TW_SLOTS = 4096;
+constexpr int FAST_SMEM_BYTES = SMEM_BYTES + FAST_TW_SLOTS * 8 + 16;
+
+template <class TW>
+struct TwSharedBlock {   // block pass: stage j (global stage 8+j) holds 2^(j+unit_log) twiddles, stages back to back
+    const TW* base;
+    int unit_log, j0;
+    unsigned pre;
+    static constexpr bool SMEM = true;
+    __device__ __forceinline__ const TW* run(int i) const {
+        return base + (((1u << (j0 + i)) - 1u) << unit_log) + (pre << i);
+    }
+};
+template <class TW>
+struct TwSharedCol {     // column pass: the first 256 table entries, indexed exactly like the global table
+    const TW* base;
+    int j0;
+    unsigned pre;
+    static constexpr bool SMEM = true;
+    __device__ __forceinline__ const TW* run(int i) const { return base + (1u << (j0 + i)) + (pre << i); }
+};
+
+// one thread arms the barrier and issues the bulk copies; everybody waits right before the first use
+__device__ __forceinline__ void stage_block_twiddles(const double* __restrict__ W, double* tws, uint64_t* bar, int B,
+                                                     unsigned chunk) {
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int unit_log = 12 - B;
+        mbar_expect_tx(bar, (unsigned)(((1u << 12) - (1u << unit_log)) * 8u));
+        for (int j = 0; j < B; ++j) {
+            const unsigned cnt = 1u << (j + unit_log);
+            tma_bulk_g2s(tws + (((1u << j) - 1u) << unit_log), W + (1u << (8 + j)) + (size_t)chunk * cnt, cnt * 8u, bar);
+        }
+    }
+}
+__device__ __forceinline__ void stage_col_twiddles(const double* __restrict__ W, double* tws, uint64_t* bar) {
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(bar, 256u * 8u);
+        tma_bulk_g2s(tws, W, 256u * 8u, bar);
+    }
+}
+
 // ---- forward pass A (column pass, stages 0..7) -------------------------------------------------------------
-template <class A>
+template <class A, bool STAGED>
 __device__ __forceinline__ void fast_fwd_col_body(const FastArgs& F, int64_t* sm, int limb) {
     using T = typename A::T;
+    using TW = typename A::TW;
     const int tau = threadIdx.x;
     const int b = F.logN - 8;
     const typename A::C c = make_const<A>((uint64_t)F.q[limb]);
     int64_t* __restrict__ row0 = F.a + (long long)blockIdx.y * F.a_stride + (long long)blockIdx.x * 16;
-    const typename A::TW* __restrict__ W = tw_row<A>(F, limb);
+    const TW* __restrict__ W = tw_row<A>(F, limb);
+    TW* tws = reinterpret_cast<TW*>(sm + SMEM_SLOTS);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(sm + SMEM_SLOTS + FAST_TW_SLOTS);
+    if constexpr (STAGED) stage_col_twiddles(reinterpret_cast<const double*>(W), reinterpret_cast<double*>(tws), bar);
     T e[16];
     {
         const int r0 = tau >> 4, col = tau & 15;
 #pragma unroll
         for (int k = 0; k < 16; ++k) e[k] = A::load(row0[((long long)(r0 + 16 * k) << b) + col]);
         if (F.scal) {
-            const typename A::TW s = scalar_tw<A>(F, limb);
+            const TW s = scalar_tw<A>(F, limb);
 #pragma unroll
             for (int k = 0; k < 16; ++k) e[k] = A::mul(e[k], s, c);
         }
-        fast_fwd_round<A, 0>(e, W, 0, 0u, c);
+        if constexpr (STAGED) {
+            mbar_wait(bar, 0);
+            fast_fwd_round<A, 0>(e, TwSharedCol<TW>{tws, 0, 0u}, c);
+        } else {
+            fast_fwd_round<A, 0>(e, TwGlobal<TW>{W, 0, 0u}, c);
+        }
         smx_store(sm, e, tau, 8);
     }
     __syncthreads();
     {
         smx_load(sm, e, tau, 4);
         const int hi = tau >> 4, col = tau & 15;
-        fast_fwd_round<A, 0>(e, W, 4, (unsigned)hi, c);
+        if constexpr (STAGED)
+            fast_fwd_round<A, 0>(e, TwSharedCol<TW>{tws, 4, (unsigned)hi}, c);
+        else
+            fast_fwd_round<A, 0>(e, TwGlobal<TW>{W, 4, (unsigned)hi}, c);
 #pragma unroll
         for (int k = 0; k < 16; ++k) row0[((long long)(hi * 16 + k) << b) + col] = A::store_lazy(e[k], c);
     }
@@ -272,48 +381,66 @@ __global__ void __launch_bounds__(NTT_THREADS) fast_fwd_colpass(const FastArgs F
     extern __shared__ __align__(16) int64_t sm[];
     const int limb = blockIdx.y % F.period;
     if (!F.force_int && (uint64_t)F.q[limb] < SMALL_PRIME_LIMIT)
-        fast_fwd_col_body<ArithF64>(F, sm, limb);
+        fast_fwd_col_body<ArithF64, true>(F, sm, limb);
     else
-        fast_fwd_col_body<ArithU64>(F, sm, limb);
+        fast_fwd_col_body<ArithU64, false>(F, sm, limb);
 }
 
 // ---- forward pass B (block pass, stages 8..logN-1), canonical [0,q) out --------------------------------------
-template <class A, int B>
+template <class A, int B, bool STAGED>
 __device__ __forceinline__ void fast_fwd_block_body(const FastArgs& F, int64_t* sm, int limb) {
     using T = typename A::T;
+    using TW = typename A::TW;
     const int tau = threadIdx.x;
     const unsigned chunk = blockIdx.x;
     constexpr int logN = B + 8;
     const typename A::C c = make_const<A>((uint64_t)F.q[limb]);
     int64_t* __restrict__ g = F.a + (long long)blockIdx.y * F.a_stride + (long long)chunk * TILE;
-    const typename A::TW* __restrict__ W = tw_row<A>(F, limb);
+    const TW* __restrict__ W = tw_row<A>(F, limb);
+    TW* tws = reinterpret_cast<TW*>(sm + SMEM_SLOTS);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(sm + SMEM_SLOTS + FAST_TW_SLOTS);
+    if constexpr (STAGED) stage_block_twiddles(reinterpret_cast<const double*>(W), reinterpret_cast<double*>(tws), bar, B, chunk);
     T e[16];
     constexpr int P1 = B - 4;
     {
         const int zb = zbase(tau, P1);
 #pragma unroll
         for (int k = 0; k < 16; ++k) e[k] = A::load(g[zb | (k << P1)]);
-        fast_fwd_round<A, 0>(e, W, logN - 4 - P1, (chunk << (8 - P1)) | (unsigned)(tau >> P1), c);
+        if constexpr (STAGED) {
+            mbar_wait(bar, 0);
+            fast_fwd_round<A, 0>(e, TwSharedBlock<TW>{tws, 12 - B, 0, (unsigned)(tau >> P1)}, c);
+        } else {
+            fast_fwd_round<A, 0>(e, TwGlobal<TW>{W, logN - 4 - P1, (chunk << (8 - P1)) | (unsigned)(tau >> P1)}, c);
+        }
     }
     if constexpr (B >= 8) {
         constexpr int P2 = B - 8;
         smx_store(sm, e, tau, P1);
         __syncthreads();
         smx_load(sm, e, tau, P2);
-        fast_fwd_round<A, 0>(e, W, logN - 4 - P2, (chunk << (8 - P2)) | (unsigned)(tau >> P2), c);
+        if constexpr (STAGED)
+            fast_fwd_round<A, 0>(e, TwSharedBlock<TW>{tws, 12 - B, 4, (unsigned)(tau >> P2)}, c);
+        else
+            fast_fwd_round<A, 0>(e, TwGlobal<TW>{W, logN - 4 - P2, (chunk << (8 - P2)) | (unsigned)(tau >> P2)}, c);
         if constexpr (B == 9) {
             __syncthreads();
             smx_store(sm, e, tau, P2);
             __syncthreads();
             smx_load(sm, e, tau, 0);
-            fast_fwd_round<A, 3>(e, W, logN - 4, (chunk << 8) | (unsigned)tau, c);
+            if constexpr (STAGED)
+                fast_fwd_round<A, 3>(e, TwSharedBlock<TW>{tws, 12 - B, B - 4, (unsigned)tau}, c);
+            else
+                fast_fwd_round<A, 3>(e, TwGlobal<TW>{W, logN - 4, (chunk << 8) | (unsigned)tau}, c);
         }
         __syncthreads();
     } else if constexpr (B > 4) {
         smx_store(sm, e, tau, P1);
         __syncthreads();
         smx_load(sm, e, tau, 0);
-        fast_fwd_round<A, 8 - B>(e, W, logN - 4, (chunk << 8) | (unsigned)tau, c);
+        if constexpr (STAGED)
+            fast_fwd_round<A, 8 - B>(e, TwSharedBlock<TW>{tws, 12 - B, B - 4, (unsigned)tau}, c);
+        else
+            fast_fwd_round<A, 8 - B>(e, TwGlobal<TW>{W, logN - 4, (chunk << 8) | (unsigned)tau}, c);
         __syncthreads();
     }
     {   // canonical values back through shared memory for coalesced 128-bit stores
@@ -331,21 +458,25 @@ __global__ void __launch_bounds__(NTT_THREADS) fast_fwd_blockpass(const FastArgs
     extern __shared__ __align__(16) int64_t sm[];
     const int limb = blockIdx.y % F.period;
     if (!F.force_int && (uint64_t)F.q[limb] < SMALL_PRIME_LIMIT)
-        fast_fwd_block_body<ArithF64, B>(F, sm, limb);
+        fast_fwd_block_body<ArithF64, B, true>(F, sm, limb);
     else
-        fast_fwd_block_body<ArithU64, B>(F, sm, limb);
+        fast_fwd_block_body<ArithU64, B, false>(F, sm, limb);
 }
 
 // ---- inverse pass B' (levels 0..B-1) ---------------------------------------------------------------------------
-template <class A, int B>
+template <class A, int B, bool STAGED>
 __device__ __forceinline__ void fast_inv_block_body(const FastArgs& F, int64_t* sm, int limb) {
     using T = typename A::T;
+    using TW = typename A::TW;
     const int tau = threadIdx.x;
     const unsigned chunk = blockIdx.x;
     constexpr int logN = B + 8;
     const typename A::C c = make_const<A>((uint64_t)F.q[limb]);
     int64_t* __restrict__ g = F.a + (long long)blockIdx.y * F.a_stride + (long long)chunk * TILE;
-    const typename A::TW* __restrict__ W = tw_row<A>(F, limb);
+    const TW* __restrict__ W = tw_row<A>(F, limb);
+    TW* tws = reinterpret_cast<TW*>(sm + SMEM_SLOTS);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(sm + SMEM_SLOTS + FAST_TW_SLOTS);
+    if constexpr (STAGED) stage_block_twiddles(reinterpret_cast<const double*>(W), reinterpret_cast<double*>(tws), bar, B, chunk);
     T e[16];
     global_to_sm(sm, g, tau);
     __syncthreads();
@@ -355,7 +486,12 @@ __device__ __forceinline__ void fast_inv_block_body(const FastArgs& F, int64_t* 
 #pragma unroll
         for (int k = 0; k < 16; ++k) e[k] = A::load(r[k]);
     }
-    fast_inv_round<A, 4>(e, W, logN - 4, (chunk << 8) | (unsigned)tau, c);
+    if constexpr (STAGED) {
+        mbar_wait(bar, 0);
+        fast_inv_round<A, 4>(e, TwSharedBlock<TW>{tws, 12 - B, B - 4, (unsigned)tau}, c);
+    } else {
+        fast_inv_round<A, 4>(e, TwGlobal<TW>{W, logN - 4, (chunk << 8) | (unsigned)tau}, c);
+    }
     if constexpr (B == 4) {
         int64_t r[16];
 #pragma unroll
@@ -370,13 +506,19 @@ __device__ __forceinline__ void fast_inv_block_body(const FastArgs& F, int64_t* 
         __syncthreads();
         smx_load(sm, e, tau, 4);
         constexpr int NST = (B >= 8) ? 4 : B - 4;
-        fast_inv_round<A, NST>(e, W, logN - 8, (chunk << 4) | (unsigned)(tau >> 4), c);
+        if constexpr (STAGED)
+            fast_inv_round<A, NST>(e, TwSharedBlock<TW>{tws, 12 - B, B - 8, (unsigned)(tau >> 4)}, c);
+        else
+            fast_inv_round<A, NST>(e, TwGlobal<TW>{W, logN - 8, (chunk << 4) | (unsigned)(tau >> 4)}, c);
         if constexpr (B == 9) {
             __syncthreads();
             smx_store(sm, e, tau, 4);
             __syncthreads();
             smx_load(sm, e, tau, 8);
-            fast_inv_round<A, 1>(e, W, logN - 12, chunk, c);
+            if constexpr (STAGED)
+                fast_inv_round<A, 1>(e, TwSharedBlock<TW>{tws, 12 - B, B - 12, 0u}, c);
+            else
+                fast_inv_round<A, 1>(e, TwGlobal<TW>{W, logN - 12, chunk}, c);
             const int zb = zbase(tau, 8);
 #pragma unroll
             for (int k = 0; k < 16; ++k) g[zb | (k << 8)] = A::store_lazy(e[k], c);
@@ -393,33 +535,45 @@ __global__ void __launch_bounds__(NTT_THREADS) fast_inv_blockpass(const FastArgs
     extern __shared__ __align__(16) int64_t sm[];
     const int limb = blockIdx.y % F.period;
     if (!F.force_int && (uint64_t)F.q[limb] < SMALL_PRIME_LIMIT)
-        fast_inv_block_body<ArithF64, B>(F, sm, limb);
+        fast_inv_block_body<ArithF64, B, true>(F, sm, limb);
     else
-        fast_inv_block_body<ArithU64, B>(F, sm, limb);
+        fast_inv_block_body<ArithU64, B, false>(F, sm, limb);
 }
 
 // ---- inverse pass A' (levels b..logN-1), x scalar, canonical out ---------------------------------------------
-template <class A>
+template <class A, bool STAGED>
 __device__ __forceinline__ void fast_inv_col_body(const FastArgs& F, int64_t* sm, int limb) {
     using T = typename A::T;
+    using TW = typename A::TW;
     const int tau = threadIdx.x;
     const int b = F.logN - 8;
     const typename A::C c = make_const<A>((uint64_t)F.q[limb]);
     int64_t* __restrict__ row0 = F.a + (long long)blockIdx.y * F.a_stride + (long long)blockIdx.x * 16;
-    const typename A::TW* __restrict__ W = tw_row<A>(F, limb);
+    const TW* __restrict__ W = tw_row<A>(F, limb);
+    TW* tws = reinterpret_cast<TW*>(sm + SMEM_SLOTS);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(sm + SMEM_SLOTS + FAST_TW_SLOTS);
+    if constexpr (STAGED) stage_col_twiddles(reinterpret_cast<const double*>(W), reinterpret_cast<double*>(tws), bar);
     T e[16];
     {
         const int hi = tau >> 4, col = tau & 15;
 #pragma unroll
         for (int k = 0; k < 16; ++k) e[k] = A::load(row0[((long long)(hi * 16 + k) << b) + col]);
-        fast_inv_round<A, 4>(e, W, 4, (unsigned)hi, c);
+        if constexpr (STAGED) {
+            mbar_wait(bar, 0);
+            fast_inv_round<A, 4>(e, TwSharedCol<TW>{tws, 4, (unsigned)hi}, c);
+        } else {
+            fast_inv_round<A, 4>(e, TwGlobal<TW>{W, 4, (unsigned)hi}, c);
+        }
         smx_store(sm, e, tau, 4);
     }
     __syncthreads();
     {
         smx_load(sm, e, tau, 8);
-        fast_inv_round<A, 4>(e, W, 0, 0u, c);
-        const typename A::TW s = scalar_tw<A>(F, limb);
+        if constexpr (STAGED)
+            fast_inv_round<A, 4>(e, TwSharedCol<TW>{tws, 0, 0u}, c);
+        else
+            fast_inv_round<A, 4>(e, TwGlobal<TW>{W, 0, 0u}, c);
+        const TW s = scalar_tw<A>(F, limb);
         const int r0 = tau >> 4, col = tau & 15;
 #pragma unroll
         for (int k = 0; k < 16; ++k)
@@ -432,9 +586,9 @@ __global__ void __launch_bounds__(NTT_THREADS) fast_inv_colpass(const FastArgs F
     extern __shared__ __align__(16) int64_t sm[];
     const int limb = blockIdx.y % F.period;
     if (!F.force_int && (uint64_t)F.q[limb] < SMALL_PRIME_LIMIT)
-        fast_inv_col_body<ArithF64>(F, sm, limb);
+        fast_inv_col_body<ArithF64, true>(F, sm, limb);
     else
-        fast_inv_col_body<ArithU64>(F, sm, limb);
+        fast_inv_col_body<ArithU64, false>(F, sm, limb);
 }
 
 // ---- table construction ----------------------------------------------------------------------------------------
