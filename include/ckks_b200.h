@@ -167,6 +167,10 @@ typedef struct {
     const int32_t *loc_row0, *loc_alpha;                      /* [nlocal] partitions whose digits this device makes */
     const int64_t* const* loc_Y; const int64_t* const* loc_Ltri;
     const int64_t* rescale_scale; int64_t round_at;           /* rescale INTO this level: [L] multipliers       */
+    /* optional (NULL = separate extend kernel): tables of the extension fused into the forward column pass */
+    const int32_t* part_wide;                                 /* [nparts] 1: digits may exceed 2^51 (alpha == 1) */
+    const double* const* Hm;                                  /* [nparts] -> [(alpha-1)][E] doubles m_i mod q_t  */
+    const double *Rd, *C31;                                   /* [E] R mod q_t, 2^31 mod q_t as doubles          */
 } ckks_level_t;
 
 /* rescale x4 -> batched enter+NTT -> tensor product -> batched iNTT+exit -> Garner digits of d2

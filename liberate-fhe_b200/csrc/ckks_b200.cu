@@ -782,10 +782,41 @@ int ckks_exec_keyswitch_stage(const ckks_level_t* lv, const int64_t* const* digi
     int64_t* acc = ext + (long long)P * E * N;          // [2E][N]
     int64_t* eff = acc + 2ll * E * N;                   // [K][N]
     const MontPack m{lv->_2q, lv->ql, lv->qh, lv->kl, lv->kh};
-    k_extend_batched<<<ew_grid(N, P * E), EW_THREADS, 0, S(stream)>>>(digit_ptrs, digit_stride, lv->part_alpha, ext, N, E, N,
-                                                                      lv->Rs, lv->Lenter, m);
-    RC(launch_status());
-    RC(ckks_ntt_fast(ext, N, P * E, E, lv->logN, lv->twf_u64, lv->twf_f64, lv->q, nullptr, nullptr, 0, stream));
+    if (lv->Hm) {
+        // basis extension fused into the column pass of the forward transform; then the block pass
+        ExtArgs X{};
+        X.F = FastArgs{ext, N, reinterpret_cast<const ulonglong2*>(lv->twf_u64), lv->twf_f64, lv->q, nullptr, nullptr, E,
+                       lv->logN, 0, 0};
+        X.digit_ptrs = digit_ptrs;
+        X.d_stride = digit_stride;
+        X.alphas = lv->part_alpha;
+        X.wide = lv->part_wide;
+        X.Hm = lv->Hm;
+        X.Rd = lv->Rd;
+        X.C31 = lv->C31;
+        X.Lenter = lv->Lenter;
+        X.Rs = lv->Rs;
+        X._2q = lv->_2q; X.ql = lv->ql; X.qh = lv->qh; X.kl = lv->kl; X.kh = lv->kh;
+        X.E = E;
+        const dim3 grid(N / TILE, P * E);
+        cudaFuncSetAttribute(fast_fwd_colpass_ext<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, FAST_SMEM_BYTES);
+        fast_fwd_colpass_ext<0><<<grid, NTT_THREADS, FAST_SMEM_BYTES, S(stream)>>>(X);
+        RC(launch_status());
+        switch (lv->logN - 8) {
+            case 4: RC(launch_fast_fwd_block<4>(X.F, grid, S(stream))); break;
+            case 5: RC(launch_fast_fwd_block<5>(X.F, grid, S(stream))); break;
+            case 6: RC(launch_fast_fwd_block<6>(X.F, grid, S(stream))); break;
+            case 7: RC(launch_fast_fwd_block<7>(X.F, grid, S(stream))); break;
+            case 8: RC(launch_fast_fwd_block<8>(X.F, grid, S(stream))); break;
+            case 9: RC(launch_fast_fwd_block<9>(X.F, grid, S(stream))); break;
+            default: return CKKS_E_LOGN;
+        }
+    } else {
+        k_extend_batched<<<ew_grid(N, P * E), EW_THREADS, 0, S(stream)>>>(digit_ptrs, digit_stride, lv->part_alpha, ext, N, E,
+                                                                          N, lv->Rs, lv->Lenter, m);
+        RC(launch_status());
+        RC(ckks_ntt_fast(ext, N, P * E, E, lv->logN, lv->twf_u64, lv->twf_f64, lv->q, nullptr, nullptr, 0, stream));
+    }
     RC(ckks_ksk_inner(ext, N, P, k0_ptrs, k1_ptrs, ksk_stride, acc, acc + (long long)E * N, N, E, N, lv->_2q, lv->ql, lv->qh,
                       lv->kl, lv->kh, stream));
     RC(ckks_intt_fast(acc, N, 2 * E, E, lv->logN, lv->twi_u64, lv->twi_f64, lv->q, lv->sExit, (const uint64_t*)lv->sExit_sh, 0, 0,

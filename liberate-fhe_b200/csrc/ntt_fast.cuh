@@ -377,13 +377,120 @@ __device__ __forceinline__ void fast_fwd_col_body(const FastArgs& F, int64_t* sm
 }
 
 template <int DUMMY>
-__global__ void __launch_bounds__(NTT_THREADS) fast_fwd_colpass(const FastArgs F) {
+__global__ void __launch_bounds__(NTT_THREADS, 3) fast_fwd_colpass(const FastArgs F) {
     extern __shared__ __align__(16) int64_t sm[];
     const int limb = blockIdx.y % F.period;
     if (!F.force_int && (uint64_t)F.q[limb] < SMALL_PRIME_LIMIT)
         fast_fwd_col_body<ArithF64, true>(F, sm, limb);
     else
         fast_fwd_col_body<ArithU64, false>(F, sm, limb);
+}
+
+// ---- forward pass A with the ModUp basis extension fused into the load (key switch) ---------------------------
+// Row r of the output block is (partition p = r / E, target limb t = r % E).  Instead of reading an extended
+// polynomial from memory, every coefficient is rebuilt from the partition's Garner digits s_0..s_{alpha-1}
+// (exact integers, engine.py:654-705) by Horner's rule in the target field,
+//      X = s_0 + m_0 (s_1 + m_1 (s_2 + ...)),   ext = X * R   (== extend, engine.py:707-743, up to congruence)
+// -- in FP64 for scale-prime targets (digits of scale-prime partitions are < 2^43; the single 60-bit digit of the
+// base-prime partition is split into 31-bit halves first), with the reference's Montgomery chain for 60-bit targets.
+struct ExtArgs {
+    FastArgs F;
+    const int64_t* const* digit_ptrs;   // [P] -> [alpha][N] digit blocks, rows d_stride apart
+    long long d_stride;
+    const int32_t* alphas;              // [P]
+    const int32_t* wide;                // [P] 1 if the partition's digits can exceed 2^51 (base-prime partition)
+    const double* const* Hm;            // [P] -> [(alpha-1)][E] doubles: m_i mod q_t
+    const double* Rd;                   // [E] R mod q_t
+    const double* C31;                  // [E] 2^31 mod q_t
+    const int64_t* const* Lenter;       // [P] -> [(alpha-1)][E] (L_i R^2) mod q_t      (60-bit targets)
+    const int64_t* Rs;                  // [E] R^2 mod q_t
+    const int64_t *_2q, *ql, *qh, *kl, *kh;
+    int E;
+};
+
+__device__ __forceinline__ double ext_value_f64(const ExtArgs& X, int p, int t, long long j, int alpha, bool wide,
+                                                const F64C& c, double Rd, double c31) {
+    const int64_t* __restrict__ st = X.digit_ptrs[p];
+    double acc;
+    if (wide) {   // alpha == 1, digit up to 2^60: hi * 2^31 + lo
+        const int64_t s0 = st[j];
+        const double hi = (double)(int)(s0 >> 31), lo = (double)(int)(s0 & 0x7FFFFFFF);
+        acc = __dadd_rn(f64_mulmod(hi, c31, c), lo);
+    } else {
+        const double* __restrict__ hm = X.Hm[p];
+        acc = i2d(st[(long long)(alpha - 1) * X.d_stride + j]);
+        for (int i = alpha - 2; i >= 0; --i)
+            acc = __dadd_rn(f64_mulmod(acc, hm[(long long)i * X.E + t], c), i2d(st[(long long)i * X.d_stride + j]));
+    }
+    return f64_mulmod(acc, Rd, c);
+}
+
+__device__ __forceinline__ uint64_t ext_value_u64(const ExtArgs& X, int p, int t, long long j, int alpha,
+                                                  const LimbConst& k) {
+    const int64_t* __restrict__ st = X.digit_ptrs[p];
+    const int64_t* __restrict__ le = X.Lenter[p];
+    const int64_t q2 = (int64_t)k.q2;
+    int64_t acc = mont_mul_ss(st[j], X.Rs[t], k.q4, k.k);
+    for (int i = 0; i < alpha - 1; ++i)
+        acc = lazy_add(acc, mont_mul_ss(st[(long long)(i + 1) * X.d_stride + j], le[(long long)i * X.E + t], k.q4, k.k), q2);
+    acc += (acc < 0) ? q2 : 0;
+    return (uint64_t)acc;
+}
+
+template <int DUMMY>
+__global__ void __launch_bounds__(NTT_THREADS, 3) fast_fwd_colpass_ext(const ExtArgs X) {
+    extern __shared__ __align__(16) int64_t sm[];
+    const FastArgs& F = X.F;
+    const int row = blockIdx.y;
+    const int p = row / X.E, t = row - p * X.E;
+    const int tau = threadIdx.x;
+    const int b = F.logN - 8;
+    const int alpha = X.alphas[p];
+    int64_t* __restrict__ row0 = F.a + (long long)row * F.a_stride + (long long)blockIdx.x * 16;
+    const long long col0 = (long long)blockIdx.x * 16;
+    const uint64_t q = (uint64_t)F.q[t];
+    if (q < SMALL_PRIME_LIMIT) {
+        using A = ArithF64;
+        const F64C c = make_const<A>(q);
+        const double* __restrict__ W = tw_row<A>(F, t);
+        double* tws = reinterpret_cast<double*>(sm + SMEM_SLOTS);
+        uint64_t* bar = reinterpret_cast<uint64_t*>(sm + SMEM_SLOTS + FAST_TW_SLOTS);
+        stage_col_twiddles(W, tws, bar);
+        double e[16];
+        const bool wide = X.wide[p] != 0;
+        const double Rd = X.Rd[t], c31 = X.C31[t];
+        const int r0 = tau >> 4, col = tau & 15;
+#pragma unroll
+        for (int k = 0; k < 16; ++k)
+            e[k] = ext_value_f64(X, p, t, ((long long)(r0 + 16 * k) << b) + col0 + col, alpha, wide, c, Rd, c31);
+        mbar_wait(bar, 0);
+        fast_fwd_round<A, 0>(e, TwSharedCol<double>{tws, 0, 0u}, c);
+        smx_store(sm, e, tau, 8);
+        __syncthreads();
+        smx_load(sm, e, tau, 4);
+        const int hi = tau >> 4;
+        fast_fwd_round<A, 0>(e, TwSharedCol<double>{tws, 4, (unsigned)hi}, c);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) row0[((long long)(hi * 16 + k) << b) + col] = A::store_lazy(e[k], c);
+    } else {
+        using A = ArithU64;
+        const U64C c = make_const<A>(q);
+        const LimbConst lk = load_limb_const(X._2q, X.ql, X.qh, X.kl, X.kh, t);
+        const ulonglong2* __restrict__ W = tw_row<A>(F, t);
+        uint64_t e[16];
+        const int r0 = tau >> 4, col = tau & 15;
+#pragma unroll
+        for (int k = 0; k < 16; ++k)
+            e[k] = ext_value_u64(X, p, t, ((long long)(r0 + 16 * k) << b) + col0 + col, alpha, lk);
+        fast_fwd_round<A, 0>(e, TwGlobal<ulonglong2>{W, 0, 0u}, c);
+        smx_store(sm, e, tau, 8);
+        __syncthreads();
+        smx_load(sm, e, tau, 4);
+        const int hi = tau >> 4;
+        fast_fwd_round<A, 0>(e, TwGlobal<ulonglong2>{W, 4, (unsigned)hi}, c);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) row0[((long long)(hi * 16 + k) << b) + col] = A::store_lazy(e[k], c);
+    }
 }
 
 // ---- forward pass B (block pass, stages 8..logN-1), canonical [0,q) out --------------------------------------
@@ -454,7 +561,7 @@ __device__ __forceinline__ void fast_fwd_block_body(const FastArgs& F, int64_t* 
 }
 
 template <int B>
-__global__ void __launch_bounds__(NTT_THREADS) fast_fwd_blockpass(const FastArgs F) {
+__global__ void __launch_bounds__(NTT_THREADS, 3) fast_fwd_blockpass(const FastArgs F) {
     extern __shared__ __align__(16) int64_t sm[];
     const int limb = blockIdx.y % F.period;
     if (!F.force_int && (uint64_t)F.q[limb] < SMALL_PRIME_LIMIT)
@@ -531,7 +638,7 @@ __device__ __forceinline__ void fast_inv_block_body(const FastArgs& F, int64_t* 
 }
 
 template <int B>
-__global__ void __launch_bounds__(NTT_THREADS) fast_inv_blockpass(const FastArgs F) {
+__global__ void __launch_bounds__(NTT_THREADS, 3) fast_inv_blockpass(const FastArgs F) {
     extern __shared__ __align__(16) int64_t sm[];
     const int limb = blockIdx.y % F.period;
     if (!F.force_int && (uint64_t)F.q[limb] < SMALL_PRIME_LIMIT)
@@ -582,7 +689,7 @@ __device__ __forceinline__ void fast_inv_col_body(const FastArgs& F, int64_t* sm
 }
 
 template <int DUMMY>
-__global__ void __launch_bounds__(NTT_THREADS) fast_inv_colpass(const FastArgs F) {
+__global__ void __launch_bounds__(NTT_THREADS, 3) fast_inv_colpass(const FastArgs F) {
     extern __shared__ __align__(16) int64_t sm[];
     const int limb = blockIdx.y % F.period;
     if (!F.force_int && (uint64_t)F.q[limb] < SMALL_PRIME_LIMIT)

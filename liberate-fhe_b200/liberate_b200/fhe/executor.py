@@ -25,7 +25,8 @@ class LevelT(ctypes.Structure):
                 ("sR", _vp), ("sR_sh", _vp), ("sExit", _vp), ("sExit_sh", _vp),
                 ("PiR", _vp), ("part_alpha", _vp), ("Lenter", _vp),
                 ("loc_row0", _vp), ("loc_alpha", _vp), ("loc_Y", _vp), ("loc_Ltri", _vp),
-                ("rescale_scale", _vp), ("round_at", ctypes.c_int64)]
+                ("rescale_scale", _vp), ("round_at", ctypes.c_int64),
+                ("part_wide", _vp), ("Hm", _vp), ("Rd", _vp), ("C31", _vp)]
 
 
 def _p(t):
@@ -100,6 +101,28 @@ class LevelPlan:
             d.rescale_scale = _p(hold(eng.rescale_scales[level - 1][dev]))
             src = ntt.p.rescaler_loc[level - 1]
             d.round_at = eng.ctx.q[ntt.p.destination_arrays[level - 1][src][0]] // 2
+        # Horner tables of the extension fused into the forward column pass (FP64 targets)
+        qrows = [eng.ctx.q[i] for i in ntt.p.d_special[dev][a:b]]
+        SMALL = 1 << 42
+        f64 = lambda v: hold(torch.tensor(v, dtype=torch.float64, device=device))
+        wide, hm_ptrs = [], []
+        for s_ in self.sids:
+            src, part_id, alpha = owners[s_]
+            primes = ntt.parts_pack[src][tuple(ntt.p.p[level][src][part_id])]["prime_ids"]
+            m = [eng.ctx.q[i] for i in primes]
+            is_wide = any(x >= SMALL for x in m)
+            if is_wide and alpha != 1 and any(qt < SMALL for qt in qrows):
+                raise NotImplementedError("multi-limb partitions of primes >= 2^42 next to FP64 target limbs")
+            wide.append(1 if is_wide else 0)
+            if alpha > 1:
+                hm = f64([[float(m[i] % qt) for qt in qrows] for i in range(alpha - 1)])
+                hm_ptrs.append(hm.data_ptr())
+            else:
+                hm_ptrs.append(0)
+        d.part_wide = _p(i32(wide))
+        d.Hm = _p(i64(hm_ptrs))
+        d.Rd = _p(f64([float(eng.ctx.R % qt) for qt in qrows]))
+        d.C31 = _p(f64([float((1 << 31) % qt) for qt in qrows]))
         self.desc = d
         self.ref = ctypes.byref(d)
         self._keep = keep
