@@ -171,6 +171,9 @@ typedef struct {
     const int32_t* part_wide;                                 /* [nparts] 1: digits may exceed 2^51 (alpha == 1) */
     const double* const* Hm;                                  /* [nparts] -> [(alpha-1)][E] doubles m_i mod q_t  */
     const double *Rd, *C31;                                   /* [E] R mod q_t, 2^31 mod q_t as doubles          */
+    const double* Rinv;                                       /* [E] R^-1 mod q_t (FP64 inner product), or NULL  */
+    const double* Pinv;                                       /* [K][E] P_i^-1 mod q_t (FP64 ModDown), or NULL   */
+    int32_t L_small, _pad2;                                   /* leading ordinary rows with q < 2^42             */
 } ckks_level_t;
 
 /* rescale x4 -> batched enter+NTT -> tensor product -> batched iNTT+exit -> Garner digits of d2

@@ -313,8 +313,8 @@ __global__ void k_moddown_special(const int64_t* __restrict__ d, long long ds, i
 __global__ void k_moddown_ordinary(const int64_t* __restrict__ d, long long ds, int L, int K, int N,
                                    const int64_t* __restrict__ Rs, const int64_t* __restrict__ PiR,
                                    const int64_t* __restrict__ eff, const int64_t* __restrict__ add, long long adds,
-                                   int64_t* __restrict__ out, long long os, MontPack m) {
-    const int t = blockIdx.y;
+                                   int64_t* __restrict__ out, long long os, int row0, MontPack m) {
+    const int t = row0 + blockIdx.y;
     const int j = 2 * (blockIdx.x * EW_THREADS + threadIdx.x);
     if (j >= N) return;
     const int E = L + K;
@@ -731,7 +731,7 @@ int ckks_moddown(int64_t* d, int64_t ds, int L, int K, int N, const int64_t* Rs,
     k_moddown_special<<<col_grid(N), EW_THREADS, 0, S(stream)>>>(d, ds, L, K, N, PiR, eff, m);
     int rc = launch_status();
     if (rc) return rc;
-    k_moddown_ordinary<<<ew_grid(N, L), EW_THREADS, 0, S(stream)>>>(d, ds, L, K, N, Rs, PiR, eff, add, adds, out, os, m);
+    k_moddown_ordinary<<<ew_grid(N, L), EW_THREADS, 0, S(stream)>>>(d, ds, L, K, N, Rs, PiR, eff, add, adds, out, os, 0, m);
     return launch_status();
 }
 
@@ -783,10 +783,8 @@ int ckks_exec_keyswitch_stage(const ckks_level_t* lv, const int64_t* const* digi
     int64_t* eff = acc + 2ll * E * N;                   // [K][N]
     const MontPack m{lv->_2q, lv->ql, lv->qh, lv->kl, lv->kh};
     if (lv->Hm) {
-        // basis extension fused into the column pass of the forward transform; then the block pass
+        // FP64-Horner / Montgomery basis extension (digits read once per partition), then the batched transform
         ExtArgs X{};
-        X.F = FastArgs{ext, N, reinterpret_cast<const ulonglong2*>(lv->twf_u64), lv->twf_f64, lv->q, nullptr, nullptr, E,
-                       lv->logN, 0, 0};
         X.digit_ptrs = digit_ptrs;
         X.d_stride = digit_stride;
         X.alphas = lv->part_alpha;
@@ -796,35 +794,49 @@ int ckks_exec_keyswitch_stage(const ckks_level_t* lv, const int64_t* const* digi
         X.C31 = lv->C31;
         X.Lenter = lv->Lenter;
         X.Rs = lv->Rs;
-        X._2q = lv->_2q; X.ql = lv->ql; X.qh = lv->qh; X.kl = lv->kl; X.kh = lv->kh;
+        X.q = lv->q; X._2q = lv->_2q; X.ql = lv->ql; X.qh = lv->qh; X.kl = lv->kl; X.kh = lv->kh;
+        X.out = ext;
         X.E = E;
-        const dim3 grid(N / TILE, P * E);
-        cudaFuncSetAttribute(fast_fwd_colpass_ext<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, FAST_SMEM_BYTES);
-        fast_fwd_colpass_ext<0><<<grid, NTT_THREADS, FAST_SMEM_BYTES, S(stream)>>>(X);
+        X.N = N;
+        k_extend_fast<<<dim3((N / 2 + 255) / 256, P), 256, 0, S(stream)>>>(X);
         RC(launch_status());
-        switch (lv->logN - 8) {
-            case 4: RC(launch_fast_fwd_block<4>(X.F, grid, S(stream))); break;
-            case 5: RC(launch_fast_fwd_block<5>(X.F, grid, S(stream))); break;
-            case 6: RC(launch_fast_fwd_block<6>(X.F, grid, S(stream))); break;
-            case 7: RC(launch_fast_fwd_block<7>(X.F, grid, S(stream))); break;
-            case 8: RC(launch_fast_fwd_block<8>(X.F, grid, S(stream))); break;
-            case 9: RC(launch_fast_fwd_block<9>(X.F, grid, S(stream))); break;
-            default: return CKKS_E_LOGN;
-        }
+        RC(ckks_ntt_fast(ext, N, P * E, E, lv->logN, lv->twf_u64, lv->twf_f64, lv->q, nullptr, nullptr, 0, stream));
     } else {
         k_extend_batched<<<ew_grid(N, P * E), EW_THREADS, 0, S(stream)>>>(digit_ptrs, digit_stride, lv->part_alpha, ext, N, E,
                                                                           N, lv->Rs, lv->Lenter, m);
         RC(launch_status());
         RC(ckks_ntt_fast(ext, N, P * E, E, lv->logN, lv->twf_u64, lv->twf_f64, lv->q, nullptr, nullptr, 0, stream));
     }
-    RC(ckks_ksk_inner(ext, N, P, k0_ptrs, k1_ptrs, ksk_stride, acc, acc + (long long)E * N, N, E, N, lv->_2q, lv->ql, lv->qh,
-                      lv->kl, lv->kh, stream));
+    if (lv->Rinv) {
+        InnerArgs I{ext, k0_ptrs, k1_ptrs, ksk_stride, acc, acc + (long long)E * N, lv->Rinv, lv->q, lv->_2q, lv->ql, lv->qh,
+                    lv->kl, lv->kh, P, E, N};
+        k_ksk_inner_fast<<<dim3((N / 2 + 255) / 256, E), 256, 0, S(stream)>>>(I);
+        RC(launch_status());
+    } else {
+        RC(ckks_ksk_inner(ext, N, P, k0_ptrs, k1_ptrs, ksk_stride, acc, acc + (long long)E * N, N, E, N, lv->_2q, lv->ql,
+                          lv->qh, lv->kl, lv->kh, stream));
+    }
     RC(ckks_intt_fast(acc, N, 2 * E, E, lv->logN, lv->twi_u64, lv->twi_f64, lv->q, lv->sExit, (const uint64_t*)lv->sExit_sh, 0, 0,
                       stream));
-    RC(ckks_moddown(acc, N, L, K, N, lv->Rs, lv->PiR, add0, add_stride, out0, out_stride, eff, lv->_2q, lv->ql, lv->qh,
-                    lv->kl, lv->kh, stream));
-    return ckks_moddown(acc + (long long)E * N, N, L, K, N, lv->Rs, lv->PiR, add1, add_stride, out1, out_stride, eff, lv->_2q,
-                        lv->ql, lv->qh, lv->kl, lv->kh, stream);
+    int64_t* outs[2] = {out0, out1};
+    const int64_t* adds[2] = {add0, add1};
+    const int Ls = lv->Pinv ? lv->L_small : 0;   // leading ordinary rows handled by the FP64 kernel
+    for (int h = 0; h < 2; ++h) {
+        int64_t* dh = acc + (long long)h * E * N;
+        k_moddown_special<<<col_grid(N), EW_THREADS, 0, S(stream)>>>(dh, N, L, K, N, lv->PiR, eff, m);
+        RC(launch_status());
+        if (Ls > 0) {
+            ModDownArgs M{dh, eff, adds[h], add_stride, outs[h], out_stride, lv->Pinv, lv->C31, lv->q, L, K, E, N};
+            k_moddown_fast<<<dim3((N / 2 + 255) / 256, Ls), 256, 0, S(stream)>>>(M);
+            RC(launch_status());
+        }
+        if (Ls < L) {
+            k_moddown_ordinary<<<ew_grid(N, L - Ls), EW_THREADS, 0, S(stream)>>>(dh, N, L, K, N, lv->Rs, lv->PiR, eff, adds[h],
+                                                                                add_stride, outs[h], out_stride, Ls, m);
+            RC(launch_status());
+        }
+    }
+    return 0;
 }
 
 int64_t ckks_exec_keyswitch_ws_elems(int L, int K, int nparts, int N) {

@@ -386,15 +386,14 @@ __global__ void __launch_bounds__(NTT_THREADS, 3) fast_fwd_colpass(const FastArg
         fast_fwd_col_body<ArithU64, false>(F, sm, limb);
 }
 
-// ---- forward pass A with the ModUp basis extension fused into the load (key switch) ---------------------------
-// Row r of the output block is (partition p = r / E, target limb t = r % E).  Instead of reading an extended
-// polynomial from memory, every coefficient is rebuilt from the partition's Garner digits s_0..s_{alpha-1}
-// (exact integers, engine.py:654-705) by Horner's rule in the target field,
+// ---- ModUp basis extension for the fast path ---------------------------------------------------------------------
+// One thread owns two coefficients of ONE partition, loads its Garner digits s_0..s_{alpha-1} (exact integers,
+// engine.py:654-705) once, and then walks over ALL E target limbs: by Horner's rule in the target field
 //      X = s_0 + m_0 (s_1 + m_1 (s_2 + ...)),   ext = X * R   (== extend, engine.py:707-743, up to congruence)
-// -- in FP64 for scale-prime targets (digits of scale-prime partitions are < 2^43; the single 60-bit digit of the
-// base-prime partition is split into 31-bit halves first), with the reference's Montgomery chain for 60-bit targets.
+// in FP64 for scale-prime targets (digits of scale-prime partitions are < 2^44; the single 60-bit digit of the
+// base-prime partition is split into 31-bit halves), with the reference's Montgomery chain for 60-bit targets.
+// The digits are read once instead of once per target; stores are coalesced 16-byte writes per target row.
 struct ExtArgs {
-    FastArgs F;
     const int64_t* const* digit_ptrs;   // [P] -> [alpha][N] digit blocks, rows d_stride apart
     long long d_stride;
     const int32_t* alphas;              // [P]
@@ -404,93 +403,184 @@ struct ExtArgs {
     const double* C31;                  // [E] 2^31 mod q_t
     const int64_t* const* Lenter;       // [P] -> [(alpha-1)][E] (L_i R^2) mod q_t      (60-bit targets)
     const int64_t* Rs;                  // [E] R^2 mod q_t
-    const int64_t *_2q, *ql, *qh, *kl, *kh;
-    int E;
+    const int64_t *q, *_2q, *ql, *qh, *kl, *kh;
+    int64_t* out;                       // [P*E][N], row p*E + t
+    int E, N;
 };
 
-__device__ __forceinline__ double ext_value_f64(const ExtArgs& X, int p, int t, long long j, int alpha, bool wide,
-                                                const F64C& c, double Rd, double c31) {
-    const int64_t* __restrict__ st = X.digit_ptrs[p];
-    double acc;
-    if (wide) {   // alpha == 1, digit up to 2^60: hi * 2^31 + lo
-        const int64_t s0 = st[j];
-        const double hi = (double)(int)(s0 >> 31), lo = (double)(int)(s0 & 0x7FFFFFFF);
-        acc = __dadd_rn(f64_mulmod(hi, c31, c), lo);
-    } else {
-        const double* __restrict__ hm = X.Hm[p];
-        acc = i2d(st[(long long)(alpha - 1) * X.d_stride + j]);
-        for (int i = alpha - 2; i >= 0; --i)
-            acc = __dadd_rn(f64_mulmod(acc, hm[(long long)i * X.E + t], c), i2d(st[(long long)i * X.d_stride + j]));
-    }
-    return f64_mulmod(acc, Rd, c);
-}
+constexpr int EXT_MAX_ALPHA = 8;
 
-__device__ __forceinline__ uint64_t ext_value_u64(const ExtArgs& X, int p, int t, long long j, int alpha,
-                                                  const LimbConst& k) {
-    const int64_t* __restrict__ st = X.digit_ptrs[p];
-    const int64_t* __restrict__ le = X.Lenter[p];
-    const int64_t q2 = (int64_t)k.q2;
-    int64_t acc = mont_mul_ss(st[j], X.Rs[t], k.q4, k.k);
-    for (int i = 0; i < alpha - 1; ++i)
-        acc = lazy_add(acc, mont_mul_ss(st[(long long)(i + 1) * X.d_stride + j], le[(long long)i * X.E + t], k.q4, k.k), q2);
-    acc += (acc < 0) ? q2 : 0;
-    return (uint64_t)acc;
-}
-
-template <int DUMMY>
-__global__ void __launch_bounds__(NTT_THREADS, 3) fast_fwd_colpass_ext(const ExtArgs X) {
-    extern __shared__ __align__(16) int64_t sm[];
-    const FastArgs& F = X.F;
-    const int row = blockIdx.y;
-    const int p = row / X.E, t = row - p * X.E;
-    const int tau = threadIdx.x;
-    const int b = F.logN - 8;
+__global__ void __launch_bounds__(256) k_extend_fast(const ExtArgs X) {
+    const int p = blockIdx.y;
+    const long long j = 2ll * (blockIdx.x * 256 + threadIdx.x);
+    if (j >= X.N) return;
     const int alpha = X.alphas[p];
-    int64_t* __restrict__ row0 = F.a + (long long)row * F.a_stride + (long long)blockIdx.x * 16;
-    const long long col0 = (long long)blockIdx.x * 16;
-    const uint64_t q = (uint64_t)F.q[t];
-    if (q < SMALL_PRIME_LIMIT) {
-        using A = ArithF64;
-        const F64C c = make_const<A>(q);
-        const double* __restrict__ W = tw_row<A>(F, t);
-        double* tws = reinterpret_cast<double*>(sm + SMEM_SLOTS);
-        uint64_t* bar = reinterpret_cast<uint64_t*>(sm + SMEM_SLOTS + FAST_TW_SLOTS);
-        stage_col_twiddles(W, tws, bar);
-        double e[16];
-        const bool wide = X.wide[p] != 0;
-        const double Rd = X.Rd[t], c31 = X.C31[t];
-        const int r0 = tau >> 4, col = tau & 15;
+    const bool wide = X.wide[p] != 0;
+    const int64_t* __restrict__ st = X.digit_ptrs[p];
+    longlong2 s[EXT_MAX_ALPHA];
 #pragma unroll
-        for (int k = 0; k < 16; ++k)
-            e[k] = ext_value_f64(X, p, t, ((long long)(r0 + 16 * k) << b) + col0 + col, alpha, wide, c, Rd, c31);
-        mbar_wait(bar, 0);
-        fast_fwd_round<A, 0>(e, TwSharedCol<double>{tws, 0, 0u}, c);
-        smx_store(sm, e, tau, 8);
-        __syncthreads();
-        smx_load(sm, e, tau, 4);
-        const int hi = tau >> 4;
-        fast_fwd_round<A, 0>(e, TwSharedCol<double>{tws, 4, (unsigned)hi}, c);
-#pragma unroll
-        for (int k = 0; k < 16; ++k) row0[((long long)(hi * 16 + k) << b) + col] = A::store_lazy(e[k], c);
+    for (int i = 0; i < EXT_MAX_ALPHA; ++i)
+        if (i < alpha) s[i] = *reinterpret_cast<const longlong2*>(st + (long long)i * X.d_stride + j);
+    double dx[EXT_MAX_ALPHA], dy[EXT_MAX_ALPHA];
+    if (wide) {
+        dx[0] = (double)(int)(s[0].x >> 31); dy[0] = (double)(int)(s[0].y >> 31);
+        dx[1] = (double)(int)(s[0].x & 0x7FFFFFFF); dy[1] = (double)(int)(s[0].y & 0x7FFFFFFF);
     } else {
-        using A = ArithU64;
-        const U64C c = make_const<A>(q);
-        const LimbConst lk = load_limb_const(X._2q, X.ql, X.qh, X.kl, X.kh, t);
-        const ulonglong2* __restrict__ W = tw_row<A>(F, t);
-        uint64_t e[16];
-        const int r0 = tau >> 4, col = tau & 15;
 #pragma unroll
-        for (int k = 0; k < 16; ++k)
-            e[k] = ext_value_u64(X, p, t, ((long long)(r0 + 16 * k) << b) + col0 + col, alpha, lk);
-        fast_fwd_round<A, 0>(e, TwGlobal<ulonglong2>{W, 0, 0u}, c);
-        smx_store(sm, e, tau, 8);
-        __syncthreads();
-        smx_load(sm, e, tau, 4);
-        const int hi = tau >> 4;
-        fast_fwd_round<A, 0>(e, TwGlobal<ulonglong2>{W, 4, (unsigned)hi}, c);
-#pragma unroll
-        for (int k = 0; k < 16; ++k) row0[((long long)(hi * 16 + k) << b) + col] = A::store_lazy(e[k], c);
+        for (int i = 0; i < EXT_MAX_ALPHA; ++i)
+            if (i < alpha) { dx[i] = i2d(s[i].x); dy[i] = i2d(s[i].y); }
     }
+    const double* __restrict__ hm = X.Hm[p];
+    const int64_t* __restrict__ le = X.Lenter[p];
+    int64_t* __restrict__ out = X.out + ((long long)p * X.E) * X.N + j;
+    for (int t = 0; t < X.E; ++t) {
+        const uint64_t q = (uint64_t)X.q[t];
+        longlong2 r;
+        if (q < SMALL_PRIME_LIMIT) {
+            const F64C c{(double)q, 1.0 / (double)q};
+            double ax, ay;
+            if (wide) {
+                const double c31 = X.C31[t];
+                ax = __dadd_rn(f64_mulmod(dx[0], c31, c), dx[1]);
+                ay = __dadd_rn(f64_mulmod(dy[0], c31, c), dy[1]);
+            } else {
+                ax = 0.0;
+                ay = 0.0;
+#pragma unroll
+                for (int i = EXT_MAX_ALPHA - 1; i >= 0; --i) {
+                    if (i == alpha - 1) {
+                        ax = dx[i];
+                        ay = dy[i];
+                    } else if (i < alpha - 1) {
+                        const double m = hm[(long long)i * X.E + t];
+                        ax = __dadd_rn(f64_mulmod(ax, m, c), dx[i]);
+                        ay = __dadd_rn(f64_mulmod(ay, m, c), dy[i]);
+                    }
+                }
+            }
+            const double Rd = X.Rd[t];
+            r.x = d2i(f64_mulmod(ax, Rd, c));
+            r.y = d2i(f64_mulmod(ay, Rd, c));
+        } else {
+            const LimbConst k = load_limb_const(X._2q, X.ql, X.qh, X.kl, X.kh, t);
+            const int64_t q2 = (int64_t)k.q2, rs = X.Rs[t];
+            r.x = mont_mul_ss(s[0].x, rs, k.q4, k.k);
+            r.y = mont_mul_ss(s[0].y, rs, k.q4, k.k);
+#pragma unroll
+            for (int i = 0; i < EXT_MAX_ALPHA - 1; ++i) {
+                if (i < alpha - 1) {
+                    const int64_t l = le[(long long)i * X.E + t];
+                    r.x = lazy_add(r.x, mont_mul_ss(s[i + 1].x, l, k.q4, k.k), q2);
+                    r.y = lazy_add(r.y, mont_mul_ss(s[i + 1].y, l, k.q4, k.k), q2);
+                }
+            }
+            r.x += (r.x < 0) ? q2 : 0;
+            r.y += (r.y < 0) ? q2 : 0;
+        }
+        *reinterpret_cast<longlong2*>(out + (long long)t * X.N) = r;
+    }
+}
+
+// ---- evaluation-key inner product for the fast path ------------------------------------------------------------
+// acc_h[t] = R^-1 * sum_p ext[p][t] * key_h[p][t]  (== the Montgomery products + running mont_add of
+// engine.py:906-937, 832-840 up to congruence).  FP64 for scale-prime rows, Montgomery for the 60-bit rows.
+struct InnerArgs {
+    const int64_t* ext;                 // [P*E][N] canonical NTT-domain values, row p*E + t
+    const int64_t* const* k0;           // [P] row-0 pointers of the key halves (rows k_stride apart)
+    const int64_t* const* k1;
+    long long k_stride;
+    int64_t *acc0, *acc1;               // [E][N]
+    const double* Rinv;                 // [E] R^-1 mod q_t
+    const int64_t *q, *_2q, *ql, *qh, *kl, *kh;
+    int P, E, N;
+};
+
+__global__ void __launch_bounds__(256) k_ksk_inner_fast(const InnerArgs X) {
+    const int t = blockIdx.y;
+    const long long j = 2ll * (blockIdx.x * 256 + threadIdx.x);
+    if (j >= X.N) return;
+    const uint64_t q = (uint64_t)X.q[t];
+    longlong2 r0, r1;
+    if (q < SMALL_PRIME_LIMIT) {
+        const F64C c{(double)q, 1.0 / (double)q};
+        double a0x = 0.0, a0y = 0.0, a1x = 0.0, a1y = 0.0;
+        for (int p = 0; p < X.P; ++p) {
+            const longlong2 e = *reinterpret_cast<const longlong2*>(X.ext + ((long long)p * X.E + t) * X.N + j);
+            const longlong2 u = *reinterpret_cast<const longlong2*>(X.k0[p] + (long long)t * X.k_stride + j);
+            const longlong2 v = *reinterpret_cast<const longlong2*>(X.k1[p] + (long long)t * X.k_stride + j);
+            const double ex = i2d(e.x), ey = i2d(e.y);
+            a0x = __dadd_rn(a0x, f64_mulmod(ex, i2d(u.x), c));
+            a0y = __dadd_rn(a0y, f64_mulmod(ey, i2d(u.y), c));
+            a1x = __dadd_rn(a1x, f64_mulmod(ex, i2d(v.x), c));
+            a1y = __dadd_rn(a1y, f64_mulmod(ey, i2d(v.y), c));
+        }
+        const double ri = X.Rinv[t];
+        r0.x = d2i(f64_mulmod(a0x, ri, c));
+        r0.y = d2i(f64_mulmod(a0y, ri, c));
+        r1.x = d2i(f64_mulmod(a1x, ri, c));
+        r1.y = d2i(f64_mulmod(a1y, ri, c));
+    } else {
+        const LimbConst k = load_limb_const(X._2q, X.ql, X.qh, X.kl, X.kh, t);
+        const int64_t q2 = (int64_t)k.q2;
+        r0 = make_longlong2(0, 0);
+        r1 = make_longlong2(0, 0);
+        for (int p = 0; p < X.P; ++p) {
+            const longlong2 e = *reinterpret_cast<const longlong2*>(X.ext + ((long long)p * X.E + t) * X.N + j);
+            const longlong2 u = *reinterpret_cast<const longlong2*>(X.k0[p] + (long long)t * X.k_stride + j);
+            const longlong2 v = *reinterpret_cast<const longlong2*>(X.k1[p] + (long long)t * X.k_stride + j);
+            r0.x = lazy_add(r0.x, mont_mul_ss(e.x, u.x, k.q4, k.k), q2);
+            r0.y = lazy_add(r0.y, mont_mul_ss(e.y, u.y, k.q4, k.k), q2);
+            r1.x = lazy_add(r1.x, mont_mul_ss(e.x, v.x, k.q4, k.k), q2);
+            r1.y = lazy_add(r1.y, mont_mul_ss(e.y, v.y, k.q4, k.k), q2);
+        }
+    }
+    *reinterpret_cast<longlong2*>(X.acc0 + (long long)t * X.N + j) = r0;
+    *reinterpret_cast<longlong2*>(X.acc1 + (long long)t * X.N + j) = r1;
+}
+
+// ---- ModDown for the fast path (ordinary rows) -------------------------------------------------------------------
+// out_t = [add_t +] (...((D_t - s_0) P_0^-1 - s_1) P_1^-1 ...) mod q_t, canonical, where s_i are the EXACT effective
+// special-limb values produced by k_moddown_special (they can exceed 2^51: split into 31-bit halves).
+// Same value as engine.py:851-901 (+ :1135-1140 / :947-948), whose ordinary rows end in reduce_2q.
+struct ModDownArgs {
+    const int64_t* d;                   // [E][N] plain canonical rows (ordinary first)
+    const int64_t* eff;                 // [K][N] effective special values (exact integers in [0, 2 q_special))
+    const int64_t* add;                 // optional [L][N] (row stride add_stride)
+    long long add_stride;
+    int64_t* out;                       // [L][N]
+    long long out_stride;
+    const double* Pinv;                 // [K][E] P_i^-1 mod q_t as doubles
+    const double* C31;                  // [E]
+    const int64_t* q;
+    int L, K, E, N;
+};
+
+__global__ void __launch_bounds__(256) k_moddown_fast(const ModDownArgs X) {
+    const int t = blockIdx.y;
+    const long long j = 2ll * (blockIdx.x * 256 + threadIdx.x);
+    if (j >= X.N) return;
+    const uint64_t q = (uint64_t)X.q[t];
+    const F64C c{(double)q, 1.0 / (double)q};
+    const double c31 = X.C31[t];
+    const longlong2 dv = *reinterpret_cast<const longlong2*>(X.d + (long long)t * X.N + j);
+    double vx = i2d(dv.x), vy = i2d(dv.y);
+    for (int i = 0; i < X.K; ++i) {
+        const longlong2 s = *reinterpret_cast<const longlong2*>(X.eff + (long long)i * X.N + j);
+        const double sx = __dadd_rn(f64_mulmod((double)(int)(s.x >> 31), c31, c), (double)(int)(s.x & 0x7FFFFFFF));
+        const double sy = __dadd_rn(f64_mulmod((double)(int)(s.y >> 31), c31, c), (double)(int)(s.y & 0x7FFFFFFF));
+        const double pinv = X.Pinv[(long long)i * X.E + t];
+        vx = f64_mulmod(__dadd_rn(vx, -sx), pinv, c);
+        vy = f64_mulmod(__dadd_rn(vy, -sy), pinv, c);
+    }
+    if (X.add) {
+        const longlong2 a = *reinterpret_cast<const longlong2*>(X.add + (long long)t * X.add_stride + j);
+        vx = __dadd_rn(vx, i2d(a.x));
+        vy = __dadd_rn(vy, i2d(a.y));
+    }
+    longlong2 r;
+    r.x = ArithF64::store_canon(vx, c, false);
+    r.y = ArithF64::store_canon(vy, c, false);
+    *reinterpret_cast<longlong2*>(X.out + (long long)t * X.out_stride + j) = r;
 }
 
 // ---- forward pass B (block pass, stages 8..logN-1), canonical [0,q) out --------------------------------------

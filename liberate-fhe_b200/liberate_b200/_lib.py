@@ -82,7 +82,7 @@ def _load():
 
 # kernels launched per entry point (for bench.py's gpu_launches accounting)
 KERNELS_PER_CALL = {"ckks_abi_version": 0, "ckks_ntt": 2, "ckks_intt": 2, "ckks_moddown": 2, "ckks_ntt_fast": 2,
-                    "ckks_intt_fast": 2, "ckks_exec_tensor_stage": 10, "ckks_exec_keyswitch_stage": 10,
+                    "ckks_intt_fast": 2, "ckks_exec_tensor_stage": 10, "ckks_exec_keyswitch_stage": 12,
                     "ckks_exec_keyswitch_ws_elems": 0}
 
 

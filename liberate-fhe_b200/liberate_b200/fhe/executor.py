@@ -26,7 +26,8 @@ class LevelT(ctypes.Structure):
                 ("PiR", _vp), ("part_alpha", _vp), ("Lenter", _vp),
                 ("loc_row0", _vp), ("loc_alpha", _vp), ("loc_Y", _vp), ("loc_Ltri", _vp),
                 ("rescale_scale", _vp), ("round_at", ctypes.c_int64),
-                ("part_wide", _vp), ("Hm", _vp), ("Rd", _vp), ("C31", _vp)]
+                ("part_wide", _vp), ("Hm", _vp), ("Rd", _vp), ("C31", _vp),
+                ("Rinv", _vp), ("Pinv", _vp), ("L_small", ctypes.c_int32), ("_pad2", ctypes.c_int32)]
 
 
 def _p(t):
@@ -123,6 +124,13 @@ class LevelPlan:
         d.Hm = _p(i64(hm_ptrs))
         d.Rd = _p(f64([float(eng.ctx.R % qt) for qt in qrows]))
         d.C31 = _p(f64([float((1 << 31) % qt) for qt in qrows]))
+        d.Rinv = _p(f64([float(pow(eng.ctx.R, -1, qt)) for qt in qrows]))
+        specials = eng.ctx.q[-K:][::-1]
+        d.Pinv = _p(f64([[float(pow(Pj, -1, qt)) if qt != Pj else 0.0 for qt in qrows] for Pj in specials]))
+        n_small = 0
+        while n_small < self.L and qrows[n_small] < SMALL:
+            n_small += 1
+        d.L_small = n_small
         self.desc = d
         self.ref = ctypes.byref(d)
         self._keep = keep
