@@ -173,7 +173,7 @@ typedef struct {
     const double *Rd, *C31;                                   /* [E] R mod q_t, 2^31 mod q_t as doubles          */
     const double* Rinv;                                       /* [E] R^-1 mod q_t (FP64 inner product), or NULL  */
     const double* Pinv;                                       /* [K][E] P_i^-1 mod q_t (FP64 ModDown), or NULL   */
-    int32_t L_small, _pad2;                                   /* leading ordinary rows with q < 2^42             */
+    int32_t L_small, amax;                                    /* leading ordinary rows with q < 2^42; max alpha  */
 } ckks_level_t;
 
 /* rescale x4 -> batched enter+NTT -> tensor product -> batched iNTT+exit -> Garner digits of d2

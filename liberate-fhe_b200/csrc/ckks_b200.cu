@@ -602,7 +602,7 @@ int ckks_ntt_fast(int64_t* a, int64_t as, int rows, int period, int logN, const 
     if (!force_int && !tw_f64) return CKKS_E_BADARG;
     if (logN < 12 || logN > 17) return CKKS_E_LOGN;
     if (!row_ok(a, as) || !aligned16(tw_u64) || (tw_f64 && !aligned16(tw_f64))) return CKKS_E_ALIGN;
-    FastArgs F{a, as, reinterpret_cast<const ulonglong2*>(tw_u64), tw_f64, q, scal, scal_sh, period, logN, 0, force_int};
+    FastArgs F{a, as, reinterpret_cast<const ulonglong2*>(tw_u64), tw_f64, q, scal, scal_sh, period, logN, 0, force_int, 0, 0, 0};
     cudaStream_t st = S(stream);
     const dim3 grid((1 << logN) / TILE, rows);
     cudaFuncSetAttribute(fast_fwd_colpass<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, FAST_SMEM_BYTES);
@@ -629,7 +629,7 @@ int ckks_intt_fast(int64_t* a, int64_t as, int rows, int period, int logN, const
     if (!force_int && !tw_f64) return CKKS_E_BADARG;
     if (logN < 12 || logN > 17) return CKKS_E_LOGN;
     if (!row_ok(a, as) || !aligned16(tw_u64) || (tw_f64 && !aligned16(tw_f64))) return CKKS_E_ALIGN;
-    FastArgs F{a, as, reinterpret_cast<const ulonglong2*>(tw_u64), tw_f64, q, scal, scal_sh, period, logN, centred, force_int};
+    FastArgs F{a, as, reinterpret_cast<const ulonglong2*>(tw_u64), tw_f64, q, scal, scal_sh, period, logN, centred, force_int, 0, 0, 0};
     cudaStream_t st = S(stream);
     const dim3 grid((1 << logN) / TILE, rows);
     int rc = CKKS_E_LOGN;
@@ -782,8 +782,9 @@ int ckks_exec_keyswitch_stage(const ckks_level_t* lv, const int64_t* const* digi
     int64_t* acc = ext + (long long)P * E * N;          // [2E][N]
     int64_t* eff = acc + 2ll * E * N;                   // [K][N]
     const MontPack m{lv->_2q, lv->ql, lv->qh, lv->kl, lv->kh};
-    if (lv->Hm) {
-        // FP64-Horner / Montgomery basis extension (digits read once per partition), then the batched transform
+    if (lv->Hm && lv->Rinv) {
+        // Slab pipeline over target limbs [t0, t1): extend -> column pass -> block pass -> inner product, slab sized so
+        // that the extended block stays L2-resident between the four kernels (only the evaluation key streams from HBM).
         ExtArgs X{};
         X.digit_ptrs = digit_ptrs;
         X.d_stride = digit_stride;
@@ -798,21 +799,43 @@ int ckks_exec_keyswitch_stage(const ckks_level_t* lv, const int64_t* const* digi
         X.out = ext;
         X.E = E;
         X.N = N;
-        k_extend_fast<<<dim3((N / 2 + 255) / 256, P), 256, 0, S(stream)>>>(X);
-        RC(launch_status());
-        RC(ckks_ntt_fast(ext, N, P * E, E, lv->logN, lv->twf_u64, lv->twf_f64, lv->q, nullptr, nullptr, 0, stream));
+        const long long slab_budget = 64ll << 20;   // bytes of extended rows per slab
+        const long long all_bytes = (long long)P * E * N * 8;
+        const int nslabs = (int)((all_bytes + slab_budget - 1) / slab_budget);
+        const int slab = (E + nslabs - 1) / nslabs;
+        cudaStream_t st = S(stream);
+        for (int t0 = 0; t0 < E; t0 += slab) {
+            const int t1 = (t0 + slab < E) ? t0 + slab : E;
+            const dim3 eg((N / 2 + 255) / 256, P);
+            if (lv->amax <= 2) k_extend_fast<2><<<eg, 256, 0, st>>>(X, t0, t1);
+            else if (lv->amax <= 4) k_extend_fast<4><<<eg, 256, 0, st>>>(X, t0, t1);
+            else k_extend_fast<8><<<eg, 256, 0, st>>>(X, t0, t1);
+            RC(launch_status());
+            FastArgs F{ext, N, reinterpret_cast<const ulonglong2*>(lv->twf_u64), lv->twf_f64, lv->q, nullptr, nullptr, E,
+                       lv->logN, 0, 0, t1 - t0, E, t0};
+            const dim3 grid(N / TILE, P * (t1 - t0));
+            cudaFuncSetAttribute(fast_fwd_colpass<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, FAST_SMEM_BYTES);
+            fast_fwd_colpass<0><<<grid, NTT_THREADS, FAST_SMEM_BYTES, st>>>(F);
+            RC(launch_status());
+            switch (lv->logN - 8) {
+                case 4: RC(launch_fast_fwd_block<4>(F, grid, st)); break;
+                case 5: RC(launch_fast_fwd_block<5>(F, grid, st)); break;
+                case 6: RC(launch_fast_fwd_block<6>(F, grid, st)); break;
+                case 7: RC(launch_fast_fwd_block<7>(F, grid, st)); break;
+                case 8: RC(launch_fast_fwd_block<8>(F, grid, st)); break;
+                case 9: RC(launch_fast_fwd_block<9>(F, grid, st)); break;
+                default: return CKKS_E_LOGN;
+            }
+            InnerArgs I{ext, k0_ptrs, k1_ptrs, ksk_stride, acc, acc + (long long)E * N, lv->Rinv, lv->q, lv->_2q, lv->ql, lv->qh,
+                        lv->kl, lv->kh, P, E, N, t0};
+            k_ksk_inner_fast<<<dim3((N / 2 + 255) / 256, t1 - t0), 256, 0, st>>>(I);
+            RC(launch_status());
+        }
     } else {
         k_extend_batched<<<ew_grid(N, P * E), EW_THREADS, 0, S(stream)>>>(digit_ptrs, digit_stride, lv->part_alpha, ext, N, E,
                                                                           N, lv->Rs, lv->Lenter, m);
         RC(launch_status());
         RC(ckks_ntt_fast(ext, N, P * E, E, lv->logN, lv->twf_u64, lv->twf_f64, lv->q, nullptr, nullptr, 0, stream));
-    }
-    if (lv->Rinv) {
-        InnerArgs I{ext, k0_ptrs, k1_ptrs, ksk_stride, acc, acc + (long long)E * N, lv->Rinv, lv->q, lv->_2q, lv->ql, lv->qh,
-                    lv->kl, lv->kh, P, E, N};
-        k_ksk_inner_fast<<<dim3((N / 2 + 255) / 256, E), 256, 0, S(stream)>>>(I);
-        RC(launch_status());
-    } else {
         RC(ckks_ksk_inner(ext, N, P, k0_ptrs, k1_ptrs, ksk_stride, acc, acc + (long long)E * N, N, E, N, lv->_2q, lv->ql,
                           lv->qh, lv->kl, lv->kh, stream));
     }

@@ -249,7 +249,21 @@ struct FastArgs {
     int logN;
     int centred;                // inverse only: output in (-q/2, q/2] instead of [0, q)
     int force_int;              // 1: use the integer path for every limb (pipe balancing / testing)
+    // slab view of a [groups][group_rows] block: grid row r -> group r / slab_rows, member r % slab_rows;
+    // data row = group * group_rows + slab_t0 + member, limb = slab_t0 + member.  slab_rows == 0: plain rows.
+    int slab_rows, group_rows, slab_t0;
 };
+
+struct RowId {
+    long long data_row;
+    int limb;
+};
+__device__ __forceinline__ RowId fast_row(const FastArgs& F) {
+    const int r = blockIdx.y;
+    if (F.slab_rows == 0) return RowId{r, r % F.period};
+    const int g = r / F.slab_rows, m = r - g * F.slab_rows;
+    return RowId{(long long)g * F.group_rows + F.slab_t0 + m, F.slab_t0 + m};
+}
 
 template <class A>
 __device__ __forceinline__ typename A::C make_const(uint64_t q);
@@ -334,13 +348,13 @@ __device__ __forceinline__ void stage_col_twiddles(const double* __restrict__ W,
 
 // ---- forward pass A (column pass, stages 0..7) -------------------------------------------------------------
 template <class A, bool STAGED>
-__device__ __forceinline__ void fast_fwd_col_body(const FastArgs& F, int64_t* sm, int limb) {
+__device__ __forceinline__ void fast_fwd_col_body(const FastArgs& F, int64_t* sm, int limb, long long drow) {
     using T = typename A::T;
     using TW = typename A::TW;
     const int tau = threadIdx.x;
     const int b = F.logN - 8;
     const typename A::C c = make_const<A>((uint64_t)F.q[limb]);
-    int64_t* __restrict__ row0 = F.a + (long long)blockIdx.y * F.a_stride + (long long)blockIdx.x * 16;
+    int64_t* __restrict__ row0 = F.a + drow * F.a_stride + (long long)blockIdx.x * 16;
     const TW* __restrict__ W = tw_row<A>(F, limb);
     TW* tws = reinterpret_cast<TW*>(sm + SMEM_SLOTS);
     uint64_t* bar = reinterpret_cast<uint64_t*>(sm + SMEM_SLOTS + FAST_TW_SLOTS);
@@ -379,11 +393,12 @@ __device__ __forceinline__ void fast_fwd_col_body(const FastArgs& F, int64_t* sm
 template <int DUMMY>
 __global__ void __launch_bounds__(NTT_THREADS, 3) fast_fwd_colpass(const FastArgs F) {
     extern __shared__ __align__(16) int64_t sm[];
-    const int limb = blockIdx.y % F.period;
+    const RowId rid = fast_row(F);
+    const int limb = rid.limb;
     if (!F.force_int && (uint64_t)F.q[limb] < SMALL_PRIME_LIMIT)
-        fast_fwd_col_body<ArithF64, true>(F, sm, limb);
+        fast_fwd_col_body<ArithF64, true>(F, sm, limb, rid.data_row);
     else
-        fast_fwd_col_body<ArithU64, false>(F, sm, limb);
+        fast_fwd_col_body<ArithU64, false>(F, sm, limb, rid.data_row);
 }
 
 // ---- ModUp basis extension for the fast path ---------------------------------------------------------------------
@@ -408,77 +423,85 @@ struct ExtArgs {
     int E, N;
 };
 
-constexpr int EXT_MAX_ALPHA = 8;
+template <int AMAX>
+__device__ __forceinline__ void ext_target(const ExtArgs& X, int p, int t, int alpha, bool wide, const longlong2 (&s)[AMAX],
+                                           const double (&dx)[AMAX], const double (&dy)[AMAX], const double* __restrict__ hm,
+                                           const int64_t* __restrict__ le, int64_t* __restrict__ out) {
+    const uint64_t q = (uint64_t)X.q[t];
+    longlong2 r;
+    if (q < SMALL_PRIME_LIMIT) {
+        const F64C c{(double)q, 1.0 / (double)q};
+        double ax = 0.0, ay = 0.0;
+        if (wide) {
+            const double c31 = X.C31[t];
+            ax = __dadd_rn(f64_mulmod(dx[0], c31, c), dx[1]);
+            ay = __dadd_rn(f64_mulmod(dy[0], c31, c), dy[1]);
+        } else {
+#pragma unroll
+            for (int i = AMAX - 1; i >= 0; --i) {
+                if (i == alpha - 1) {
+                    ax = dx[i];
+                    ay = dy[i];
+                } else if (i < alpha - 1) {
+                    const double m = hm[(long long)i * X.E + t];
+                    ax = __dadd_rn(f64_mulmod(ax, m, c), dx[i]);
+                    ay = __dadd_rn(f64_mulmod(ay, m, c), dy[i]);
+                }
+            }
+        }
+        const double Rd = X.Rd[t];
+        r.x = d2i(f64_mulmod(ax, Rd, c));
+        r.y = d2i(f64_mulmod(ay, Rd, c));
+    } else {
+        const LimbConst k = load_limb_const(X._2q, X.ql, X.qh, X.kl, X.kh, t);
+        const int64_t q2 = (int64_t)k.q2, rs = X.Rs[t];
+        r.x = mont_mul_ss(s[0].x, rs, k.q4, k.k);
+        r.y = mont_mul_ss(s[0].y, rs, k.q4, k.k);
+#pragma unroll
+        for (int i = 0; i < AMAX - 1; ++i) {
+            if (i < alpha - 1) {
+                const int64_t l = le[(long long)i * X.E + t];
+                r.x = lazy_add(r.x, mont_mul_ss(s[i + 1].x, l, k.q4, k.k), q2);
+                r.y = lazy_add(r.y, mont_mul_ss(s[i + 1].y, l, k.q4, k.k), q2);
+            }
+        }
+        r.x += (r.x < 0) ? q2 : 0;
+        r.y += (r.y < 0) ? q2 : 0;
+    }
+    *reinterpret_cast<longlong2*>(out + (long long)t * X.N) = r;
+}
 
-__global__ void __launch_bounds__(256) k_extend_fast(const ExtArgs X) {
+// AMAX = capacity of the per-thread digit arrays (>= alpha, and >= 2 for the 31-bit split of a wide digit)
+template <int AMAX>
+__global__ void __launch_bounds__(256) k_extend_fast(const ExtArgs X, int t0, int t1) {
     const int p = blockIdx.y;
     const long long j = 2ll * (blockIdx.x * 256 + threadIdx.x);
     if (j >= X.N) return;
     const int alpha = X.alphas[p];
     const bool wide = X.wide[p] != 0;
     const int64_t* __restrict__ st = X.digit_ptrs[p];
-    longlong2 s[EXT_MAX_ALPHA];
+    longlong2 s[AMAX];
+    double dx[AMAX], dy[AMAX];
 #pragma unroll
-    for (int i = 0; i < EXT_MAX_ALPHA; ++i)
+    for (int i = 0; i < AMAX; ++i) {
+        s[i] = make_longlong2(0, 0);
         if (i < alpha) s[i] = *reinterpret_cast<const longlong2*>(st + (long long)i * X.d_stride + j);
-    double dx[EXT_MAX_ALPHA], dy[EXT_MAX_ALPHA];
+        dx[i] = i2d(s[i].x);
+        dy[i] = i2d(s[i].y);
+    }
     if (wide) {
         dx[0] = (double)(int)(s[0].x >> 31); dy[0] = (double)(int)(s[0].y >> 31);
         dx[1] = (double)(int)(s[0].x & 0x7FFFFFFF); dy[1] = (double)(int)(s[0].y & 0x7FFFFFFF);
-    } else {
-#pragma unroll
-        for (int i = 0; i < EXT_MAX_ALPHA; ++i)
-            if (i < alpha) { dx[i] = i2d(s[i].x); dy[i] = i2d(s[i].y); }
     }
     const double* __restrict__ hm = X.Hm[p];
     const int64_t* __restrict__ le = X.Lenter[p];
     int64_t* __restrict__ out = X.out + ((long long)p * X.E) * X.N + j;
-    for (int t = 0; t < X.E; ++t) {
-        const uint64_t q = (uint64_t)X.q[t];
-        longlong2 r;
-        if (q < SMALL_PRIME_LIMIT) {
-            const F64C c{(double)q, 1.0 / (double)q};
-            double ax, ay;
-            if (wide) {
-                const double c31 = X.C31[t];
-                ax = __dadd_rn(f64_mulmod(dx[0], c31, c), dx[1]);
-                ay = __dadd_rn(f64_mulmod(dy[0], c31, c), dy[1]);
-            } else {
-                ax = 0.0;
-                ay = 0.0;
-#pragma unroll
-                for (int i = EXT_MAX_ALPHA - 1; i >= 0; --i) {
-                    if (i == alpha - 1) {
-                        ax = dx[i];
-                        ay = dy[i];
-                    } else if (i < alpha - 1) {
-                        const double m = hm[(long long)i * X.E + t];
-                        ax = __dadd_rn(f64_mulmod(ax, m, c), dx[i]);
-                        ay = __dadd_rn(f64_mulmod(ay, m, c), dy[i]);
-                    }
-                }
-            }
-            const double Rd = X.Rd[t];
-            r.x = d2i(f64_mulmod(ax, Rd, c));
-            r.y = d2i(f64_mulmod(ay, Rd, c));
-        } else {
-            const LimbConst k = load_limb_const(X._2q, X.ql, X.qh, X.kl, X.kh, t);
-            const int64_t q2 = (int64_t)k.q2, rs = X.Rs[t];
-            r.x = mont_mul_ss(s[0].x, rs, k.q4, k.k);
-            r.y = mont_mul_ss(s[0].y, rs, k.q4, k.k);
-#pragma unroll
-            for (int i = 0; i < EXT_MAX_ALPHA - 1; ++i) {
-                if (i < alpha - 1) {
-                    const int64_t l = le[(long long)i * X.E + t];
-                    r.x = lazy_add(r.x, mont_mul_ss(s[i + 1].x, l, k.q4, k.k), q2);
-                    r.y = lazy_add(r.y, mont_mul_ss(s[i + 1].y, l, k.q4, k.k), q2);
-                }
-            }
-            r.x += (r.x < 0) ? q2 : 0;
-            r.y += (r.y < 0) ? q2 : 0;
-        }
-        *reinterpret_cast<longlong2*>(out + (long long)t * X.N) = r;
+    int t = t0;
+    for (; t + 1 < t1; t += 2) {   // two independent targets in flight per iteration
+        ext_target<AMAX>(X, p, t, alpha, wide, s, dx, dy, hm, le, out);
+        ext_target<AMAX>(X, p, t + 1, alpha, wide, s, dx, dy, hm, le, out);
     }
+    if (t < t1) ext_target<AMAX>(X, p, t, alpha, wide, s, dx, dy, hm, le, out);
 }
 
 // ---- evaluation-key inner product for the fast path ------------------------------------------------------------
@@ -492,11 +515,11 @@ struct InnerArgs {
     int64_t *acc0, *acc1;               // [E][N]
     const double* Rinv;                 // [E] R^-1 mod q_t
     const int64_t *q, *_2q, *ql, *qh, *kl, *kh;
-    int P, E, N;
+    int P, E, N, t0;
 };
 
 __global__ void __launch_bounds__(256) k_ksk_inner_fast(const InnerArgs X) {
-    const int t = blockIdx.y;
+    const int t = X.t0 + blockIdx.y;
     const long long j = 2ll * (blockIdx.x * 256 + threadIdx.x);
     if (j >= X.N) return;
     const uint64_t q = (uint64_t)X.q[t];
@@ -572,27 +595,28 @@ __global__ void __launch_bounds__(256) k_moddown_fast(const ModDownArgs X) {
         vx = f64_mulmod(__dadd_rn(vx, -sx), pinv, c);
         vy = f64_mulmod(__dadd_rn(vy, -sy), pinv, c);
     }
-    if (X.add) {
-        const longlong2 a = *reinterpret_cast<const longlong2*>(X.add + (long long)t * X.add_stride + j);
-        vx = __dadd_rn(vx, i2d(a.x));
-        vy = __dadd_rn(vy, i2d(a.y));
-    }
     longlong2 r;
     r.x = ArithF64::store_canon(vx, c, false);
     r.y = ArithF64::store_canon(vy, c, false);
+    if (X.add) {   // the reference's integer tail mont_add + reduce_2q, exact for ANY addend (conjugate feeds signed values)
+        const longlong2 a = *reinterpret_cast<const longlong2*>(X.add + (long long)t * X.add_stride + j);
+        const int64_t qi = (int64_t)q;
+        r.x = reduce_q(lazy_add(a.x, r.x, 2 * qi), qi);
+        r.y = reduce_q(lazy_add(a.y, r.y, 2 * qi), qi);
+    }
     *reinterpret_cast<longlong2*>(X.out + (long long)t * X.out_stride + j) = r;
 }
 
 // ---- forward pass B (block pass, stages 8..logN-1), canonical [0,q) out --------------------------------------
 template <class A, int B, bool STAGED>
-__device__ __forceinline__ void fast_fwd_block_body(const FastArgs& F, int64_t* sm, int limb) {
+__device__ __forceinline__ void fast_fwd_block_body(const FastArgs& F, int64_t* sm, int limb, long long drow) {
     using T = typename A::T;
     using TW = typename A::TW;
     const int tau = threadIdx.x;
     const unsigned chunk = blockIdx.x;
     constexpr int logN = B + 8;
     const typename A::C c = make_const<A>((uint64_t)F.q[limb]);
-    int64_t* __restrict__ g = F.a + (long long)blockIdx.y * F.a_stride + (long long)chunk * TILE;
+    int64_t* __restrict__ g = F.a + drow * F.a_stride + (long long)chunk * TILE;
     const TW* __restrict__ W = tw_row<A>(F, limb);
     TW* tws = reinterpret_cast<TW*>(sm + SMEM_SLOTS);
     uint64_t* bar = reinterpret_cast<uint64_t*>(sm + SMEM_SLOTS + FAST_TW_SLOTS);
@@ -653,23 +677,24 @@ __device__ __forceinline__ void fast_fwd_block_body(const FastArgs& F, int64_t* 
 template <int B>
 __global__ void __launch_bounds__(NTT_THREADS, 3) fast_fwd_blockpass(const FastArgs F) {
     extern __shared__ __align__(16) int64_t sm[];
-    const int limb = blockIdx.y % F.period;
+    const RowId rid = fast_row(F);
+    const int limb = rid.limb;
     if (!F.force_int && (uint64_t)F.q[limb] < SMALL_PRIME_LIMIT)
-        fast_fwd_block_body<ArithF64, B, true>(F, sm, limb);
+        fast_fwd_block_body<ArithF64, B, true>(F, sm, limb, rid.data_row);
     else
-        fast_fwd_block_body<ArithU64, B, false>(F, sm, limb);
+        fast_fwd_block_body<ArithU64, B, false>(F, sm, limb, rid.data_row);
 }
 
 // ---- inverse pass B' (levels 0..B-1) ---------------------------------------------------------------------------
 template <class A, int B, bool STAGED>
-__device__ __forceinline__ void fast_inv_block_body(const FastArgs& F, int64_t* sm, int limb) {
+__device__ __forceinline__ void fast_inv_block_body(const FastArgs& F, int64_t* sm, int limb, long long drow) {
     using T = typename A::T;
     using TW = typename A::TW;
     const int tau = threadIdx.x;
     const unsigned chunk = blockIdx.x;
     constexpr int logN = B + 8;
     const typename A::C c = make_const<A>((uint64_t)F.q[limb]);
-    int64_t* __restrict__ g = F.a + (long long)blockIdx.y * F.a_stride + (long long)chunk * TILE;
+    int64_t* __restrict__ g = F.a + drow * F.a_stride + (long long)chunk * TILE;
     const TW* __restrict__ W = tw_row<A>(F, limb);
     TW* tws = reinterpret_cast<TW*>(sm + SMEM_SLOTS);
     uint64_t* bar = reinterpret_cast<uint64_t*>(sm + SMEM_SLOTS + FAST_TW_SLOTS);
@@ -730,22 +755,23 @@ __device__ __forceinline__ void fast_inv_block_body(const FastArgs& F, int64_t* 
 template <int B>
 __global__ void __launch_bounds__(NTT_THREADS, 3) fast_inv_blockpass(const FastArgs F) {
     extern __shared__ __align__(16) int64_t sm[];
-    const int limb = blockIdx.y % F.period;
+    const RowId rid = fast_row(F);
+    const int limb = rid.limb;
     if (!F.force_int && (uint64_t)F.q[limb] < SMALL_PRIME_LIMIT)
-        fast_inv_block_body<ArithF64, B, true>(F, sm, limb);
+        fast_inv_block_body<ArithF64, B, true>(F, sm, limb, rid.data_row);
     else
-        fast_inv_block_body<ArithU64, B, false>(F, sm, limb);
+        fast_inv_block_body<ArithU64, B, false>(F, sm, limb, rid.data_row);
 }
 
 // ---- inverse pass A' (levels b..logN-1), x scalar, canonical out ---------------------------------------------
 template <class A, bool STAGED>
-__device__ __forceinline__ void fast_inv_col_body(const FastArgs& F, int64_t* sm, int limb) {
+__device__ __forceinline__ void fast_inv_col_body(const FastArgs& F, int64_t* sm, int limb, long long drow) {
     using T = typename A::T;
     using TW = typename A::TW;
     const int tau = threadIdx.x;
     const int b = F.logN - 8;
     const typename A::C c = make_const<A>((uint64_t)F.q[limb]);
-    int64_t* __restrict__ row0 = F.a + (long long)blockIdx.y * F.a_stride + (long long)blockIdx.x * 16;
+    int64_t* __restrict__ row0 = F.a + drow * F.a_stride + (long long)blockIdx.x * 16;
     const TW* __restrict__ W = tw_row<A>(F, limb);
     TW* tws = reinterpret_cast<TW*>(sm + SMEM_SLOTS);
     uint64_t* bar = reinterpret_cast<uint64_t*>(sm + SMEM_SLOTS + FAST_TW_SLOTS);
@@ -781,11 +807,12 @@ __device__ __forceinline__ void fast_inv_col_body(const FastArgs& F, int64_t* sm
 template <int DUMMY>
 __global__ void __launch_bounds__(NTT_THREADS, 3) fast_inv_colpass(const FastArgs F) {
     extern __shared__ __align__(16) int64_t sm[];
-    const int limb = blockIdx.y % F.period;
+    const RowId rid = fast_row(F);
+    const int limb = rid.limb;
     if (!F.force_int && (uint64_t)F.q[limb] < SMALL_PRIME_LIMIT)
-        fast_inv_col_body<ArithF64, true>(F, sm, limb);
+        fast_inv_col_body<ArithF64, true>(F, sm, limb, rid.data_row);
     else
-        fast_inv_col_body<ArithU64, false>(F, sm, limb);
+        fast_inv_col_body<ArithU64, false>(F, sm, limb, rid.data_row);
 }
 
 // ---- table construction ----------------------------------------------------------------------------------------

@@ -27,7 +27,7 @@ class LevelT(ctypes.Structure):
                 ("loc_row0", _vp), ("loc_alpha", _vp), ("loc_Y", _vp), ("loc_Ltri", _vp),
                 ("rescale_scale", _vp), ("round_at", ctypes.c_int64),
                 ("part_wide", _vp), ("Hm", _vp), ("Rd", _vp), ("C31", _vp),
-                ("Rinv", _vp), ("Pinv", _vp), ("L_small", ctypes.c_int32), ("_pad2", ctypes.c_int32)]
+                ("Rinv", _vp), ("Pinv", _vp), ("L_small", ctypes.c_int32), ("amax", ctypes.c_int32)]
 
 
 def _p(t):
@@ -131,6 +131,7 @@ class LevelPlan:
         while n_small < self.L and qrows[n_small] < SMALL:
             n_small += 1
         d.L_small = n_small
+        d.amax = max(2, max(owners[s_][2] for s_ in self.sids))
         self.desc = d
         self.ref = ctypes.byref(d)
         self._keep = keep
