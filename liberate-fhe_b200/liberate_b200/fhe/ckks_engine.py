@@ -522,6 +522,8 @@ class ckks_engine:
             raise errors.NotMatchType(origin=sk.origin, to=types.origins["sk"])
         if (not sk.ntt_state) or (not sk.montgomery_state):
             raise errors.NotMatchDataStructState(origin=sk.origin)
+        if not self._local(0):
+            return [None]          # the base prime lives on logical device 0 (part.py:34): only that rank can decrypt
         pt = self._decrypt_rows(ct, sk)
         base_at = -self.ctx.num_special_primes - 1 if ct.include_special else -1
         return self._final_rescale(pt[0][base_at][None, :], pt[0][0][None, :], ct.level, final_round)
@@ -533,6 +535,8 @@ class ckks_engine:
         if (not sk.ntt_state) or (not sk.montgomery_state):
             raise errors.NotMatchDataStructState(origin=sk.origin)
         level = ct.level
+        if not self._local(0):
+            return None
         pt = self._decrypt_rows(ct, sk)
         base_at = -self.ctx.num_special_primes - 1 if ct.include_special else -1
         base = pt[0][base_at][None, :]
