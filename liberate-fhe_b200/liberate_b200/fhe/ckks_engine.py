@@ -175,6 +175,7 @@ class ckks_engine:
         self._ptr_cache = {}
         self._plans = {}
         self._ws = {}
+        self._dead_gather = {}
 
         P = math.prod(c.q[-K:])
         self.mont_PR = [self._t([P * c.R % c.q[i] for i in p.destination_arrays[0][dev]], dev) if self._local(dev) else None
@@ -214,29 +215,37 @@ class ckks_engine:
                         blocks[sid] = buf
                 out[dst] = blocks
             return out
-        (dst, plan), = plans.items()
+        # DistComm: ONE all_gather into a persistent buffer.  Every rank takes part, also ranks whose device holds
+        # no ordinary limb any more at this level (they contribute an empty block and receive nothing they use).
         world = self.comm.world
+        owners = self._part_owners(level)
         rows_of = [0] * world
-        for sid in plan.sids:
-            rows_of[plan.owners[sid][0]] += plan.owners[sid][2]
+        for sid, (src, _pid, alpha) in owners.items():
+            rows_of[src] += alpha
         width = max(max(rows_of), 1)
-        if "gather" not in plan.peer:
-            plan.peer["mine"] = torch.zeros((width, N), dtype=torch.int64, device=self.ntt.devices[dst])
-            plan.peer["gather"] = torch.empty((world, width, N), dtype=torch.int64, device=self.ntt.devices[dst])
-        mine, gathered = plan.peer["mine"], plan.peer["gather"]
-        r = 0
-        for sid in plan.local_sids:
-            st = plan.local_state(sid)
-            mine[r:r + st.size(0)].copy_(st)
-            r += st.size(0)
+        me = self.comm.rank
+        plan = plans.get(me)
+        store = plan.peer if plan is not None else self._dead_gather.setdefault(level, {})
+        if "gather" not in store:
+            store["mine"] = torch.zeros((width, N), dtype=torch.int64, device=self.ntt.devices[me])
+            store["gather"] = torch.empty((world, width, N), dtype=torch.int64, device=self.ntt.devices[me])
+        mine, gathered = store["mine"], store["gather"]
+        if plan is not None:
+            r = 0
+            for sid in plan.local_sids:
+                st = plan.local_state(sid)
+                mine[r:r + st.size(0)].copy_(st)
+                r += st.size(0)
         self.comm.dist.all_gather_into_tensor(gathered.view(-1, N), mine, group=self.comm.group)
+        if plan is None:
+            return {}
         cursor = [0] * world
         blocks = {}
         for sid in plan.sids:
             src, _pid, alpha = plan.owners[sid]
             blocks[sid] = gathered[src, cursor[src]:cursor[src] + alpha]
             cursor[src] += alpha
-        return {dst: blocks}
+        return {me: blocks}
 
     def _moddown_table(self, level, dev):
         """[K, E] row-major table of P_j^-1 * R for the rows of `dev` live at `level` (zero where a row is dead)"""
