@@ -55,6 +55,9 @@ struct ArithF64 {
     using C = F64C;
     static __device__ __forceinline__ T load(int64_t x) { return i2d(x); }
     static __device__ __forceinline__ int64_t store_lazy(T v, const C& c) { return d2i(f64_reduce(v, c)); }
+    // hand-off between the two passes of one transform: the raw double (|v| < 2^51 integer-valued), no conversion
+    static __device__ __forceinline__ int64_t store_mid(T v, const C& c) { return (int64_t)__double_as_longlong(v); }
+    static __device__ __forceinline__ T load_mid(int64_t x) { return __longlong_as_double((long long)x); }
     static __device__ __forceinline__ int64_t store_canon(T v, const C& c, bool centred) {
         double r = f64_reduce(v, c);
         if (!centred) r = (r < 0.0) ? __dadd_rn(r, c.q) : r;
@@ -104,6 +107,8 @@ struct ArithU64 {
     using C = U64C;
     static __device__ __forceinline__ T load(int64_t x) { return (uint64_t)x; }   // expects [0, 4q)
     static __device__ __forceinline__ int64_t store_lazy(T v, const C& c) { return (int64_t)v; }
+    static __device__ __forceinline__ int64_t store_mid(T v, const C& c) { return (int64_t)v; }
+    static __device__ __forceinline__ T load_mid(int64_t x) { return (uint64_t)x; }
     static __device__ __forceinline__ int64_t store_canon(T v, const C& c, bool centred) {
         v = (v >= c.q2) ? v - c.q2 : v;
         v = (v >= c.q2) ? v - c.q2 : v;           // [0,4q) or even [0,6q) -> [0,2q)
@@ -248,7 +253,7 @@ struct FastArgs {
     int period;                 // constants / twiddles of row r are those of limb r % period
     int logN;
     int centred;                // inverse only: output in (-q/2, q/2] instead of [0, q)
-    int force_int;              // 1: use the integer path for every limb (pipe balancing / testing)
+    int force_int;              // 1: integer path for every limb; m > 1: for every m-th row (INT + FP64 pipes side by side)
     // slab view of a [groups][group_rows] block: grid row r -> group r / slab_rows, member r % slab_rows;
     // data row = group * group_rows + slab_t0 + member, limb = slab_t0 + member.  slab_rows == 0: plain rows.
     int slab_rows, group_rows, slab_t0;
@@ -258,11 +263,18 @@ struct RowId {
     long long data_row;
     int limb;
 };
+__device__ __forceinline__ bool fast_use_f64(const FastArgs& F, const RowId& rid);
 __device__ __forceinline__ RowId fast_row(const FastArgs& F) {
     const int r = blockIdx.y;
     if (F.slab_rows == 0) return RowId{r, r % F.period};
     const int g = r / F.slab_rows, m = r - g * F.slab_rows;
     return RowId{(long long)g * F.group_rows + F.slab_t0 + m, F.slab_t0 + m};
+}
+__device__ __forceinline__ bool fast_use_f64(const FastArgs& F, const RowId& rid) {
+    if ((uint64_t)F.q[rid.limb] >= SMALL_PRIME_LIMIT) return false;
+    if (F.force_int == 0) return true;
+    if (F.force_int == 1) return false;
+    return (rid.data_row % F.force_int) != (F.force_int - 1);
 }
 
 template <class A>
@@ -386,7 +398,7 @@ __device__ __forceinline__ void fast_fwd_col_body(const FastArgs& F, int64_t* sm
         else
             fast_fwd_round<A, 0>(e, TwGlobal<TW>{W, 4, (unsigned)hi}, c);
 #pragma unroll
-        for (int k = 0; k < 16; ++k) row0[((long long)(hi * 16 + k) << b) + col] = A::store_lazy(e[k], c);
+        for (int k = 0; k < 16; ++k) row0[((long long)(hi * 16 + k) << b) + col] = A::store_mid(e[k], c);
     }
 }
 
@@ -395,7 +407,7 @@ __global__ void __launch_bounds__(NTT_THREADS, 3) fast_fwd_colpass(const FastArg
     extern __shared__ __align__(16) int64_t sm[];
     const RowId rid = fast_row(F);
     const int limb = rid.limb;
-    if (!F.force_int && (uint64_t)F.q[limb] < SMALL_PRIME_LIMIT)
+    if (fast_use_f64(F, rid))
         fast_fwd_col_body<ArithF64, true>(F, sm, limb, rid.data_row);
     else
         fast_fwd_col_body<ArithU64, false>(F, sm, limb, rid.data_row);
@@ -626,7 +638,7 @@ __device__ __forceinline__ void fast_fwd_block_body(const FastArgs& F, int64_t* 
     {
         const int zb = zbase(tau, P1);
 #pragma unroll
-        for (int k = 0; k < 16; ++k) e[k] = A::load(g[zb | (k << P1)]);
+        for (int k = 0; k < 16; ++k) e[k] = A::load_mid(g[zb | (k << P1)]);
         if constexpr (STAGED) {
             mbar_wait(bar, 0);
             fast_fwd_round<A, 0>(e, TwSharedBlock<TW>{tws, 12 - B, 0, (unsigned)(tau >> P1)}, c);
@@ -679,7 +691,7 @@ __global__ void __launch_bounds__(NTT_THREADS, 3) fast_fwd_blockpass(const FastA
     extern __shared__ __align__(16) int64_t sm[];
     const RowId rid = fast_row(F);
     const int limb = rid.limb;
-    if (!F.force_int && (uint64_t)F.q[limb] < SMALL_PRIME_LIMIT)
+    if (fast_use_f64(F, rid))
         fast_fwd_block_body<ArithF64, B, true>(F, sm, limb, rid.data_row);
     else
         fast_fwd_block_body<ArithU64, B, false>(F, sm, limb, rid.data_row);
@@ -717,7 +729,7 @@ __device__ __forceinline__ void fast_inv_block_body(const FastArgs& F, int64_t* 
     if constexpr (B == 4) {
         int64_t r[16];
 #pragma unroll
-        for (int k = 0; k < 16; ++k) r[k] = A::store_lazy(e[k], c);
+        for (int k = 0; k < 16; ++k) r[k] = A::store_mid(e[k], c);
         __syncthreads();
         sm_store_field(sm, r, tau, 0);
         __syncthreads();
@@ -743,11 +755,11 @@ __device__ __forceinline__ void fast_inv_block_body(const FastArgs& F, int64_t* 
                 fast_inv_round<A, 1>(e, TwGlobal<TW>{W, logN - 12, chunk}, c);
             const int zb = zbase(tau, 8);
 #pragma unroll
-            for (int k = 0; k < 16; ++k) g[zb | (k << 8)] = A::store_lazy(e[k], c);
+            for (int k = 0; k < 16; ++k) g[zb | (k << 8)] = A::store_mid(e[k], c);
         } else {
             const int zb = zbase(tau, 4);
 #pragma unroll
-            for (int k = 0; k < 16; ++k) g[zb | (k << 4)] = A::store_lazy(e[k], c);
+            for (int k = 0; k < 16; ++k) g[zb | (k << 4)] = A::store_mid(e[k], c);
         }
     }
 }
@@ -757,7 +769,7 @@ __global__ void __launch_bounds__(NTT_THREADS, 3) fast_inv_blockpass(const FastA
     extern __shared__ __align__(16) int64_t sm[];
     const RowId rid = fast_row(F);
     const int limb = rid.limb;
-    if (!F.force_int && (uint64_t)F.q[limb] < SMALL_PRIME_LIMIT)
+    if (fast_use_f64(F, rid))
         fast_inv_block_body<ArithF64, B, true>(F, sm, limb, rid.data_row);
     else
         fast_inv_block_body<ArithU64, B, false>(F, sm, limb, rid.data_row);
@@ -780,7 +792,7 @@ __device__ __forceinline__ void fast_inv_col_body(const FastArgs& F, int64_t* sm
     {
         const int hi = tau >> 4, col = tau & 15;
 #pragma unroll
-        for (int k = 0; k < 16; ++k) e[k] = A::load(row0[((long long)(hi * 16 + k) << b) + col]);
+        for (int k = 0; k < 16; ++k) e[k] = A::load_mid(row0[((long long)(hi * 16 + k) << b) + col]);
         if constexpr (STAGED) {
             mbar_wait(bar, 0);
             fast_inv_round<A, 4>(e, TwSharedCol<TW>{tws, 4, (unsigned)hi}, c);
@@ -809,7 +821,7 @@ __global__ void __launch_bounds__(NTT_THREADS, 3) fast_inv_colpass(const FastArg
     extern __shared__ __align__(16) int64_t sm[];
     const RowId rid = fast_row(F);
     const int limb = rid.limb;
-    if (!F.force_int && (uint64_t)F.q[limb] < SMALL_PRIME_LIMIT)
+    if (fast_use_f64(F, rid))
         fast_inv_col_body<ArithF64, true>(F, sm, limb, rid.data_row);
     else
         fast_inv_col_body<ArithU64, false>(F, sm, limb, rid.data_row);

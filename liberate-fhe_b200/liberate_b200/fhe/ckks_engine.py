@@ -708,13 +708,13 @@ class ckks_engine:
         src = self.ntt.p.rescaler_loc[level]
         n_before, n_after = self.len_devices[level], self.len_devices[nxt]
         polys = (a.data[0], a.data[1], b.data[0], b.data[1])
-        r0 = []
-        for poly in polys:
-            if isinstance(self.comm, LocalComm):
-                r0.append(self.comm.bcast(poly[src][0], src, range(n_before)))
-            else:
-                r0.append(self.comm.bcast(poly[src][0] if self._local(src) else None, src, range(n_before),
-                                          shape=(self.ctx.N,)))
+        if isinstance(self.comm, LocalComm):
+            r0 = [self.comm.bcast(poly[src][0], src, range(n_before)) for poly in polys]
+        else:
+            # ONE broadcast of the four dropped limbs, packed
+            packed = torch.stack([poly[src][0] for poly in polys]) if self._local(src) else None
+            got = self.comm.bcast(packed, src, range(n_before), shape=(4, self.ctx.N))
+            r0 = [{d: t[i] for d, t in got.items()} for i in range(4)]
         plans = {d: self._plan(nxt, d) for d in range(n_after) if self._local(d)}
         for d, plan in plans.items():
             rows = [p[d][1:] if d == src else p[d] for p in polys]
