@@ -435,8 +435,29 @@ static int launch_inv_block(const NttArgs& A, dim3 grid, cudaStream_t st) {
     return launch_status();
 }
 
+int g_persist = 1;   // 1: persistent TMA-pipelined block pass (ckks_set_option(1, v))
+int sm_count() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    }
+    return n;
+}
+
 template <int B>
 static int launch_fast_fwd_block(const FastArgs& F, dim3 grid, cudaStream_t st) {
+    if (g_persist) {
+        // rows of one launch that share a limb: plain batches rows/period, slab views rows/slab_rows
+        const int rows = grid.y;
+        const int G = F.slab_rows ? rows / F.slab_rows : rows / F.period;
+        const long long tiles = (long long)rows * grid.x;
+        const int ctas = (int)((tiles < 2ll * sm_count()) ? tiles : 2ll * sm_count());
+        cudaFuncSetAttribute(fast_fwd_blockpass_persist<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, PERSIST_SMEM_BYTES);
+        fast_fwd_blockpass_persist<B><<<ctas, NTT_THREADS, PERSIST_SMEM_BYTES, st>>>(F, tiles, G > 0 ? G : 1);
+        return launch_status();
+    }
     cudaFuncSetAttribute(fast_fwd_blockpass<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, FAST_SMEM_BYTES);
     fast_fwd_blockpass<B><<<grid, NTT_THREADS, FAST_SMEM_BYTES, st>>>(F);
     return launch_status();
@@ -459,6 +480,11 @@ static int launch_fast_inv_block(const FastArgs& F, dim3 grid, cudaStream_t st) 
 extern "C" {
 
 int ckks_abi_version(void) { return CKKS_ABI_VERSION; }
+
+int ckks_set_option(int key, int value) {
+    if (key == 1) { g_persist = value; return 0; }
+    return CKKS_E_BADARG;
+}
 
 int ckks_mont_mult(const int64_t* a, int64_t as, const int64_t* b, int64_t bs, int64_t* c, int64_t cs, int C, int N,
                    const int64_t* ql, const int64_t* qh, const int64_t* kl, const int64_t* kh, void* stream) {

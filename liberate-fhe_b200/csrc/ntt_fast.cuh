@@ -697,6 +697,166 @@ __global__ void __launch_bounds__(NTT_THREADS, 3) fast_fwd_blockpass(const FastA
         fast_fwd_block_body<ArithU64, B, false>(F, sm, limb, rid.data_row);
 }
 
+// ---- PERSISTENT forward block pass: TMA double-buffered tiles ----------------------------------------------------
+// One CTA walks a contiguous range of tiles.  While tile i is being transformed out of registers, the 32 KB of
+// tile i+1 are already in flight (one cp.async.bulk into the other buffer, completion on an mbarrier), so the
+// DRAM/L2 latency that the one-tile-per-CTA kernels expose at every CTA start is hidden behind compute.  Tiles are
+// ordered so that consecutive tiles share (limb, chunk): the staged twiddles are reused by all G rows of a batch
+// that belong to the same limb (the P partitions of a key switch, the 4 polynomials of a tensor stage, ...).
+struct TileId {
+    long long drow;
+    int limb, chunk, group;
+};
+__device__ __forceinline__ TileId decode_tile(const FastArgs& F, long long id, int G, int chunks) {
+    const int group = (int)(id / G), g = (int)(id - (long long)group * G);
+    const int m = group / chunks, chunk = group - m * chunks;
+    TileId t;
+    t.group = group;
+    t.chunk = chunk;
+    if (F.slab_rows == 0) {
+        t.limb = m;
+        t.drow = (long long)g * F.period + m;
+    } else {
+        t.limb = F.slab_t0 + m;
+        t.drow = (long long)g * F.group_rows + F.slab_t0 + m;
+    }
+    return t;
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+constexpr int PERSIST_SMEM_BYTES = 2 * SMEM_BYTES + FAST_TW_SLOTS * 8 + 32;
+
+template <class A, int B, bool STAGED>
+__device__ __forceinline__ void persist_fwd_block_tile(const FastArgs& F, int64_t* xb, const typename A::TW* tws,
+                                                       const TileId& tl, int64_t* __restrict__ gout) {
+    using T = typename A::T;
+    using TW = typename A::TW;
+    const int tau = threadIdx.x;
+    constexpr int logN = B + 8;
+    constexpr int P1 = B - 4;
+    const unsigned chunk = (unsigned)tl.chunk;
+    const typename A::C c = make_const<A>((uint64_t)F.q[tl.limb]);
+    const TW* __restrict__ W = tw_row<A>(F, tl.limb);
+    T e[16];
+    {
+        const int zb = zbase(tau, P1);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) e[k] = A::load_mid(xb[zb | (k << P1)]);   // raw (unpadded) tile as delivered by TMA
+    }
+    __syncthreads();   // the raw tile is in registers: xb becomes the padded exchange buffer
+    if constexpr (STAGED)
+        fast_fwd_round<A, 0>(e, TwSharedBlock<TW>{tws, 12 - B, 0, (unsigned)(tau >> P1)}, c);
+    else
+        fast_fwd_round<A, 0>(e, TwGlobal<TW>{W, logN - 4 - P1, (chunk << (8 - P1)) | (unsigned)(tau >> P1)}, c);
+    if constexpr (B >= 8) {
+        constexpr int P2 = B - 8;
+        smx_store(xb, e, tau, P1);
+        __syncthreads();
+        smx_load(xb, e, tau, P2);
+        if constexpr (STAGED)
+            fast_fwd_round<A, 0>(e, TwSharedBlock<TW>{tws, 12 - B, 4, (unsigned)(tau >> P2)}, c);
+        else
+            fast_fwd_round<A, 0>(e, TwGlobal<TW>{W, logN - 4 - P2, (chunk << (8 - P2)) | (unsigned)(tau >> P2)}, c);
+        if constexpr (B == 9) {
+            __syncthreads();
+            smx_store(xb, e, tau, P2);
+            __syncthreads();
+            smx_load(xb, e, tau, 0);
+            if constexpr (STAGED)
+                fast_fwd_round<A, 3>(e, TwSharedBlock<TW>{tws, 12 - B, B - 4, (unsigned)tau}, c);
+            else
+                fast_fwd_round<A, 3>(e, TwGlobal<TW>{W, logN - 4, (chunk << 8) | (unsigned)tau}, c);
+        }
+        __syncthreads();
+    } else if constexpr (B > 4) {
+        smx_store(xb, e, tau, P1);
+        __syncthreads();
+        smx_load(xb, e, tau, 0);
+        if constexpr (STAGED)
+            fast_fwd_round<A, 8 - B>(e, TwSharedBlock<TW>{tws, 12 - B, B - 4, (unsigned)tau}, c);
+        else
+            fast_fwd_round<A, 8 - B>(e, TwGlobal<TW>{W, logN - 4, (chunk << 8) | (unsigned)tau}, c);
+        __syncthreads();
+    }
+    {
+        int64_t r[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) r[k] = A::store_canon(e[k], c, false);
+        sm_store_field(xb, r, tau, 0);
+    }
+    __syncthreads();
+    sm_to_global(xb, gout, tau);
+}
+
+template <int B>
+__global__ void __launch_bounds__(NTT_THREADS, 2) fast_fwd_blockpass_persist(const FastArgs F, long long total_tiles, int G) {
+    extern __shared__ __align__(16) int64_t sm[];
+    int64_t* buf0 = sm;
+    int64_t* buf1 = sm + SMEM_SLOTS;
+    double* tws = reinterpret_cast<double*>(sm + 2 * SMEM_SLOTS);
+    uint64_t* bar_data = reinterpret_cast<uint64_t*>(sm + 2 * SMEM_SLOTS + FAST_TW_SLOTS);   // [2]
+    uint64_t* bar_tw = bar_data + 2;
+    const int tau = threadIdx.x;
+    const int chunks = (1 << (B + 8)) / TILE;
+    const long long t_begin = total_tiles * blockIdx.x / gridDim.x;
+    const long long t_end = total_tiles * (blockIdx.x + 1) / gridDim.x;
+    if (t_begin >= t_end) return;
+    if (tau == 0) {
+        mbar_init(&bar_data[0], 1);
+        mbar_init(&bar_data[1], 1);
+        mbar_init(bar_tw, 1);
+    }
+    __syncthreads();
+    auto issue_data = [&](long long id, int slot) {   // thread 0 only
+        const TileId t = decode_tile(F, id, G, chunks);
+        const int64_t* src = F.a + t.drow * F.a_stride + (long long)t.chunk * TILE;
+        uint64_t* bar = &bar_data[slot];
+        fence_async_smem();
+        mbar_expect_tx(bar, TILE * 8u);
+        tma_bulk_g2s(slot ? buf1 : buf0, src, TILE * 8u, bar);
+    };
+    if (tau == 0) issue_data(t_begin, 0);
+    int cur_group = -1;
+    unsigned tw_uses = 0;
+    unsigned it = 0;
+    for (long long id = t_begin; id < t_end; ++id, ++it) {
+        const int slot = it & 1;
+        const TileId tl = decode_tile(F, id, G, chunks);
+        const RowId rid{tl.drow, tl.limb};
+        const bool f64 = fast_use_f64(F, rid);
+        bool restaged = false;
+        if (tau == 0) {
+            if (id + 1 < t_end) issue_data(id + 1, slot ^ 1);   // previous user of that buffer finished at the loop-end barrier
+        }
+        if (f64 && tl.group != cur_group) {
+            if (tau == 0) {
+                const double* W = F.tw_f64 + ((long long)tl.limb << (B + 8));
+                const int unit_log = 12 - B;
+                fence_async_smem();
+                mbar_expect_tx(bar_tw, (unsigned)(((1u << 12) - (1u << unit_log)) * 8u));
+                for (int j = 0; j < B; ++j) {
+                    const unsigned cnt = 1u << (j + unit_log);
+                    tma_bulk_g2s(tws + (((1u << j) - 1u) << unit_log), W + (1u << (8 + j)) + (size_t)tl.chunk * cnt, cnt * 8u, bar_tw);
+                }
+            }
+            restaged = true;
+            cur_group = tl.group;
+        }
+        mbar_wait(&bar_data[slot], (it >> 1) & 1);
+        if (restaged) {
+            mbar_wait(bar_tw, tw_uses & 1);
+            ++tw_uses;
+        }
+        int64_t* xb = slot ? buf1 : buf0;
+        int64_t* gout = F.a + tl.drow * F.a_stride + (long long)tl.chunk * TILE;
+        if (f64)
+            persist_fwd_block_tile<ArithF64, B, true>(F, xb, tws, tl, gout);
+        else
+            persist_fwd_block_tile<ArithU64, B, false>(F, xb, nullptr, tl, gout);
+        __syncthreads();   // xb and (if the group changes) the twiddle stage are free again
+    }
+}
+
 // ---- inverse pass B' (levels 0..B-1) ---------------------------------------------------------------------------
 template <class A, int B, bool STAGED>
 __device__ __forceinline__ void fast_inv_block_body(const FastArgs& F, int64_t* sm, int limb, long long drow) {

@@ -20,6 +20,7 @@ _vp = ctypes.c_void_p
 # name -> argtypes, mirroring include/ckks_b200.h exactly (checked by tests/test_abi.py)
 SIGNATURES = {
     "ckks_abi_version": [],
+    "ckks_set_option": [_int, _int],
     "ckks_mont_mult": [_i64p, _i64, _i64p, _i64, _i64p, _i64, _int, _int, _i64p, _i64p, _i64p, _i64p, _vp],
     "ckks_mont_enter": [_i64p, _i64, _i64p, _int, _int, _i64p, _i64p, _i64p, _i64p, _vp],
     "ckks_ntt": [_i64p, _i64, _int, _int, _i64p, _i64, _i64p, _i64p, _i64p, _i64p, _i64p, _i64p, _vp],
@@ -81,7 +82,7 @@ def _load():
 
 
 # kernels launched per entry point (for bench.py's gpu_launches accounting)
-KERNELS_PER_CALL = {"ckks_abi_version": 0, "ckks_ntt": 2, "ckks_intt": 2, "ckks_moddown": 2, "ckks_ntt_fast": 2,
+KERNELS_PER_CALL = {"ckks_abi_version": 0, "ckks_set_option": 0, "ckks_ntt": 2, "ckks_intt": 2, "ckks_moddown": 2, "ckks_ntt_fast": 2,
                     "ckks_intt_fast": 2, "ckks_exec_tensor_stage": 10, "ckks_exec_keyswitch_stage": 12,
                     "ckks_exec_keyswitch_ws_elems": 0}
 

@@ -64,8 +64,10 @@ def run(logN, L, iters, pool_bytes=320 << 20):
     out = {}
     for name, fn in (("fwd", fwd), ("inv_exit_reduce", inv), ("fast_fwd", ffwd), ("fast_inv", finv),
                      ("fast_fwd_int", lambda b: ffwd(b, 1)), ("fast_inv_int", lambda b: finv(b, 1)),
-                     ("fast_fwd_mix2", lambda b: ffwd(b, 2)), ("fast_fwd_mix3", lambda b: ffwd(b, 3)),
-                     ("fast_fwd_mix4", lambda b: ffwd(b, 4)), ("fast_inv_mix3", lambda b: finv(b, 3))):
+                     ("fast_fwd_nopersist", "nopersist")):
+        if fn == "nopersist":
+            lib.ckks_set_option(1, 0)
+            fn = ffwd
         for i in range(3):
             fn(bufs[i % nbuf])
         torch.cuda.synchronize()
@@ -77,6 +79,7 @@ def run(logN, L, iters, pool_bytes=320 << 20):
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / iters
         out[name] = dict(ms=ms, gbps=16.0 * L * N / (ms * 1e-3) / 1e9, limb_ntt_us=ms * 1e3 / L)
+        lib.ckks_set_option(1, 1)
     return out
 
 
