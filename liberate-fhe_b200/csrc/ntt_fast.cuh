@@ -76,6 +76,70 @@ struct ArithF64 {
     }
     // magnitudes double along the sum outputs of GS stages: re-centre once per radix-16 round
     static __device__ __forceinline__ void tame(T& v, const C& c) { v = f64_reduce(v, c); }
+    // one whole radix-2 stage (8 butterflies) written "vertically": every step of the 6-deep mulmod chain is issued
+    // for all 8 butterflies before the next step, so that 8 independent FP64 chains are in flight per warp
+    template <int I>
+    static __device__ __forceinline__ void ct_stage(T (&e)[16], const TW (&w)[8], const C& c) {
+        constexpr int d = 8 >> I;
+        double p[8], r[8], m[8];
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            const int k = ((b / d) * 2 * d) + (b % d);
+            p[b] = __dmul_rn(e[k + d], w[k >> (4 - I)]);
+        }
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            const int k = ((b / d) * 2 * d) + (b % d);
+            r[b] = __fma_rn(e[k + d], w[k >> (4 - I)], -p[b]);
+        }
+#pragma unroll
+        for (int b = 0; b < 8; ++b) m[b] = __fma_rn(p[b], c.qinv, F64_MAGIC);
+#pragma unroll
+        for (int b = 0; b < 8; ++b) m[b] = __dadd_rn(m[b], -F64_MAGIC);
+#pragma unroll
+        for (int b = 0; b < 8; ++b) p[b] = __fma_rn(-m[b], c.q, p[b]);
+#pragma unroll
+        for (int b = 0; b < 8; ++b) p[b] = __dadd_rn(p[b], r[b]);
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            const int k = ((b / d) * 2 * d) + (b % d);
+            const double u = e[k];
+            e[k] = __dadd_rn(u, p[b]);
+            e[k + d] = __dadd_rn(u, -p[b]);
+        }
+    }
+    template <int I>   // I = distance exponent: pairs (k, k + 2^I), twiddle index k >> (I+1)
+    static __device__ __forceinline__ void gs_stage(T (&e)[16], const TW (&w)[8], const C& c) {
+        constexpr int d = 1 << I;
+        double t[8], p[8], r[8], m[8];
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            const int k = ((b / d) * 2 * d) + (b % d);
+            t[b] = __dadd_rn(e[k], -e[k + d]);
+            e[k] = __dadd_rn(e[k], e[k + d]);
+        }
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            const int k = ((b / d) * 2 * d) + (b % d);
+            p[b] = __dmul_rn(t[b], w[k >> (I + 1)]);
+        }
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            const int k = ((b / d) * 2 * d) + (b % d);
+            r[b] = __fma_rn(t[b], w[k >> (I + 1)], -p[b]);
+        }
+#pragma unroll
+        for (int b = 0; b < 8; ++b) m[b] = __fma_rn(p[b], c.qinv, F64_MAGIC);
+#pragma unroll
+        for (int b = 0; b < 8; ++b) m[b] = __dadd_rn(m[b], -F64_MAGIC);
+#pragma unroll
+        for (int b = 0; b < 8; ++b) p[b] = __fma_rn(-m[b], c.q, p[b]);
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            const int k = ((b / d) * 2 * d) + (b % d);
+            e[k + d] = __dadd_rn(p[b], r[b]);
+        }
+    }
     template <int RUN, bool SMEM>
     static __device__ __forceinline__ void load_tw(TW (&w)[8], const TW* __restrict__ p) {
         if (RUN == 1) {
@@ -131,6 +195,20 @@ struct ArithU64 {
         V = shoup_mul(d, w.x, w.y, c.q);
     }
     static __device__ __forceinline__ void tame(T& v, const C& c) {}
+    template <int I>
+    static __device__ __forceinline__ void ct_stage(T (&e)[16], const TW (&w)[8], const C& c) {
+        constexpr int d = 8 >> I;
+#pragma unroll
+        for (int k = 0; k < 16; ++k)
+            if (!(k & d)) ct(e[k], e[k + d], w[k >> (4 - I)], c);
+    }
+    template <int I>
+    static __device__ __forceinline__ void gs_stage(T (&e)[16], const TW (&w)[8], const C& c) {
+        constexpr int d = 1 << I;
+#pragma unroll
+        for (int k = 0; k < 16; ++k)
+            if (!(k & d)) gs(e[k], e[k + d], w[k >> (I + 1)], c);
+    }
     template <int RUN, bool SMEM>
     static __device__ __forceinline__ void load_tw(TW (&w)[8], const TW* __restrict__ p) {
 #pragma unroll
@@ -190,38 +268,31 @@ struct TwShared {
 // ------------------------------------------------------------------------------------------------------------
 // rounds
 // ------------------------------------------------------------------------------------------------------------
+template <class A, int I, class SRC>
+__device__ __forceinline__ void fast_fwd_stage(typename A::T (&e)[16], const SRC& src, const typename A::C& c) {
+    typename A::TW w[8];
+    A::template load_tw<(1 << I), SRC::SMEM>(w, src.run(I));
+    A::template ct_stage<I>(e, w, c);
+}
 template <class A, int FIRST, class SRC>
 __device__ __forceinline__ void fast_fwd_round(typename A::T (&e)[16], const SRC& src, const typename A::C& c) {
-#pragma unroll
-    for (int i = FIRST; i < 4; ++i) {
-        const int d = 8 >> i;
-        const typename A::TW* wp = src.run(i);
-        typename A::TW w[8];
-        if (i == 0) A::template load_tw<1, SRC::SMEM>(w, wp);
-        if (i == 1) A::template load_tw<2, SRC::SMEM>(w, wp);
-        if (i == 2) A::template load_tw<4, SRC::SMEM>(w, wp);
-        if (i == 3) A::template load_tw<8, SRC::SMEM>(w, wp);
-#pragma unroll
-        for (int k = 0; k < 16; ++k)
-            if (!(k & d)) A::ct(e[k], e[k + d], w[k >> (4 - i)], c);
-    }
+    if constexpr (FIRST <= 0) fast_fwd_stage<A, 0>(e, src, c);
+    if constexpr (FIRST <= 1) fast_fwd_stage<A, 1>(e, src, c);
+    if constexpr (FIRST <= 2) fast_fwd_stage<A, 2>(e, src, c);
+    fast_fwd_stage<A, 3>(e, src, c);
+}
+template <class A, int I, class SRC>
+__device__ __forceinline__ void fast_inv_stage(typename A::T (&e)[16], const SRC& src, const typename A::C& c) {
+    typename A::TW w[8];
+    A::template load_tw<(1 << (3 - I)), SRC::SMEM>(w, src.run(3 - I));
+    A::template gs_stage<I>(e, w, c);
 }
 template <class A, int NST, class SRC>
 __device__ __forceinline__ void fast_inv_round(typename A::T (&e)[16], const SRC& src, const typename A::C& c) {
-#pragma unroll
-    for (int i = 0; i < NST; ++i) {
-        const int d = 1 << i;
-        const int ip = 3 - i;
-        const typename A::TW* wp = src.run(ip);
-        typename A::TW w[8];
-        if (ip == 0) A::template load_tw<1, SRC::SMEM>(w, wp);
-        if (ip == 1) A::template load_tw<2, SRC::SMEM>(w, wp);
-        if (ip == 2) A::template load_tw<4, SRC::SMEM>(w, wp);
-        if (ip == 3) A::template load_tw<8, SRC::SMEM>(w, wp);
-#pragma unroll
-        for (int k = 0; k < 16; ++k)
-            if (!(k & d)) A::gs(e[k], e[k + d], w[k >> (i + 1)], c);
-    }
+    fast_inv_stage<A, 0>(e, src, c);
+    if constexpr (NST >= 2) fast_inv_stage<A, 1>(e, src, c);
+    if constexpr (NST >= 3) fast_inv_stage<A, 2>(e, src, c);
+    if constexpr (NST >= 4) fast_inv_stage<A, 3>(e, src, c);
 #pragma unroll
     for (int k = 0; k < 16; ++k) A::tame(e[k], c);
 }
@@ -309,6 +380,9 @@ __device__ __forceinline__ ulonglong2 scalar_tw<ArithU64>(const FastArgs& F, int
 }
 
 // shared memory of the fast kernels: [data tile | staged twiddles (F64 path) | mbarrier]
+#ifndef FAST_CTAS_PER_SM
+#define FAST_CTAS_PER_SM 2
+#endif
 constexpr int FAST_TW_SLOTS = 4096;
 constexpr int FAST_SMEM_BYTES = SMEM_BYTES + FAST_TW_SLOTS * 8 + 16;
 
@@ -403,7 +477,7 @@ __device__ __forceinline__ void fast_fwd_col_body(const FastArgs& F, int64_t* sm
 }
 
 template <int DUMMY>
-__global__ void __launch_bounds__(NTT_THREADS, 3) fast_fwd_colpass(const FastArgs F) {
+__global__ void __launch_bounds__(NTT_THREADS, FAST_CTAS_PER_SM) fast_fwd_colpass(const FastArgs F) {
     extern __shared__ __align__(16) int64_t sm[];
     const RowId rid = fast_row(F);
     const int limb = rid.limb;
@@ -687,7 +761,7 @@ __device__ __forceinline__ void fast_fwd_block_body(const FastArgs& F, int64_t* 
 }
 
 template <int B>
-__global__ void __launch_bounds__(NTT_THREADS, 3) fast_fwd_blockpass(const FastArgs F) {
+__global__ void __launch_bounds__(NTT_THREADS, FAST_CTAS_PER_SM) fast_fwd_blockpass(const FastArgs F) {
     extern __shared__ __align__(16) int64_t sm[];
     const RowId rid = fast_row(F);
     const int limb = rid.limb;
@@ -925,7 +999,7 @@ __device__ __forceinline__ void fast_inv_block_body(const FastArgs& F, int64_t* 
 }
 
 template <int B>
-__global__ void __launch_bounds__(NTT_THREADS, 3) fast_inv_blockpass(const FastArgs F) {
+__global__ void __launch_bounds__(NTT_THREADS, FAST_CTAS_PER_SM) fast_inv_blockpass(const FastArgs F) {
     extern __shared__ __align__(16) int64_t sm[];
     const RowId rid = fast_row(F);
     const int limb = rid.limb;
@@ -977,7 +1051,7 @@ __device__ __forceinline__ void fast_inv_col_body(const FastArgs& F, int64_t* sm
 }
 
 template <int DUMMY>
-__global__ void __launch_bounds__(NTT_THREADS, 3) fast_inv_colpass(const FastArgs F) {
+__global__ void __launch_bounds__(NTT_THREADS, FAST_CTAS_PER_SM) fast_inv_colpass(const FastArgs F) {
     extern __shared__ __align__(16) int64_t sm[];
     const RowId rid = fast_row(F);
     const int limb = rid.limb;
