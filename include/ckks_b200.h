@@ -30,8 +30,8 @@ extern "C" {
 #define CKKS_E_ALIGN (-3)      /* pointer or stride not 16-byte aligned */
 
 int ckks_abi_version(void);
-/* tuning knobs: key 1 = persistent TMA-pipelined forward block pass (default 1) */
-int ckks_set_option(int key, int value);
+/* tuning knobs: key 1 = persistent TMA-pipelined forward block pass (default 0: measured slower than the one-tile-per-CTA kernel) */
+int ckks_set_option(int key, int value);   /* key 2 = L2 prefetch distance in rows (default 28, 0 = off) */
 
 /* ---- level 1: the 15 ntt_cuda operators (ntt.cpp:421-437), one device per call ---------------------- */
 

@@ -435,7 +435,8 @@ static int launch_inv_block(const NttArgs& A, dim3 grid, cudaStream_t st) {
     return launch_status();
 }
 
-int g_persist = 1;   // 1: persistent TMA-pipelined block pass (ckks_set_option(1, v))
+int g_persist = 0;
+int g_prefetch = PREFETCH_ROWS_AHEAD;   // ckks_set_option(2, rows_ahead); 0 disables the L2 prefetch   // 1: persistent TMA-pipelined block pass (ckks_set_option(1, v))
 int sm_count() {
     static int n = 0;
     if (!n) {
@@ -483,6 +484,7 @@ int ckks_abi_version(void) { return CKKS_ABI_VERSION; }
 
 int ckks_set_option(int key, int value) {
     if (key == 1) { g_persist = value; return 0; }
+    if (key == 2) { g_prefetch = value; return 0; }
     return CKKS_E_BADARG;
 }
 
@@ -628,7 +630,7 @@ int ckks_ntt_fast(int64_t* a, int64_t as, int rows, int period, int logN, const 
     if (!force_int && !tw_f64) return CKKS_E_BADARG;
     if (logN < 12 || logN > 17) return CKKS_E_LOGN;
     if (!row_ok(a, as) || !aligned16(tw_u64) || (tw_f64 && !aligned16(tw_f64))) return CKKS_E_ALIGN;
-    FastArgs F{a, as, reinterpret_cast<const ulonglong2*>(tw_u64), tw_f64, q, scal, scal_sh, period, logN, 0, force_int, 0, 0, 0};
+    FastArgs F{a, as, reinterpret_cast<const ulonglong2*>(tw_u64), tw_f64, q, scal, scal_sh, period, logN, 0, force_int, 0, 0, 0, g_prefetch};
     cudaStream_t st = S(stream);
     const dim3 grid((1 << logN) / TILE, rows);
     cudaFuncSetAttribute(fast_fwd_colpass<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, FAST_SMEM_BYTES);
@@ -655,7 +657,7 @@ int ckks_intt_fast(int64_t* a, int64_t as, int rows, int period, int logN, const
     if (!force_int && !tw_f64) return CKKS_E_BADARG;
     if (logN < 12 || logN > 17) return CKKS_E_LOGN;
     if (!row_ok(a, as) || !aligned16(tw_u64) || (tw_f64 && !aligned16(tw_f64))) return CKKS_E_ALIGN;
-    FastArgs F{a, as, reinterpret_cast<const ulonglong2*>(tw_u64), tw_f64, q, scal, scal_sh, period, logN, centred, force_int, 0, 0, 0};
+    FastArgs F{a, as, reinterpret_cast<const ulonglong2*>(tw_u64), tw_f64, q, scal, scal_sh, period, logN, centred, force_int, 0, 0, 0, g_prefetch};
     cudaStream_t st = S(stream);
     const dim3 grid((1 << logN) / TILE, rows);
     int rc = CKKS_E_LOGN;
@@ -838,7 +840,7 @@ int ckks_exec_keyswitch_stage(const ckks_level_t* lv, const int64_t* const* digi
             else k_extend_fast<8><<<eg, 256, 0, st>>>(X, t0, t1);
             RC(launch_status());
             FastArgs F{ext, N, reinterpret_cast<const ulonglong2*>(lv->twf_u64), lv->twf_f64, lv->q, nullptr, nullptr, E,
-                       lv->logN, 0, 0, t1 - t0, E, t0};
+                       lv->logN, 0, 0, t1 - t0, E, t0, g_prefetch};
             const dim3 grid(N / TILE, P * (t1 - t0));
             cudaFuncSetAttribute(fast_fwd_colpass<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, FAST_SMEM_BYTES);
             fast_fwd_colpass<0><<<grid, NTT_THREADS, FAST_SMEM_BYTES, st>>>(F);

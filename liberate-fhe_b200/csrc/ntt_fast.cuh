@@ -247,6 +247,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned phase) {
         : "memory");
 }
 
+// L2 prefetch (TMA prefetch engine / LSU prefetch): pulls the tile that a CTA about one wave later will load from
+// HBM into L2 while this CTA computes, turning that CTA's exposed DRAM latency into an L2 hit.
+constexpr int PREFETCH_ROWS_AHEAD = 28;   // x 16 chunks ~ one wave of 3 CTAs x 148 SMs
+__device__ __forceinline__ void l2_prefetch_bulk(const void* gptr, unsigned bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void l2_prefetch_line(const void* gptr) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(gptr));
+}
 // where a round's twiddles come from: the global table (index 2^s + ...) or the CTA's staged copy in shared memory
 template <class TW>
 struct TwGlobal {
@@ -328,12 +337,21 @@ struct FastArgs {
     // slab view of a [groups][group_rows] block: grid row r -> group r / slab_rows, member r % slab_rows;
     // data row = group * group_rows + slab_t0 + member, limb = slab_t0 + member.  slab_rows == 0: plain rows.
     int slab_rows, group_rows, slab_t0;
+    int prefetch;               // rows ahead whose tile is pulled into L2 by every CTA (0 = off)
 };
 
 struct RowId {
     long long data_row;
     int limb;
 };
+__device__ __forceinline__ long long fast_row_ahead(const FastArgs& F, int ahead) {
+    const int r = blockIdx.y + ahead;
+    if (r >= (int)gridDim.y) return -1;
+    if (F.slab_rows == 0) return r;
+    const int g = r / F.slab_rows, m = r - g * F.slab_rows;
+    return (long long)g * F.group_rows + F.slab_t0 + m;
+}
+
 __device__ __forceinline__ bool fast_use_f64(const FastArgs& F, const RowId& rid);
 __device__ __forceinline__ RowId fast_row(const FastArgs& F) {
     const int r = blockIdx.y;
@@ -381,7 +399,7 @@ __device__ __forceinline__ ulonglong2 scalar_tw<ArithU64>(const FastArgs& F, int
 
 // shared memory of the fast kernels: [data tile | staged twiddles (F64 path) | mbarrier]
 #ifndef FAST_CTAS_PER_SM
-#define FAST_CTAS_PER_SM 2
+#define FAST_CTAS_PER_SM 3
 #endif
 constexpr int FAST_TW_SLOTS = 4096;
 constexpr int FAST_SMEM_BYTES = SMEM_BYTES + FAST_TW_SLOTS * 8 + 16;
@@ -445,6 +463,10 @@ __device__ __forceinline__ void fast_fwd_col_body(const FastArgs& F, int64_t* sm
     TW* tws = reinterpret_cast<TW*>(sm + SMEM_SLOTS);
     uint64_t* bar = reinterpret_cast<uint64_t*>(sm + SMEM_SLOTS + FAST_TW_SLOTS);
     if constexpr (STAGED) stage_col_twiddles(reinterpret_cast<const double*>(W), reinterpret_cast<double*>(tws), bar);
+    {
+        const long long ra = F.prefetch ? fast_row_ahead(F, F.prefetch) : -1;
+        if (ra >= 0) l2_prefetch_line(F.a + ra * F.a_stride + (long long)blockIdx.x * 16 + ((long long)tau << b));
+    }
     T e[16];
     {
         const int r0 = tau >> 4, col = tau & 15;
@@ -707,6 +729,10 @@ __device__ __forceinline__ void fast_fwd_block_body(const FastArgs& F, int64_t* 
     TW* tws = reinterpret_cast<TW*>(sm + SMEM_SLOTS);
     uint64_t* bar = reinterpret_cast<uint64_t*>(sm + SMEM_SLOTS + FAST_TW_SLOTS);
     if constexpr (STAGED) stage_block_twiddles(reinterpret_cast<const double*>(W), reinterpret_cast<double*>(tws), bar, B, chunk);
+    if (tau == 32) {
+        const long long ra = F.prefetch ? fast_row_ahead(F, F.prefetch) : -1;
+        if (ra >= 0) l2_prefetch_bulk(F.a + ra * F.a_stride + (long long)chunk * TILE, TILE * 8u);
+    }
     T e[16];
     constexpr int P1 = B - 4;
     {
@@ -945,6 +971,10 @@ __device__ __forceinline__ void fast_inv_block_body(const FastArgs& F, int64_t* 
     TW* tws = reinterpret_cast<TW*>(sm + SMEM_SLOTS);
     uint64_t* bar = reinterpret_cast<uint64_t*>(sm + SMEM_SLOTS + FAST_TW_SLOTS);
     if constexpr (STAGED) stage_block_twiddles(reinterpret_cast<const double*>(W), reinterpret_cast<double*>(tws), bar, B, chunk);
+    if (tau == 32) {
+        const long long ra = F.prefetch ? fast_row_ahead(F, F.prefetch) : -1;
+        if (ra >= 0) l2_prefetch_bulk(F.a + ra * F.a_stride + (long long)chunk * TILE, TILE * 8u);
+    }
     T e[16];
     global_to_sm(sm, g, tau);
     __syncthreads();
@@ -1022,6 +1052,10 @@ __device__ __forceinline__ void fast_inv_col_body(const FastArgs& F, int64_t* sm
     TW* tws = reinterpret_cast<TW*>(sm + SMEM_SLOTS);
     uint64_t* bar = reinterpret_cast<uint64_t*>(sm + SMEM_SLOTS + FAST_TW_SLOTS);
     if constexpr (STAGED) stage_col_twiddles(reinterpret_cast<const double*>(W), reinterpret_cast<double*>(tws), bar);
+    {
+        const long long ra = F.prefetch ? fast_row_ahead(F, F.prefetch) : -1;
+        if (ra >= 0) l2_prefetch_line(F.a + ra * F.a_stride + (long long)blockIdx.x * 16 + ((long long)tau << b));
+    }
     T e[16];
     {
         const int hi = tau >> 4, col = tau & 15;

@@ -64,9 +64,16 @@ def run(logN, L, iters, pool_bytes=320 << 20):
     out = {}
     for name, fn in (("fwd", fwd), ("inv_exit_reduce", inv), ("fast_fwd", ffwd), ("fast_inv", finv),
                      ("fast_fwd_int", lambda b: ffwd(b, 1)), ("fast_inv_int", lambda b: finv(b, 1)),
-                     ("fast_fwd_nopersist", "nopersist")):
-        if fn == "nopersist":
+                     ("fast_fwd_nopf", "nopf"), ("fast_fwd_pf56", "pf56"), ("fast_fwd_persist", "persist")):
+        if fn == "nopf":
+            lib.ckks_set_option(2, 0)
+            fn = ffwd
+        if fn == "pf56":
+            lib.ckks_set_option(2, 56)
+            fn = ffwd
+        if fn == "persist":
             lib.ckks_set_option(1, 0)
+        lib.ckks_set_option(2, 28)
             fn = ffwd
         for i in range(3):
             fn(bufs[i % nbuf])
@@ -79,7 +86,8 @@ def run(logN, L, iters, pool_bytes=320 << 20):
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / iters
         out[name] = dict(ms=ms, gbps=16.0 * L * N / (ms * 1e-3) / 1e9, limb_ntt_us=ms * 1e3 / L)
-        lib.ckks_set_option(1, 1)
+        lib.ckks_set_option(1, 0)
+        lib.ckks_set_option(2, 28)
     return out
 
 
