@@ -454,7 +454,7 @@ static int launch_fast_fwd_block(const FastArgs& F, dim3 grid, cudaStream_t st) 
         const int rows = grid.y;
         const int G = F.slab_rows ? rows / F.slab_rows : rows / F.period;
         const long long tiles = (long long)rows * grid.x;
-        const int ctas = (int)((tiles < 2ll * sm_count()) ? tiles : 2ll * sm_count());
+        const int ctas = (int)((tiles < (long long)sm_count()) ? tiles : (long long)sm_count());
         cudaFuncSetAttribute(fast_fwd_blockpass_persist<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, PERSIST_SMEM_BYTES);
         fast_fwd_blockpass_persist<B><<<ctas, NTT_THREADS, PERSIST_SMEM_BYTES, st>>>(F, tiles, G > 0 ? G : 1);
         return launch_status();

@@ -824,12 +824,15 @@ __device__ __forceinline__ TileId decode_tile(const FastArgs& F, long long id, i
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-constexpr int PERSIST_SMEM_BYTES = 2 * SMEM_BYTES + FAST_TW_SLOTS * 8 + 32;
+// persistent kernel shared memory:
+// [exchange buffer (padded tile) | PERSIST_SLOTS raw tile slots | 2 twiddle stages | mbarriers]
+constexpr int PERSIST_SLOTS = 3;
+constexpr int PERSIST_SMEM_BYTES = SMEM_BYTES + PERSIST_SLOTS * TILE * 8 + 2 * FAST_TW_SLOTS * 8 + 64;
 
 template <class A, int B, bool STAGED>
-__device__ __forceinline__ void persist_fwd_block_tile(const FastArgs& F, int64_t* xb, const typename A::TW* tws,
-                                                       const TileId& tl, int64_t* __restrict__ gout) {
-    using T = typename A::T;
+__device__ __forceinline__ void persist_fwd_block_compute(const FastArgs& F, typename A::T (&e)[16], int64_t* xb,
+                                                          const typename A::TW* tws, const TileId& tl,
+                                                          int64_t* __restrict__ gout) {
     using TW = typename A::TW;
     const int tau = threadIdx.x;
     constexpr int logN = B + 8;
@@ -837,13 +840,6 @@ __device__ __forceinline__ void persist_fwd_block_tile(const FastArgs& F, int64_
     const unsigned chunk = (unsigned)tl.chunk;
     const typename A::C c = make_const<A>((uint64_t)F.q[tl.limb]);
     const TW* __restrict__ W = tw_row<A>(F, tl.limb);
-    T e[16];
-    {
-        const int zb = zbase(tau, P1);
-#pragma unroll
-        for (int k = 0; k < 16; ++k) e[k] = A::load_mid(xb[zb | (k << P1)]);   // raw (unpadded) tile as delivered by TMA
-    }
-    __syncthreads();   // the raw tile is in registers: xb becomes the padded exchange buffer
     if constexpr (STAGED)
         fast_fwd_round<A, 0>(e, TwSharedBlock<TW>{tws, 12 - B, 0, (unsigned)(tau >> P1)}, c);
     else
@@ -888,72 +884,96 @@ __device__ __forceinline__ void persist_fwd_block_tile(const FastArgs& F, int64_
     sm_to_global(xb, gout, tau);
 }
 
+// One CTA per SM.  A ring of PERSIST_SLOTS raw tiles keeps the next tiles' loads (TMA bulk copies) in flight while
+// the current tile is transformed, and the twiddles of the NEXT (limb, chunk) group are staged into the second
+// twiddle buffer while the current group is processed: after the prologue no wait on L2/DRAM is exposed.
 template <int B>
-__global__ void __launch_bounds__(NTT_THREADS, 2) fast_fwd_blockpass_persist(const FastArgs F, long long total_tiles, int G) {
+__global__ void __launch_bounds__(NTT_THREADS, 1) fast_fwd_blockpass_persist(const FastArgs F, long long total_tiles, int G) {
     extern __shared__ __align__(16) int64_t sm[];
-    int64_t* buf0 = sm;
-    int64_t* buf1 = sm + SMEM_SLOTS;
-    double* tws = reinterpret_cast<double*>(sm + 2 * SMEM_SLOTS);
-    uint64_t* bar_data = reinterpret_cast<uint64_t*>(sm + 2 * SMEM_SLOTS + FAST_TW_SLOTS);   // [2]
-    uint64_t* bar_tw = bar_data + 2;
+    int64_t* xb = sm;
+    int64_t* ring = sm + SMEM_SLOTS;
+    double* tws = reinterpret_cast<double*>(ring + PERSIST_SLOTS * TILE);      // [2][FAST_TW_SLOTS]
+    uint64_t* bar_data = reinterpret_cast<uint64_t*>(tws + 2 * FAST_TW_SLOTS);  // [PERSIST_SLOTS]
+    uint64_t* bar_tw = bar_data + PERSIST_SLOTS;                               // [2]
     const int tau = threadIdx.x;
+    constexpr int P1 = B - 4;
     const int chunks = (1 << (B + 8)) / TILE;
     const long long t_begin = total_tiles * blockIdx.x / gridDim.x;
     const long long t_end = total_tiles * (blockIdx.x + 1) / gridDim.x;
     if (t_begin >= t_end) return;
     if (tau == 0) {
-        mbar_init(&bar_data[0], 1);
-        mbar_init(&bar_data[1], 1);
-        mbar_init(bar_tw, 1);
+        for (int i = 0; i < PERSIST_SLOTS; ++i) mbar_init(&bar_data[i], 1);
+        mbar_init(&bar_tw[0], 1);
+        mbar_init(&bar_tw[1], 1);
     }
     __syncthreads();
     auto issue_data = [&](long long id, int slot) {   // thread 0 only
         const TileId t = decode_tile(F, id, G, chunks);
         const int64_t* src = F.a + t.drow * F.a_stride + (long long)t.chunk * TILE;
-        uint64_t* bar = &bar_data[slot];
         fence_async_smem();
-        mbar_expect_tx(bar, TILE * 8u);
-        tma_bulk_g2s(slot ? buf1 : buf0, src, TILE * 8u, bar);
+        mbar_expect_tx(&bar_data[slot], TILE * 8u);
+        tma_bulk_g2s(ring + slot * TILE, src, TILE * 8u, &bar_data[slot]);
     };
-    if (tau == 0) issue_data(t_begin, 0);
-    int cur_group = -1;
-    unsigned tw_uses = 0;
+    auto group_staged = [&](int limb) { return (uint64_t)F.q[limb] < SMALL_PRIME_LIMIT && F.force_int != 1; };
+    auto issue_tw = [&](long long id, int tslot) {    // thread 0 only; id = first tile of the group
+        const TileId t = decode_tile(F, id, G, chunks);
+        if (!group_staged(t.limb)) return;
+        const double* W = F.tw_f64 + ((long long)t.limb << (B + 8));
+        const int unit_log = 12 - B;
+        double* dst = tws + tslot * FAST_TW_SLOTS;
+        fence_async_smem();
+        mbar_expect_tx(&bar_tw[tslot], (unsigned)(((1u << 12) - (1u << unit_log)) * 8u));
+        for (int j = 0; j < B; ++j) {
+            const unsigned cnt = 1u << (j + unit_log);
+            tma_bulk_g2s(dst + (((1u << j) - 1u) << unit_log), W + (1u << (8 + j)) + (size_t)t.chunk * cnt, cnt * 8u, &bar_tw[tslot]);
+        }
+    };
+    if (tau == 0) {
+        issue_tw(t_begin, 0);
+        for (int i = 0; i < PERSIST_SLOTS && t_begin + i < t_end; ++i) issue_data(t_begin + i, i);
+    }
+    long long cur_group = -1;
+    unsigned gcount = 0;            // groups seen by this CTA; group k stages into buffer k & 1
+    unsigned tw_w0 = 0, tw_w1 = 0;  // completed phases per twiddle buffer
     unsigned it = 0;
     for (long long id = t_begin; id < t_end; ++id, ++it) {
-        const int slot = it & 1;
+        const int slot = it % PERSIST_SLOTS;
         const TileId tl = decode_tile(F, id, G, chunks);
         const RowId rid{tl.drow, tl.limb};
         const bool f64 = fast_use_f64(F, rid);
-        bool restaged = false;
-        if (tau == 0) {
-            if (id + 1 < t_end) issue_data(id + 1, slot ^ 1);   // previous user of that buffer finished at the loop-end barrier
-        }
-        if (f64 && tl.group != cur_group) {
-            if (tau == 0) {
-                const double* W = F.tw_f64 + ((long long)tl.limb << (B + 8));
-                const int unit_log = 12 - B;
-                fence_async_smem();
-                mbar_expect_tx(bar_tw, (unsigned)(((1u << 12) - (1u << unit_log)) * 8u));
-                for (int j = 0; j < B; ++j) {
-                    const unsigned cnt = 1u << (j + unit_log);
-                    tma_bulk_g2s(tws + (((1u << j) - 1u) << unit_log), W + (1u << (8 + j)) + (size_t)tl.chunk * cnt, cnt * 8u, bar_tw);
-                }
-            }
-            restaged = true;
+        bool new_group = false;
+        if (tl.group != cur_group) {   // readers of buffer (gcount+1)&1 (two groups back) left at the loop-end barrier
             cur_group = tl.group;
+            new_group = true;
+            const long long next_first = (long long)(tl.group + 1) * G;
+            if (tau == 0 && next_first < t_end) issue_tw(next_first, (gcount + 1) & 1);
+            ++gcount;
         }
-        mbar_wait(&bar_data[slot], (it >> 1) & 1);
-        if (restaged) {
-            mbar_wait(bar_tw, tw_uses & 1);
-            ++tw_uses;
-        }
-        int64_t* xb = slot ? buf1 : buf0;
+        const int tslot = (gcount - 1) & 1;
+        mbar_wait(&bar_data[slot], (it / PERSIST_SLOTS) & 1);
         int64_t* gout = F.a + tl.drow * F.a_stride + (long long)tl.chunk * TILE;
-        if (f64)
-            persist_fwd_block_tile<ArithF64, B, true>(F, xb, tws, tl, gout);
-        else
-            persist_fwd_block_tile<ArithU64, B, false>(F, xb, nullptr, tl, gout);
-        __syncthreads();   // xb and (if the group changes) the twiddle stage are free again
+        const int64_t* raw = ring + slot * TILE;
+        const int zb = zbase(tau, P1);
+        if (new_group && group_staged(tl.limb)) {
+            mbar_wait(&bar_tw[tslot], (tslot ? tw_w1 : tw_w0) & 1);
+            if (tslot) ++tw_w1; else ++tw_w0;
+        }
+        if (f64) {
+            double e[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) e[k] = ArithF64::load_mid(raw[zb | (k << P1)]);
+            __syncthreads();   // slot consumed
+            if (tau == 0 && id + PERSIST_SLOTS < t_end) issue_data(id + PERSIST_SLOTS, slot);
+            persist_fwd_block_compute<ArithF64, B, true>(F, e, xb, tws + tslot * FAST_TW_SLOTS, tl, gout);
+        } else {
+            uint64_t e[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) e[k] = ArithU64::load_mid(raw[zb | (k << P1)]);
+            __syncthreads();
+            if (tau == 0 && id + PERSIST_SLOTS < t_end) issue_data(id + PERSIST_SLOTS, slot);
+            persist_fwd_block_compute<ArithU64, B, false>(F, e, xb, nullptr, tl, gout);
+        }
+        __syncthreads();   // exchange buffer free; on a group change the older twiddle buffer is free
     }
 }
 

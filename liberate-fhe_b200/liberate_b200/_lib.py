@@ -4,6 +4,7 @@ There is NO CPU fallback: if the CUDA library cannot be loaded the import fails 
 wrapper refuses tensors that are not on a CUDA device.
 """
 import ctypes
+import os
 import shutil
 import sys
 from pathlib import Path
@@ -104,6 +105,10 @@ class _Counted:
 
 
 lib = _Counted(_load())
+# tuning switches of the library (ckks_set_option): CKKS_B200_OPTIONS="1=1,2=28"
+for _kv in filter(None, os.environ.get("CKKS_B200_OPTIONS", "").split(",")):
+    _k, _v = _kv.split("=")
+    lib.ckks_set_option(int(_k), int(_v))
 
 
 def check(rc, what):

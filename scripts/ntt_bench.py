@@ -62,19 +62,12 @@ def run(logN, L, iters, pool_bytes=320 << 20):
         check(lib.ckks_intt_fast(P(b), N, L, L, logN, P(twu), P(twd), P(qd), P(sc), P(sc), 0, fi, st), "intt_fast")
 
     out = {}
-    for name, fn in (("fwd", fwd), ("inv_exit_reduce", inv), ("fast_fwd", ffwd), ("fast_inv", finv),
-                     ("fast_fwd_int", lambda b: ffwd(b, 1)), ("fast_inv_int", lambda b: finv(b, 1)),
-                     ("fast_fwd_nopf", "nopf"), ("fast_fwd_pf56", "pf56"), ("fast_fwd_persist", "persist")):
-        if fn == "nopf":
-            lib.ckks_set_option(2, 0)
-            fn = ffwd
-        if fn == "pf56":
-            lib.ckks_set_option(2, 56)
-            fn = ffwd
-        if fn == "persist":
-            lib.ckks_set_option(1, 0)
-        lib.ckks_set_option(2, 28)
-            fn = ffwd
+    variants = [("fwd", fwd, None), ("inv_exit_reduce", inv, None), ("fast_fwd", ffwd, None), ("fast_inv", finv, None),
+                ("fast_fwd_int", lambda b: ffwd(b, 1), None), ("fast_inv_int", lambda b: finv(b, 1), None),
+                ("fast_fwd_nopf", ffwd, (2, 0)), ("fast_fwd_pf56", ffwd, (2, 56)), ("fast_fwd_persist", ffwd, (1, 1))]
+    for name, fn, opt in variants:
+        if opt:
+            lib.ckks_set_option(*opt)
         for i in range(3):
             fn(bufs[i % nbuf])
         torch.cuda.synchronize()

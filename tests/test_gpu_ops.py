@@ -273,3 +273,30 @@ def test_fast_transforms_equal_reference_sequences_after_reduction(logN, force_i
     big = T(np.concatenate([a, a]))
     fused.ntt_fast(big, sh_f, dbl_f, qd, period=C, force_int=force_int)
     assert eq(big[:C], ref2) and eq(big[C:], ref2), "batched period"
+
+
+@pytest.mark.parametrize("logN", [12, 14, 16, 17])
+def test_fast_forward_persistent_blockpass_option(logN):
+    """ckks_set_option(1, 1): the block pass runs as one CTA per SM fed by a TMA ring; results do not change."""
+    from liberate_b200._lib import lib
+    from liberate_b200.ntt import fused
+    P = O.Params(primes_for(logN, 3, 2), logN)
+    t = packs(P)
+    C = len(P.q)
+    rng = np.random.default_rng(900 + logN)
+    q = np.array(P.q, dtype=np.int64)
+    sh_f, dbl_f = fused.fast_tables(T(P.psi_plain), t["_2q"] // 2)
+    a = rng.integers(0, 2 * q[:, None], (C, P.N), dtype=np.int64)
+    ref = a.copy()
+    O.C.ntt(ref, P.psi, P._2q, *P.mont)
+    O.C.reduce_2q(ref, P._2q)
+    reps = 7                                  # enough tiles that every CTA loops and slots wrap around
+    big = T(np.concatenate([a] * reps))
+    try:
+        lib.ckks_set_option(1, 1)
+        fused.ntt_fast(big, sh_f, dbl_f, T(q), period=C)
+        torch.cuda.synchronize()
+    finally:
+        lib.ckks_set_option(1, 0)
+    for r in range(reps):
+        assert eq(big[r * C:(r + 1) * C], ref), f"persistent block pass, replica {r}"
