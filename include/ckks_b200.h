@@ -32,6 +32,11 @@ extern "C" {
 int ckks_abi_version(void);
 /* tuning knobs: key 1 = persistent TMA-pipelined forward block pass (default 0: measured slower than the one-tile-per-CTA kernel) */
 int ckks_set_option(int key, int value);   /* key 2 = L2 prefetch distance in rows (default 28, 0 = off) */
+/* key 3 = block passes: 0 one tile per CTA, 1 warp-independent + 256-bit accesses, 2 persistent software-pipelined;
+ * key 4 = 1: persistent software-pipelined column passes; key 5 = measurement only, skip column (1) / block (2) pass;
+ * key 6 = persistent CTAs per SM (1..4); key 7 = cap on the persistent grid (0 = none)  -- keys 3/4 need 32-byte aligned rows */
+int ckks_get_option(int key);               /* current value of a knob (negative: unknown key) */
+int64_t ckks_launch_count(void);            /* kernels launched by the library since it was loaded */
 
 /* ---- level 1: the 15 ntt_cuda operators (ntt.cpp:421-437), one device per call ---------------------- */
 

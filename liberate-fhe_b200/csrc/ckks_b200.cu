@@ -17,7 +17,8 @@ namespace {
 constexpr int EW_THREADS = 256;
 
 inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
-inline int launch_status() { return (int)cudaGetLastError(); }
+long long g_launches = 0;   // kernels launched by this library since load (ckks_launch_count)
+inline int launch_status() { ++g_launches; return (int)cudaGetLastError(); }
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 inline bool row_ok(const void* p, long long stride) { return aligned16(p) && (stride % 2 == 0); }
 
@@ -437,6 +438,9 @@ static int launch_inv_block(const NttArgs& A, dim3 grid, cudaStream_t st) {
 
 int g_persist = 0;
 int g_prefetch = PREFETCH_ROWS_AHEAD;   // ckks_set_option(2, rows_ahead); 0 disables the L2 prefetch   // 1: persistent TMA-pipelined block pass (ckks_set_option(1, v))
+int g_skip = 0;   // ckks_set_option(5, mask): measurement only -- bit 0 skips the column pass, bit 1 the block pass
+int g_warp = 0;   // ckks_set_option(3, v): 1 = warp-independent block passes with 256-bit global accesses
+inline bool aligned32(const void* p, long long stride) { return (((uintptr_t)p) & 31) == 0 && (stride & 3) == 0; }
 int sm_count() {
     static int n = 0;
     if (!n) {
@@ -445,6 +449,45 @@ int sm_count() {
         cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     }
     return n;
+}
+
+// persistent software-pipelined ("pp") kernels: rows must tile into G rows per limb and be 32-byte aligned
+int g_swap = 0;    // ckks_set_option(8, v): 1 = (row, chunk) grid order for the one-tile-per-CTA kernels
+inline dim3 tile_grid(dim3 grid) { return g_swap ? dim3(grid.y, grid.x) : grid; }
+int g_colpp = 0;   // ckks_set_option(4, v): 1 = persistent software-pipelined column passes
+int g_pp_ctas = 2; // ckks_set_option(6, v): persistent CTAs per SM
+int g_pp_cap = 0;  // ckks_set_option(7, v): cap on the persistent grid (0 = none; tests use it to make every CTA walk many tiles)
+inline bool pp_ok(const FastArgs& F, dim3 grid) {
+    if (!aligned32(F.a, F.a_stride)) return false;
+    return F.slab_rows ? (grid.y % F.slab_rows == 0) : (grid.y % F.period == 0);
+}
+inline int pp_group(const FastArgs& F, dim3 grid) { return F.slab_rows ? grid.y / F.slab_rows : grid.y / F.period; }
+inline int pp_ctas(long long tiles) {
+    long long slots = (long long)sm_count() * g_pp_ctas;
+    if (g_pp_cap > 0 && g_pp_cap < slots) slots = g_pp_cap;
+    return (int)(tiles < slots ? tiles : slots);
+}
+static int launch_fast_col(bool fwd, const FastArgs& F, dim3 grid, cudaStream_t st) {
+    if (g_colpp && pp_ok(F, grid)) {
+        const int G = pp_group(F, grid);
+        const long long tiles = (long long)grid.x * grid.y;
+        if (fwd) {
+            cudaFuncSetAttribute(fast_colpass_pp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PPC_SMEM_BYTES);
+            fast_colpass_pp<true><<<pp_ctas(tiles), NTT_THREADS, PPC_SMEM_BYTES, st>>>(F, tiles, G);
+        } else {
+            cudaFuncSetAttribute(fast_colpass_pp<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PPC_SMEM_BYTES);
+            fast_colpass_pp<false><<<pp_ctas(tiles), NTT_THREADS, PPC_SMEM_BYTES, st>>>(F, tiles, G);
+        }
+        return launch_status();
+    }
+    if (fwd) {
+        cudaFuncSetAttribute(fast_fwd_colpass<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, FAST_SMEM_BYTES);
+        fast_fwd_colpass<0><<<tile_grid(grid), NTT_THREADS, FAST_SMEM_BYTES, st>>>(F);
+    } else {
+        cudaFuncSetAttribute(fast_inv_colpass<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, FAST_SMEM_BYTES);
+        fast_inv_colpass<0><<<tile_grid(grid), NTT_THREADS, FAST_SMEM_BYTES, st>>>(F);
+    }
+    return launch_status();
 }
 
 template <int B>
@@ -459,14 +502,38 @@ static int launch_fast_fwd_block(const FastArgs& F, dim3 grid, cudaStream_t st) 
         fast_fwd_blockpass_persist<B><<<ctas, NTT_THREADS, PERSIST_SMEM_BYTES, st>>>(F, tiles, G > 0 ? G : 1);
         return launch_status();
     }
+    if (g_warp == 2 && pp_ok(F, grid)) {
+        const int G = pp_group(F, grid);
+        const long long tiles = (long long)grid.x * grid.y;
+        cudaFuncSetAttribute(fast_fwd_blockpass_pp<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, PP_SMEM_BYTES);
+        fast_fwd_blockpass_pp<B><<<pp_ctas(tiles), NTT_THREADS, PP_SMEM_BYTES, st>>>(F, tiles, G);
+        return launch_status();
+    }
+    if (g_warp && aligned32(F.a, F.a_stride)) {
+        cudaFuncSetAttribute(fast_fwd_blockpass_w<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, FAST_SMEM_BYTES);
+        fast_fwd_blockpass_w<B><<<tile_grid(grid), NTT_THREADS, FAST_SMEM_BYTES, st>>>(F);
+        return launch_status();
+    }
     cudaFuncSetAttribute(fast_fwd_blockpass<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, FAST_SMEM_BYTES);
-    fast_fwd_blockpass<B><<<grid, NTT_THREADS, FAST_SMEM_BYTES, st>>>(F);
+    fast_fwd_blockpass<B><<<tile_grid(grid), NTT_THREADS, FAST_SMEM_BYTES, st>>>(F);
     return launch_status();
 }
 template <int B>
 static int launch_fast_inv_block(const FastArgs& F, dim3 grid, cudaStream_t st) {
+    if (g_warp == 2 && pp_ok(F, grid)) {
+        const int G = pp_group(F, grid);
+        const long long tiles = (long long)grid.x * grid.y;
+        cudaFuncSetAttribute(fast_inv_blockpass_pp<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, PP_SMEM_BYTES);
+        fast_inv_blockpass_pp<B><<<pp_ctas(tiles), NTT_THREADS, PP_SMEM_BYTES, st>>>(F, tiles, G);
+        return launch_status();
+    }
+    if (g_warp && aligned32(F.a, F.a_stride)) {
+        cudaFuncSetAttribute(fast_inv_blockpass_w<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, FAST_SMEM_BYTES);
+        fast_inv_blockpass_w<B><<<tile_grid(grid), NTT_THREADS, FAST_SMEM_BYTES, st>>>(F);
+        return launch_status();
+    }
     cudaFuncSetAttribute(fast_inv_blockpass<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, FAST_SMEM_BYTES);
-    fast_inv_blockpass<B><<<grid, NTT_THREADS, FAST_SMEM_BYTES, st>>>(F);
+    fast_inv_blockpass<B><<<tile_grid(grid), NTT_THREADS, FAST_SMEM_BYTES, st>>>(F);
     return launch_status();
 }
 }  // namespace
@@ -482,9 +549,29 @@ extern "C" {
 
 int ckks_abi_version(void) { return CKKS_ABI_VERSION; }
 
+int64_t ckks_launch_count(void) { return (int64_t)g_launches; }
+
+int ckks_get_option(int key) {
+    if (key == 1) return g_persist;
+    if (key == 2) return g_prefetch;
+    if (key == 3) return g_warp;
+    if (key == 4) return g_colpp;
+    if (key == 5) return g_skip;
+    if (key == 6) return g_pp_ctas;
+    if (key == 7) return g_pp_cap;
+    if (key == 8) return g_swap;
+    return CKKS_E_BADARG;
+}
+
 int ckks_set_option(int key, int value) {
     if (key == 1) { g_persist = value; return 0; }
     if (key == 2) { g_prefetch = value; return 0; }
+    if (key == 3) { g_warp = value; return 0; }
+    if (key == 4) { g_colpp = value; return 0; }
+    if (key == 5) { g_skip = value; return 0; }
+    if (key == 6) { if (value < 1 || value > 4) return CKKS_E_BADARG; g_pp_ctas = value; return 0; }
+    if (key == 7) { g_pp_cap = value; return 0; }
+    if (key == 8) { g_swap = value; return 0; }
     return CKKS_E_BADARG;
 }
 
@@ -630,13 +717,14 @@ int ckks_ntt_fast(int64_t* a, int64_t as, int rows, int period, int logN, const 
     if (!force_int && !tw_f64) return CKKS_E_BADARG;
     if (logN < 12 || logN > 17) return CKKS_E_LOGN;
     if (!row_ok(a, as) || !aligned16(tw_u64) || (tw_f64 && !aligned16(tw_f64))) return CKKS_E_ALIGN;
-    FastArgs F{a, as, reinterpret_cast<const ulonglong2*>(tw_u64), tw_f64, q, scal, scal_sh, period, logN, 0, force_int, 0, 0, 0, g_prefetch};
+    FastArgs F{a, as, reinterpret_cast<const ulonglong2*>(tw_u64), tw_f64, q, scal, scal_sh, period, logN, 0, force_int, 0, 0, 0, g_prefetch, g_swap};
     cudaStream_t st = S(stream);
     const dim3 grid((1 << logN) / TILE, rows);
-    cudaFuncSetAttribute(fast_fwd_colpass<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, FAST_SMEM_BYTES);
-    fast_fwd_colpass<0><<<grid, NTT_THREADS, FAST_SMEM_BYTES, st>>>(F);
-    int rc = launch_status();
-    if (rc) return rc;
+    if (!(g_skip & 1)) {
+        int rc = launch_fast_col(true, F, grid, st);
+        if (rc) return rc;
+    }
+    if (g_skip & 2) return 0;
     F.scal = nullptr;
     switch (logN - 8) {
         case 4: return launch_fast_fwd_block<4>(F, grid, st);
@@ -657,11 +745,12 @@ int ckks_intt_fast(int64_t* a, int64_t as, int rows, int period, int logN, const
     if (!force_int && !tw_f64) return CKKS_E_BADARG;
     if (logN < 12 || logN > 17) return CKKS_E_LOGN;
     if (!row_ok(a, as) || !aligned16(tw_u64) || (tw_f64 && !aligned16(tw_f64))) return CKKS_E_ALIGN;
-    FastArgs F{a, as, reinterpret_cast<const ulonglong2*>(tw_u64), tw_f64, q, scal, scal_sh, period, logN, centred, force_int, 0, 0, 0, g_prefetch};
+    FastArgs F{a, as, reinterpret_cast<const ulonglong2*>(tw_u64), tw_f64, q, scal, scal_sh, period, logN, centred, force_int, 0, 0, 0, g_prefetch, g_swap};
     cudaStream_t st = S(stream);
     const dim3 grid((1 << logN) / TILE, rows);
     int rc = CKKS_E_LOGN;
-    switch (logN - 8) {
+    if (g_skip & 2) rc = 0;
+    else switch (logN - 8) {
         case 4: rc = launch_fast_inv_block<4>(F, grid, st); break;
         case 5: rc = launch_fast_inv_block<5>(F, grid, st); break;
         case 6: rc = launch_fast_inv_block<6>(F, grid, st); break;
@@ -670,9 +759,8 @@ int ckks_intt_fast(int64_t* a, int64_t as, int rows, int period, int logN, const
         case 9: rc = launch_fast_inv_block<9>(F, grid, st); break;
     }
     if (rc) return rc;
-    cudaFuncSetAttribute(fast_inv_colpass<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, FAST_SMEM_BYTES);
-    fast_inv_colpass<0><<<grid, NTT_THREADS, FAST_SMEM_BYTES, st>>>(F);
-    return launch_status();
+    if (g_skip & 1) return 0;
+    return launch_fast_col(false, F, grid, st);
 }
 
 // ---- level 2 -----------------------------------------------------------------------------------------
@@ -840,11 +928,9 @@ int ckks_exec_keyswitch_stage(const ckks_level_t* lv, const int64_t* const* digi
             else k_extend_fast<8><<<eg, 256, 0, st>>>(X, t0, t1);
             RC(launch_status());
             FastArgs F{ext, N, reinterpret_cast<const ulonglong2*>(lv->twf_u64), lv->twf_f64, lv->q, nullptr, nullptr, E,
-                       lv->logN, 0, 0, t1 - t0, E, t0, g_prefetch};
+                       lv->logN, 0, 0, t1 - t0, E, t0, g_prefetch, g_swap};
             const dim3 grid(N / TILE, P * (t1 - t0));
-            cudaFuncSetAttribute(fast_fwd_colpass<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, FAST_SMEM_BYTES);
-            fast_fwd_colpass<0><<<grid, NTT_THREADS, FAST_SMEM_BYTES, st>>>(F);
-            RC(launch_status());
+            RC(launch_fast_col(true, F, grid, st));
             switch (lv->logN - 8) {
                 case 4: RC(launch_fast_fwd_block<4>(F, grid, st)); break;
                 case 5: RC(launch_fast_fwd_block<5>(F, grid, st)); break;

@@ -256,6 +256,18 @@ __device__ __forceinline__ void l2_prefetch_bulk(const void* gptr, unsigned byte
 __device__ __forceinline__ void l2_prefetch_line(const void* gptr) {
     asm volatile("prefetch.global.L2 [%0];" ::"l"(gptr));
 }
+// 256-bit global accesses (sm_100: LDG.E.256 / STG.E.256): a thread's 16 contiguous coefficients move as 4 full
+// 32-byte sectors, so contiguous register tiles go to / come from global memory without a shared-memory detour
+__device__ __forceinline__ void ldg256(const int64_t* p, int64_t (&r)[16], int j) {
+    asm volatile("ld.global.v4.b64 {%0,%1,%2,%3}, [%4];"
+                 : "=l"(r[4 * j]), "=l"(r[4 * j + 1]), "=l"(r[4 * j + 2]), "=l"(r[4 * j + 3])
+                 : "l"(p + 4 * j));
+}
+__device__ __forceinline__ void stg256(int64_t* p, const int64_t (&r)[16], int j) {
+    asm volatile("st.global.v4.b64 [%0], {%1,%2,%3,%4};" ::"l"(p + 4 * j), "l"(r[4 * j]), "l"(r[4 * j + 1]),
+                 "l"(r[4 * j + 2]), "l"(r[4 * j + 3])
+                 : "memory");
+}
 // where a round's twiddles come from: the global table (index 2^s + ...) or the CTA's staged copy in shared memory
 template <class TW>
 struct TwGlobal {
@@ -338,15 +350,34 @@ struct FastArgs {
     // data row = group * group_rows + slab_t0 + member, limb = slab_t0 + member.  slab_rows == 0: plain rows.
     int slab_rows, group_rows, slab_t0;
     int prefetch;               // rows ahead whose tile is pulled into L2 by every CTA (0 = off)
+    int swap_grid;              // one-tile-per-CTA kernels: blockIdx.x = row, blockIdx.y = chunk
 };
+
+// grid mapping of the one-tile-per-CTA kernels: (chunk, row) by default; swapped (row, chunk) when F.swap_grid is
+// set, so that consecutive CTAs belong to consecutive rows and the integer-path rows (60-bit limbs) are spread
+// finely among the FP64 rows -- the two kinds of tile load different pipes and overlap when they share an SM.
+__device__ __forceinline__ int grid_row(const FastArgs& F) { return F.swap_grid ? blockIdx.x : blockIdx.y; }
+__device__ __forceinline__ int grid_rows(const FastArgs& F) { return F.swap_grid ? gridDim.x : gridDim.y; }
+__device__ __forceinline__ unsigned grid_chunk(const FastArgs& F) { return F.swap_grid ? blockIdx.y : blockIdx.x; }
 
 struct RowId {
     long long data_row;
     int limb;
 };
-__device__ __forceinline__ long long fast_row_ahead(const FastArgs& F, int ahead) {
-    const int r = blockIdx.y + ahead;
-    if (r >= (int)gridDim.y) return -1;
+// the tile that a CTA dispatched about `ahead` rows x (chunks per row) tiles later will load: data row (or -1) and chunk
+__device__ __forceinline__ long long fast_row_ahead(const FastArgs& F, int ahead, unsigned& chunk) {
+    int r;
+    if (F.swap_grid) {   // dispatch order: row fastest, then chunk
+        const long long lin = (long long)blockIdx.y * gridDim.x + blockIdx.x + (long long)ahead * gridDim.y;
+        const int c = (int)(lin / gridDim.x);
+        if (c >= (int)gridDim.y) return -1;
+        r = (int)(lin - (long long)c * gridDim.x);
+        chunk = (unsigned)c;
+    } else {
+        r = blockIdx.y + ahead;
+        if (r >= (int)gridDim.y) return -1;
+        chunk = blockIdx.x;
+    }
     if (F.slab_rows == 0) return r;
     const int g = r / F.slab_rows, m = r - g * F.slab_rows;
     return (long long)g * F.group_rows + F.slab_t0 + m;
@@ -354,7 +385,7 @@ __device__ __forceinline__ long long fast_row_ahead(const FastArgs& F, int ahead
 
 __device__ __forceinline__ bool fast_use_f64(const FastArgs& F, const RowId& rid);
 __device__ __forceinline__ RowId fast_row(const FastArgs& F) {
-    const int r = blockIdx.y;
+    const int r = grid_row(F);
     if (F.slab_rows == 0) return RowId{r, r % F.period};
     const int g = r / F.slab_rows, m = r - g * F.slab_rows;
     return RowId{(long long)g * F.group_rows + F.slab_t0 + m, F.slab_t0 + m};
@@ -458,14 +489,15 @@ __device__ __forceinline__ void fast_fwd_col_body(const FastArgs& F, int64_t* sm
     const int tau = threadIdx.x;
     const int b = F.logN - 8;
     const typename A::C c = make_const<A>((uint64_t)F.q[limb]);
-    int64_t* __restrict__ row0 = F.a + drow * F.a_stride + (long long)blockIdx.x * 16;
+    int64_t* __restrict__ row0 = F.a + drow * F.a_stride + (long long)grid_chunk(F) * 16;
     const TW* __restrict__ W = tw_row<A>(F, limb);
     TW* tws = reinterpret_cast<TW*>(sm + SMEM_SLOTS);
     uint64_t* bar = reinterpret_cast<uint64_t*>(sm + SMEM_SLOTS + FAST_TW_SLOTS);
     if constexpr (STAGED) stage_col_twiddles(reinterpret_cast<const double*>(W), reinterpret_cast<double*>(tws), bar);
     {
-        const long long ra = F.prefetch ? fast_row_ahead(F, F.prefetch) : -1;
-        if (ra >= 0) l2_prefetch_line(F.a + ra * F.a_stride + (long long)blockIdx.x * 16 + ((long long)tau << b));
+        unsigned ca = 0;
+        const long long ra = F.prefetch ? fast_row_ahead(F, F.prefetch, ca) : -1;
+        if (ra >= 0) l2_prefetch_line(F.a + ra * F.a_stride + (long long)ca * 16 + ((long long)tau << b));
     }
     T e[16];
     {
@@ -721,7 +753,7 @@ __device__ __forceinline__ void fast_fwd_block_body(const FastArgs& F, int64_t* 
     using T = typename A::T;
     using TW = typename A::TW;
     const int tau = threadIdx.x;
-    const unsigned chunk = blockIdx.x;
+    const unsigned chunk = grid_chunk(F);
     constexpr int logN = B + 8;
     const typename A::C c = make_const<A>((uint64_t)F.q[limb]);
     int64_t* __restrict__ g = F.a + drow * F.a_stride + (long long)chunk * TILE;
@@ -730,8 +762,9 @@ __device__ __forceinline__ void fast_fwd_block_body(const FastArgs& F, int64_t* 
     uint64_t* bar = reinterpret_cast<uint64_t*>(sm + SMEM_SLOTS + FAST_TW_SLOTS);
     if constexpr (STAGED) stage_block_twiddles(reinterpret_cast<const double*>(W), reinterpret_cast<double*>(tws), bar, B, chunk);
     if (tau == 32) {
-        const long long ra = F.prefetch ? fast_row_ahead(F, F.prefetch) : -1;
-        if (ra >= 0) l2_prefetch_bulk(F.a + ra * F.a_stride + (long long)chunk * TILE, TILE * 8u);
+        unsigned ca = 0;
+        const long long ra = F.prefetch ? fast_row_ahead(F, F.prefetch, ca) : -1;
+        if (ra >= 0) l2_prefetch_bulk(F.a + ra * F.a_stride + (long long)ca * TILE, TILE * 8u);
     }
     T e[16];
     constexpr int P1 = B - 4;
@@ -786,6 +819,92 @@ __device__ __forceinline__ void fast_fwd_block_body(const FastArgs& F, int64_t* 
     sm_to_global(sm, g, tau);
 }
 
+// ---- forward pass B, WARP-INDEPENDENT form -------------------------------------------------------------------------
+// Stages 8..logN-1 only mix coefficients inside 2^B-point sub-blocks (B <= 9), i.e. inside the 512 contiguous
+// coefficients a warp owns (32 threads x 16).  Every exchange therefore stays inside the warp's private slice of the
+// exchange buffer and needs __syncwarp() only -- no CTA barrier anywhere, so the 8 warps of a CTA drift apart and keep
+// the FP64 pipe fed while others wait on loads.  After the last round a thread holds 16 contiguous coefficients,
+// which leave as four 256-bit stores (no staging pass through shared memory).
+template <class A, int B, bool STAGED>
+__device__ __forceinline__ void fast_fwd_block_body_w(const FastArgs& F, int64_t* sm, int limb, long long drow) {
+    using T = typename A::T;
+    using TW = typename A::TW;
+    const int tau = threadIdx.x;
+    const unsigned chunk = grid_chunk(F);
+    constexpr int logN = B + 8;
+    const typename A::C c = make_const<A>((uint64_t)F.q[limb]);
+    int64_t* __restrict__ g = F.a + drow * F.a_stride + (long long)chunk * TILE;
+    const TW* __restrict__ W = tw_row<A>(F, limb);
+    TW* tws = reinterpret_cast<TW*>(sm + SMEM_SLOTS);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(sm + SMEM_SLOTS + FAST_TW_SLOTS);
+    if constexpr (STAGED) stage_block_twiddles(reinterpret_cast<const double*>(W), reinterpret_cast<double*>(tws), bar, B, chunk);
+    if (tau == 32) {
+        unsigned ca = 0;
+        const long long ra = F.prefetch ? fast_row_ahead(F, F.prefetch, ca) : -1;
+        if (ra >= 0) l2_prefetch_bulk(F.a + ra * F.a_stride + (long long)ca * TILE, TILE * 8u);
+    }
+    T e[16];
+    constexpr int P1 = B - 4;
+    {
+        const int zb = zbase(tau, P1);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) e[k] = A::load_mid(g[zb | (k << P1)]);
+        if constexpr (STAGED) {
+            mbar_wait(bar, 0);
+            fast_fwd_round<A, 0>(e, TwSharedBlock<TW>{tws, 12 - B, 0, (unsigned)(tau >> P1)}, c);
+        } else {
+            fast_fwd_round<A, 0>(e, TwGlobal<TW>{W, logN - 4 - P1, (chunk << (8 - P1)) | (unsigned)(tau >> P1)}, c);
+        }
+    }
+    if constexpr (B >= 8) {
+        constexpr int P2 = B - 8;
+        smx_store(sm, e, tau, P1);
+        __syncwarp();
+        smx_load(sm, e, tau, P2);
+        if constexpr (STAGED)
+            fast_fwd_round<A, 0>(e, TwSharedBlock<TW>{tws, 12 - B, 4, (unsigned)(tau >> P2)}, c);
+        else
+            fast_fwd_round<A, 0>(e, TwGlobal<TW>{W, logN - 4 - P2, (chunk << (8 - P2)) | (unsigned)(tau >> P2)}, c);
+        if constexpr (B == 9) {
+            __syncwarp();
+            smx_store(sm, e, tau, P2);
+            __syncwarp();
+            smx_load(sm, e, tau, 0);
+            if constexpr (STAGED)
+                fast_fwd_round<A, 3>(e, TwSharedBlock<TW>{tws, 12 - B, B - 4, (unsigned)tau}, c);
+            else
+                fast_fwd_round<A, 3>(e, TwGlobal<TW>{W, logN - 4, (chunk << 8) | (unsigned)tau}, c);
+        }
+    } else if constexpr (B > 4) {
+        smx_store(sm, e, tau, P1);
+        __syncwarp();
+        smx_load(sm, e, tau, 0);
+        if constexpr (STAGED)
+            fast_fwd_round<A, 8 - B>(e, TwSharedBlock<TW>{tws, 12 - B, B - 4, (unsigned)tau}, c);
+        else
+            fast_fwd_round<A, 8 - B>(e, TwGlobal<TW>{W, logN - 4, (chunk << 8) | (unsigned)tau}, c);
+    }
+    {   // the thread's 16 contiguous canonical coefficients: four full-sector 256-bit stores
+        int64_t r[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) r[k] = A::store_canon(e[k], c, false);
+        int64_t* o = g + tau * 16;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) stg256(o, r, j);
+    }
+}
+
+template <int B>
+__global__ void __launch_bounds__(NTT_THREADS, FAST_CTAS_PER_SM) fast_fwd_blockpass_w(const FastArgs F) {
+    extern __shared__ __align__(16) int64_t sm[];
+    const RowId rid = fast_row(F);
+    const int limb = rid.limb;
+    if (fast_use_f64(F, rid))
+        fast_fwd_block_body_w<ArithF64, B, true>(F, sm, limb, rid.data_row);
+    else
+        fast_fwd_block_body_w<ArithU64, B, false>(F, sm, limb, rid.data_row);
+}
+
 template <int B>
 __global__ void __launch_bounds__(NTT_THREADS, FAST_CTAS_PER_SM) fast_fwd_blockpass(const FastArgs F) {
     extern __shared__ __align__(16) int64_t sm[];
@@ -809,6 +928,21 @@ struct TileId {
 };
 __device__ __forceinline__ TileId decode_tile(const FastArgs& F, long long id, int G, int chunks) {
     const int group = (int)(id / G), g = (int)(id - (long long)group * G);
+    const int m = group / chunks, chunk = group - m * chunks;
+    TileId t;
+    t.group = group;
+    t.chunk = chunk;
+    if (F.slab_rows == 0) {
+        t.limb = m;
+        t.drow = (long long)g * F.period + m;
+    } else {
+        t.limb = F.slab_t0 + m;
+        t.drow = (long long)g * F.group_rows + F.slab_t0 + m;
+    }
+    return t;
+}
+__device__ __forceinline__ TileId decode_tile32(const FastArgs& F, int id, int G, int chunks) {   // 32-bit index maths
+    const int group = id / G, g = id - group * G;
     const int m = group / chunks, chunk = group - m * chunks;
     TileId t;
     t.group = group;
@@ -936,7 +1070,7 @@ __global__ void __launch_bounds__(NTT_THREADS, 1) fast_fwd_blockpass_persist(con
     unsigned gcount = 0;            // groups seen by this CTA; group k stages into buffer k & 1
     unsigned tw_w0 = 0, tw_w1 = 0;  // completed phases per twiddle buffer
     unsigned it = 0;
-    for (long long id = t_begin; id < t_end; ++id, ++it) {
+    for (int id = t_begin; id < t_end; ++id, ++it) {
         const int slot = it % PERSIST_SLOTS;
         const TileId tl = decode_tile(F, id, G, chunks);
         const RowId rid{tl.drow, tl.limb};
@@ -945,7 +1079,7 @@ __global__ void __launch_bounds__(NTT_THREADS, 1) fast_fwd_blockpass_persist(con
         if (tl.group != cur_group) {   // readers of buffer (gcount+1)&1 (two groups back) left at the loop-end barrier
             cur_group = tl.group;
             new_group = true;
-            const long long next_first = (long long)(tl.group + 1) * G;
+            const int next_first = (tl.group + 1) * G;
             if (tau == 0 && next_first < t_end) issue_tw(next_first, (gcount + 1) & 1);
             ++gcount;
         }
@@ -977,13 +1111,188 @@ __global__ void __launch_bounds__(NTT_THREADS, 1) fast_fwd_blockpass_persist(con
     }
 }
 
+// ---- PERSISTENT, SOFTWARE-PIPELINED forward block pass ("pp") ---------------------------------------------------------
+// The one-tile-per-CTA kernels run load -> compute -> store back to back in every CTA, and the CTAs of an SM fall
+// into step: the memory system is idle while they compute and the FP64 pipe is idle while they load (ncu: FP64 pipe
+// 42 % busy, no dominant stall).  Here a CTA walks a contiguous range of tiles and every thread PREFETCHES THE NEXT
+// TILE'S 16 COEFFICIENTS INTO REGISTERS before it transforms the current one, so the load latency of tile i+1 hides
+// behind the butterflies of tile i.  Warps are independent inside a tile (see fast_fwd_block_body_w): the only CTA
+// barrier is at a change of (limb, chunk) group, where the twiddle buffer of the group before last is handed back
+// to the TMA engine (twiddles are double-buffered and staged one group ahead).  Tiles are ordered so that the G
+// rows sharing a limb (the partitions of a key switch) are consecutive and reuse the staged twiddles.
+// Static split of the (limb-major) tile list over the persistent CTAs, by COST rather than by count: a tile of a
+// 60-bit limb (integer Shoup path) takes about PP_INT_WEIGHT times as long as an FP64 tile, and those limbs sit at
+// the end of the list -- an even split by count leaves the last CTAs with integer tiles only (measured: 35 % idle).
+constexpr int PP_INT_WEIGHT = 3;
+struct TileRange {
+    int begin, end;
+};
+__device__ __forceinline__ TileRange pp_tile_range(const FastArgs& F, int nlimbs, int tiles_per_limb) {
+    const int l0 = F.slab_rows ? F.slab_t0 : 0;
+    auto weight = [&](int l) { return ((uint64_t)F.q[l0 + l] < SMALL_PRIME_LIMIT && F.force_int != 1) ? 1 : PP_INT_WEIGHT; };
+    long long W = 0;
+    for (int l = 0; l < nlimbs; ++l) W += (long long)weight(l) * tiles_per_limb;
+    const long long lo = W * blockIdx.x / gridDim.x, hi = W * (blockIdx.x + 1) / gridDim.x;
+    auto to_tile = [&](long long x) {
+        long long acc = 0;
+        int tiles = 0;
+        for (int l = 0; l < nlimbs; ++l) {
+            const int w = weight(l);
+            const long long seg = (long long)w * tiles_per_limb;
+            if (x < acc + seg) return tiles + (int)((x - acc) / w);
+            acc += seg;
+            tiles += tiles_per_limb;
+        }
+        return tiles;
+    };
+    return TileRange{to_tile(lo), to_tile(hi)};
+}
+constexpr int PP_SMEM_BYTES = SMEM_BYTES + 2 * FAST_TW_SLOTS * 8 + 32;
+
+template <class A, int B, bool STAGED>
+__device__ __forceinline__ void pp_fwd_block_tile(const FastArgs& F, const int64_t (&raw)[16], int64_t* xb,
+                                                  const typename A::TW* tws, const TileId& tl, int64_t* __restrict__ g) {
+    using T = typename A::T;
+    using TW = typename A::TW;
+    const int tau = threadIdx.x;
+    constexpr int logN = B + 8;
+    constexpr int P1 = B - 4;
+    const unsigned chunk = (unsigned)tl.chunk;
+    const typename A::C c = make_const<A>((uint64_t)F.q[tl.limb]);
+    const TW* __restrict__ W = tw_row<A>(F, tl.limb);
+    T e[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) e[k] = A::load_mid(raw[k]);
+    if constexpr (STAGED)
+        fast_fwd_round<A, 0>(e, TwSharedBlock<TW>{tws, 12 - B, 0, (unsigned)(tau >> P1)}, c);
+    else
+        fast_fwd_round<A, 0>(e, TwGlobal<TW>{W, logN - 4 - P1, (chunk << (8 - P1)) | (unsigned)(tau >> P1)}, c);
+    if constexpr (B >= 8) {
+        constexpr int P2 = B - 8;
+        __syncwarp();   // the warp's slice of the exchange buffer is free (previous tile fully read)
+        smx_store(xb, e, tau, P1);
+        __syncwarp();
+        smx_load(xb, e, tau, P2);
+        if constexpr (STAGED)
+            fast_fwd_round<A, 0>(e, TwSharedBlock<TW>{tws, 12 - B, 4, (unsigned)(tau >> P2)}, c);
+        else
+            fast_fwd_round<A, 0>(e, TwGlobal<TW>{W, logN - 4 - P2, (chunk << (8 - P2)) | (unsigned)(tau >> P2)}, c);
+        if constexpr (B == 9) {
+            __syncwarp();
+            smx_store(xb, e, tau, P2);
+            __syncwarp();
+            smx_load(xb, e, tau, 0);
+            if constexpr (STAGED)
+                fast_fwd_round<A, 3>(e, TwSharedBlock<TW>{tws, 12 - B, B - 4, (unsigned)tau}, c);
+            else
+                fast_fwd_round<A, 3>(e, TwGlobal<TW>{W, logN - 4, (chunk << 8) | (unsigned)tau}, c);
+        }
+    } else if constexpr (B > 4) {
+        __syncwarp();
+        smx_store(xb, e, tau, P1);
+        __syncwarp();
+        smx_load(xb, e, tau, 0);
+        if constexpr (STAGED)
+            fast_fwd_round<A, 8 - B>(e, TwSharedBlock<TW>{tws, 12 - B, B - 4, (unsigned)tau}, c);
+        else
+            fast_fwd_round<A, 8 - B>(e, TwGlobal<TW>{W, logN - 4, (chunk << 8) | (unsigned)tau}, c);
+    }
+    int64_t r[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) r[k] = A::store_canon(e[k], c, false);
+    int64_t* o = g + tau * 16;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) stg256(o, r, j);
+}
+
+// thread 0: stage the block-pass twiddles of (limb, chunk) into `dst` (FP64 rows only), completion on `bar`
+template <int B>
+__device__ __forceinline__ void pp_issue_block_twiddles(const FastArgs& F, int limb, int chunk, double* dst, uint64_t* bar) {
+    const double* W = F.tw_f64 + ((long long)limb << (B + 8));
+    constexpr int unit_log = 12 - B;
+    fence_async_smem();
+    mbar_expect_tx(bar, (unsigned)(((1u << 12) - (1u << unit_log)) * 8u));
+#pragma unroll
+    for (int j = 0; j < B; ++j) {
+        const unsigned cnt = 1u << (j + unit_log);
+        tma_bulk_g2s(dst + (((1u << j) - 1u) << unit_log), W + (1u << (8 + j)) + (size_t)chunk * cnt, cnt * 8u, bar);
+    }
+}
+
+template <int B>
+__global__ void __launch_bounds__(NTT_THREADS, 2) fast_fwd_blockpass_pp(const FastArgs F, long long total_tiles, int G) {
+    extern __shared__ __align__(16) int64_t sm[];
+    int64_t* xb = sm;
+    double* tws = reinterpret_cast<double*>(sm + SMEM_SLOTS);                   // [2][FAST_TW_SLOTS]
+    uint64_t* bar_tw = reinterpret_cast<uint64_t*>(tws + 2 * FAST_TW_SLOTS);    // [2]
+    const int tau = threadIdx.x;
+    constexpr int P1 = B - 4;
+    const int chunks = (1 << (B + 8)) / TILE;
+    const TileRange range = pp_tile_range(F, (int)(total_tiles / ((long long)chunks * G)), chunks * G);
+    const int t_begin = range.begin, t_end = range.end;
+    if (t_begin >= t_end) return;
+    auto staged = [&](int limb) { return (uint64_t)F.q[limb] < SMALL_PRIME_LIMIT && F.force_int != 1; };
+    if (tau == 0) {
+        mbar_init(&bar_tw[0], 1);
+        mbar_init(&bar_tw[1], 1);
+    }
+    __syncthreads();
+    const int zb = zbase(tau, P1);
+    int64_t nxt[16];
+    {
+        const TileId t0 = decode_tile32(F, t_begin, G, chunks);
+        if (tau == 0 && staged(t0.limb)) pp_issue_block_twiddles<B>(F, t0.limb, t0.chunk, tws, &bar_tw[0]);
+        const int64_t* __restrict__ src = F.a + t0.drow * F.a_stride + (long long)t0.chunk * TILE;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) nxt[k] = src[zb | (k << P1)];
+    }
+    int cur_group = -1;
+    unsigned gcount = 0;                 // groups seen by this CTA; group k uses twiddle buffer k & 1
+    unsigned ph0 = 0, ph1 = 0;           // completed phases of the two twiddle barriers
+#pragma unroll 1
+    for (int id = t_begin; id < t_end; ++id) {
+        const TileId tl = decode_tile32(F, id, G, chunks);
+        int64_t cur[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) cur[k] = nxt[k];
+        if (id + 1 < t_end) {            // prefetch the next tile while this one is transformed
+            const TileId tn = decode_tile32(F, id + 1, G, chunks);
+            const int64_t* __restrict__ src = F.a + tn.drow * F.a_stride + (long long)tn.chunk * TILE;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) nxt[k] = src[zb | (k << P1)];
+        }
+        if (tl.group != cur_group) {
+            cur_group = tl.group;
+            __syncthreads();             // every warp is done with the group before: its twiddle buffer can be refilled
+            const int next_first = (tl.group + 1) * G;
+            if (tau == 0 && next_first < t_end) {
+                const TileId tg = decode_tile32(F, next_first, G, chunks);
+                if (staged(tg.limb)) pp_issue_block_twiddles<B>(F, tg.limb, tg.chunk, tws + ((gcount + 1) & 1) * FAST_TW_SLOTS, &bar_tw[(gcount + 1) & 1]);
+            }
+            if (staged(tl.limb)) {
+                const unsigned b = gcount & 1;
+                mbar_wait(&bar_tw[b], (b ? ph1 : ph0) & 1);
+                if (b) ++ph1; else ++ph0;
+            }
+            ++gcount;
+        }
+        const unsigned tb = (gcount - 1) & 1;
+        int64_t* gout = F.a + tl.drow * F.a_stride + (long long)tl.chunk * TILE;
+        const RowId rid{tl.drow, tl.limb};
+        if (fast_use_f64(F, rid))
+            pp_fwd_block_tile<ArithF64, B, true>(F, cur, xb, tws + tb * FAST_TW_SLOTS, tl, gout);
+        else
+            pp_fwd_block_tile<ArithU64, B, false>(F, cur, xb, nullptr, tl, gout);
+    }
+}
+
 // ---- inverse pass B' (levels 0..B-1) ---------------------------------------------------------------------------
 template <class A, int B, bool STAGED>
 __device__ __forceinline__ void fast_inv_block_body(const FastArgs& F, int64_t* sm, int limb, long long drow) {
     using T = typename A::T;
     using TW = typename A::TW;
     const int tau = threadIdx.x;
-    const unsigned chunk = blockIdx.x;
+    const unsigned chunk = grid_chunk(F);
     constexpr int logN = B + 8;
     const typename A::C c = make_const<A>((uint64_t)F.q[limb]);
     int64_t* __restrict__ g = F.a + drow * F.a_stride + (long long)chunk * TILE;
@@ -992,8 +1301,9 @@ __device__ __forceinline__ void fast_inv_block_body(const FastArgs& F, int64_t* 
     uint64_t* bar = reinterpret_cast<uint64_t*>(sm + SMEM_SLOTS + FAST_TW_SLOTS);
     if constexpr (STAGED) stage_block_twiddles(reinterpret_cast<const double*>(W), reinterpret_cast<double*>(tws), bar, B, chunk);
     if (tau == 32) {
-        const long long ra = F.prefetch ? fast_row_ahead(F, F.prefetch) : -1;
-        if (ra >= 0) l2_prefetch_bulk(F.a + ra * F.a_stride + (long long)chunk * TILE, TILE * 8u);
+        unsigned ca = 0;
+        const long long ra = F.prefetch ? fast_row_ahead(F, F.prefetch, ca) : -1;
+        if (ra >= 0) l2_prefetch_bulk(F.a + ra * F.a_stride + (long long)ca * TILE, TILE * 8u);
     }
     T e[16];
     global_to_sm(sm, g, tau);
@@ -1048,6 +1358,96 @@ __device__ __forceinline__ void fast_inv_block_body(const FastArgs& F, int64_t* 
     }
 }
 
+// ---- inverse pass B', WARP-INDEPENDENT form (see fast_fwd_block_body_w) ------------------------------------------------
+// A thread starts from its 16 contiguous coefficients (four 256-bit loads), exchanges stay inside the warp; for
+// B == 9 the last level (distance 256) is taken as the top stage of field [8:5], which keeps it warp-private too.
+template <class A, int B, bool STAGED>
+__device__ __forceinline__ void fast_inv_block_body_w(const FastArgs& F, int64_t* sm, int limb, long long drow) {
+    using T = typename A::T;
+    using TW = typename A::TW;
+    const int tau = threadIdx.x;
+    const unsigned chunk = grid_chunk(F);
+    constexpr int logN = B + 8;
+    const typename A::C c = make_const<A>((uint64_t)F.q[limb]);
+    int64_t* __restrict__ g = F.a + drow * F.a_stride + (long long)chunk * TILE;
+    const TW* __restrict__ W = tw_row<A>(F, limb);
+    TW* tws = reinterpret_cast<TW*>(sm + SMEM_SLOTS);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(sm + SMEM_SLOTS + FAST_TW_SLOTS);
+    if constexpr (STAGED) stage_block_twiddles(reinterpret_cast<const double*>(W), reinterpret_cast<double*>(tws), bar, B, chunk);
+    if (tau == 32) {
+        unsigned ca = 0;
+        const long long ra = F.prefetch ? fast_row_ahead(F, F.prefetch, ca) : -1;
+        if (ra >= 0) l2_prefetch_bulk(F.a + ra * F.a_stride + (long long)ca * TILE, TILE * 8u);
+    }
+    T e[16];
+    {
+        int64_t r[16];
+        const int64_t* in = g + tau * 16;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) ldg256(in, r, j);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) e[k] = A::load(r[k]);
+    }
+    if constexpr (STAGED) {
+        mbar_wait(bar, 0);
+        fast_inv_round<A, 4>(e, TwSharedBlock<TW>{tws, 12 - B, B - 4, (unsigned)tau}, c);
+    } else {
+        fast_inv_round<A, 4>(e, TwGlobal<TW>{W, logN - 4, (chunk << 8) | (unsigned)tau}, c);
+    }
+    if constexpr (B == 4) {
+        int64_t r[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) r[k] = A::store_mid(e[k], c);
+        int64_t* o = g + tau * 16;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) stg256(o, r, j);
+    } else {
+        smx_store(sm, e, tau, 0);
+        __syncwarp();
+        smx_load(sm, e, tau, 4);
+        constexpr int NST = (B >= 8) ? 4 : B - 4;
+        if constexpr (STAGED)
+            fast_inv_round<A, NST>(e, TwSharedBlock<TW>{tws, 12 - B, B - 8, (unsigned)(tau >> 4)}, c);
+        else
+            fast_inv_round<A, NST>(e, TwGlobal<TW>{W, logN - 8, (chunk << 4) | (unsigned)(tau >> 4)}, c);
+        if constexpr (B == 9) {
+            __syncwarp();
+            smx_store(sm, e, tau, 4);
+            __syncwarp();
+            smx_load(sm, e, tau, 5);
+            {   // level with distance 2^8 = top stage of field [8:5]: pairs (k, k+8), one twiddle per 512-point sub-block
+                TW w[8];
+                const unsigned sub = (unsigned)(tau >> 5);
+                if constexpr (STAGED)
+                    w[0] = tws[sub];
+                else
+                    w[0] = __ldg(W + (1u << (logN - 9)) + ((chunk << 3) | sub));
+                A::template gs_stage<3>(e, w, c);
+#pragma unroll
+                for (int k = 0; k < 16; ++k) A::tame(e[k], c);
+            }
+            const int zb = zbase(tau, 5);
+#pragma unroll
+            for (int k = 0; k < 16; ++k) g[zb | (k << 5)] = A::store_mid(e[k], c);
+        } else {
+            const int zb = zbase(tau, 4);
+#pragma unroll
+            for (int k = 0; k < 16; ++k) g[zb | (k << 4)] = A::store_mid(e[k], c);
+        }
+    }
+}
+
+template <int B>
+__global__ void __launch_bounds__(NTT_THREADS, FAST_CTAS_PER_SM) fast_inv_blockpass_w(const FastArgs F) {
+    extern __shared__ __align__(16) int64_t sm[];
+    const RowId rid = fast_row(F);
+    const int limb = rid.limb;
+    if (fast_use_f64(F, rid))
+        fast_inv_block_body_w<ArithF64, B, true>(F, sm, limb, rid.data_row);
+    else
+        fast_inv_block_body_w<ArithU64, B, false>(F, sm, limb, rid.data_row);
+}
+
 template <int B>
 __global__ void __launch_bounds__(NTT_THREADS, FAST_CTAS_PER_SM) fast_inv_blockpass(const FastArgs F) {
     extern __shared__ __align__(16) int64_t sm[];
@@ -1059,6 +1459,133 @@ __global__ void __launch_bounds__(NTT_THREADS, FAST_CTAS_PER_SM) fast_inv_blockp
         fast_inv_block_body<ArithU64, B, false>(F, sm, limb, rid.data_row);
 }
 
+// ---- PERSISTENT, SOFTWARE-PIPELINED inverse block pass (see fast_fwd_blockpass_pp) --------------------------------------
+template <class A, int B, bool STAGED>
+__device__ __forceinline__ void pp_inv_block_tile(const FastArgs& F, const int64_t (&raw)[16], int64_t* xb,
+                                                  const typename A::TW* tws, const TileId& tl, int64_t* __restrict__ g) {
+    using T = typename A::T;
+    using TW = typename A::TW;
+    const int tau = threadIdx.x;
+    constexpr int logN = B + 8;
+    const unsigned chunk = (unsigned)tl.chunk;
+    const typename A::C c = make_const<A>((uint64_t)F.q[tl.limb]);
+    const TW* __restrict__ W = tw_row<A>(F, tl.limb);
+    T e[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) e[k] = A::load(raw[k]);
+    if constexpr (STAGED)
+        fast_inv_round<A, 4>(e, TwSharedBlock<TW>{tws, 12 - B, B - 4, (unsigned)tau}, c);
+    else
+        fast_inv_round<A, 4>(e, TwGlobal<TW>{W, logN - 4, (chunk << 8) | (unsigned)tau}, c);
+    if constexpr (B == 4) {
+        int64_t r[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) r[k] = A::store_mid(e[k], c);
+        int64_t* o = g + tau * 16;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) stg256(o, r, j);
+    } else {
+        __syncwarp();   // the warp's slice of the exchange buffer is free (previous tile fully read)
+        smx_store(xb, e, tau, 0);
+        __syncwarp();
+        smx_load(xb, e, tau, 4);
+        constexpr int NST = (B >= 8) ? 4 : B - 4;
+        if constexpr (STAGED)
+            fast_inv_round<A, NST>(e, TwSharedBlock<TW>{tws, 12 - B, B - 8, (unsigned)(tau >> 4)}, c);
+        else
+            fast_inv_round<A, NST>(e, TwGlobal<TW>{W, logN - 8, (chunk << 4) | (unsigned)(tau >> 4)}, c);
+        if constexpr (B == 9) {
+            __syncwarp();
+            smx_store(xb, e, tau, 4);
+            __syncwarp();
+            smx_load(xb, e, tau, 5);
+            {
+                TW w[8];
+                const unsigned sub = (unsigned)(tau >> 5);
+                if constexpr (STAGED)
+                    w[0] = tws[sub];
+                else
+                    w[0] = __ldg(W + (1u << (logN - 9)) + ((chunk << 3) | sub));
+                A::template gs_stage<3>(e, w, c);
+#pragma unroll
+                for (int k = 0; k < 16; ++k) A::tame(e[k], c);
+            }
+            const int zb = zbase(tau, 5);
+#pragma unroll
+            for (int k = 0; k < 16; ++k) g[zb | (k << 5)] = A::store_mid(e[k], c);
+        } else {
+            const int zb = zbase(tau, 4);
+#pragma unroll
+            for (int k = 0; k < 16; ++k) g[zb | (k << 4)] = A::store_mid(e[k], c);
+        }
+    }
+}
+
+template <int B>
+__global__ void __launch_bounds__(NTT_THREADS, 2) fast_inv_blockpass_pp(const FastArgs F, long long total_tiles, int G) {
+    extern __shared__ __align__(16) int64_t sm[];
+    int64_t* xb = sm;
+    double* tws = reinterpret_cast<double*>(sm + SMEM_SLOTS);                   // [2][FAST_TW_SLOTS]
+    uint64_t* bar_tw = reinterpret_cast<uint64_t*>(tws + 2 * FAST_TW_SLOTS);    // [2]
+    const int tau = threadIdx.x;
+    const int chunks = (1 << (B + 8)) / TILE;
+    const TileRange range = pp_tile_range(F, (int)(total_tiles / ((long long)chunks * G)), chunks * G);
+    const int t_begin = range.begin, t_end = range.end;
+    if (t_begin >= t_end) return;
+    auto staged = [&](int limb) { return (uint64_t)F.q[limb] < SMALL_PRIME_LIMIT && F.force_int != 1; };
+    if (tau == 0) {
+        mbar_init(&bar_tw[0], 1);
+        mbar_init(&bar_tw[1], 1);
+    }
+    __syncthreads();
+    int64_t nxt[16];
+    {
+        const TileId t0 = decode_tile32(F, t_begin, G, chunks);
+        if (tau == 0 && staged(t0.limb)) pp_issue_block_twiddles<B>(F, t0.limb, t0.chunk, tws, &bar_tw[0]);
+        const int64_t* src = F.a + t0.drow * F.a_stride + (long long)t0.chunk * TILE + tau * 16;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) ldg256(src, nxt, j);
+    }
+    long long cur_group = -1;
+    unsigned gcount = 0;
+    unsigned ph0 = 0, ph1 = 0;
+#pragma unroll 1
+    for (int id = t_begin; id < t_end; ++id) {
+        const TileId tl = decode_tile32(F, id, G, chunks);
+        int64_t cur[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) cur[k] = nxt[k];
+        if (id + 1 < t_end) {
+            const TileId tn = decode_tile32(F, id + 1, G, chunks);
+            const int64_t* src = F.a + tn.drow * F.a_stride + (long long)tn.chunk * TILE + tau * 16;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) ldg256(src, nxt, j);
+        }
+        if (tl.group != cur_group) {
+            cur_group = tl.group;
+            __syncthreads();
+            const int next_first = (tl.group + 1) * G;
+            if (tau == 0 && next_first < t_end) {
+                const TileId tg = decode_tile32(F, next_first, G, chunks);
+                if (staged(tg.limb)) pp_issue_block_twiddles<B>(F, tg.limb, tg.chunk, tws + ((gcount + 1) & 1) * FAST_TW_SLOTS, &bar_tw[(gcount + 1) & 1]);
+            }
+            if (staged(tl.limb)) {
+                const unsigned b = gcount & 1;
+                mbar_wait(&bar_tw[b], (b ? ph1 : ph0) & 1);
+                if (b) ++ph1; else ++ph0;
+            }
+            ++gcount;
+        }
+        const unsigned tb = (gcount - 1) & 1;
+        int64_t* gout = F.a + tl.drow * F.a_stride + (long long)tl.chunk * TILE;
+        const RowId rid{tl.drow, tl.limb};
+        if (fast_use_f64(F, rid))
+            pp_inv_block_tile<ArithF64, B, true>(F, cur, xb, tws + tb * FAST_TW_SLOTS, tl, gout);
+        else
+            pp_inv_block_tile<ArithU64, B, false>(F, cur, xb, nullptr, tl, gout);
+    }
+}
+
 // ---- inverse pass A' (levels b..logN-1), x scalar, canonical out ---------------------------------------------
 template <class A, bool STAGED>
 __device__ __forceinline__ void fast_inv_col_body(const FastArgs& F, int64_t* sm, int limb, long long drow) {
@@ -1067,14 +1594,15 @@ __device__ __forceinline__ void fast_inv_col_body(const FastArgs& F, int64_t* sm
     const int tau = threadIdx.x;
     const int b = F.logN - 8;
     const typename A::C c = make_const<A>((uint64_t)F.q[limb]);
-    int64_t* __restrict__ row0 = F.a + drow * F.a_stride + (long long)blockIdx.x * 16;
+    int64_t* __restrict__ row0 = F.a + drow * F.a_stride + (long long)grid_chunk(F) * 16;
     const TW* __restrict__ W = tw_row<A>(F, limb);
     TW* tws = reinterpret_cast<TW*>(sm + SMEM_SLOTS);
     uint64_t* bar = reinterpret_cast<uint64_t*>(sm + SMEM_SLOTS + FAST_TW_SLOTS);
     if constexpr (STAGED) stage_col_twiddles(reinterpret_cast<const double*>(W), reinterpret_cast<double*>(tws), bar);
     {
-        const long long ra = F.prefetch ? fast_row_ahead(F, F.prefetch) : -1;
-        if (ra >= 0) l2_prefetch_line(F.a + ra * F.a_stride + (long long)blockIdx.x * 16 + ((long long)tau << b));
+        unsigned ca = 0;
+        const long long ra = F.prefetch ? fast_row_ahead(F, F.prefetch, ca) : -1;
+        if (ra >= 0) l2_prefetch_line(F.a + ra * F.a_stride + (long long)ca * 16 + ((long long)tau << b));
     }
     T e[16];
     {
@@ -1113,6 +1641,177 @@ __global__ void __launch_bounds__(NTT_THREADS, FAST_CTAS_PER_SM) fast_inv_colpas
         fast_inv_col_body<ArithF64, true>(F, sm, limb, rid.data_row);
     else
         fast_inv_col_body<ArithU64, false>(F, sm, limb, rid.data_row);
+}
+
+// ---- PERSISTENT, SOFTWARE-PIPELINED column passes -------------------------------------------------------------------------
+// Same idea as fast_fwd_blockpass_pp for the strided passes: a CTA walks tiles (256 rows x 16 columns of one limb row),
+// prefetching the next tile's 16 coefficients per thread into registers while the current tile is transformed.  The
+// exchange between the two radix-16 rounds crosses warps here, so there is one CTA barrier per tile; the exchange
+// buffer is double-buffered so that no second barrier is needed.  Tile order: all column chunks of a row, then the
+// next of the G rows that share the limb, then the next limb: the 2 KB of column-pass twiddles are staged once per
+// limb (double-buffered, one limb ahead).
+constexpr int PPC_SMEM_BYTES = 2 * SMEM_BYTES + 2 * 256 * 8 + 32;
+
+struct ColTile {
+    long long drow;
+    int limb, ch, group;
+};
+__device__ __forceinline__ ColTile decode_col_tile(const FastArgs& F, int id, int G, int chunks) {
+    const int per_group = G * chunks;
+    const int group = id / per_group, rem = id - group * per_group;
+    const int g = rem / chunks;
+    ColTile t;
+    t.group = group;
+    t.ch = rem - g * chunks;
+    if (F.slab_rows == 0) {
+        t.limb = group;
+        t.drow = (long long)g * F.period + group;
+    } else {
+        t.limb = F.slab_t0 + group;
+        t.drow = (long long)g * F.group_rows + F.slab_t0 + group;
+    }
+    return t;
+}
+__device__ __forceinline__ void pp_issue_col_twiddles(const FastArgs& F, int limb, double* dst, uint64_t* bar) {
+    fence_async_smem();
+    mbar_expect_tx(bar, 256u * 8u);
+    tma_bulk_g2s(dst, F.tw_f64 + ((long long)limb << F.logN), 256u * 8u, bar);
+}
+
+template <class A, bool STAGED>
+__device__ __forceinline__ void pp_fwd_col_tile(const FastArgs& F, const int64_t (&raw)[16], int64_t* xb,
+                                                const typename A::TW* tws, const ColTile& tl) {
+    using T = typename A::T;
+    using TW = typename A::TW;
+    const int tau = threadIdx.x;
+    const int b = F.logN - 8;
+    const typename A::C c = make_const<A>((uint64_t)F.q[tl.limb]);
+    int64_t* __restrict__ row0 = F.a + tl.drow * F.a_stride + (long long)tl.ch * 16;
+    const TW* __restrict__ W = tw_row<A>(F, tl.limb);
+    T e[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) e[k] = A::load(raw[k]);
+    if (F.scal) {
+        const TW s = scalar_tw<A>(F, tl.limb);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) e[k] = A::mul(e[k], s, c);
+    }
+    if constexpr (STAGED)
+        fast_fwd_round<A, 0>(e, TwSharedCol<TW>{tws, 0, 0u}, c);
+    else
+        fast_fwd_round<A, 0>(e, TwGlobal<TW>{W, 0, 0u}, c);
+    smx_store(xb, e, tau, 8);
+    __syncthreads();
+    smx_load(xb, e, tau, 4);
+    const int hi = tau >> 4, col = tau & 15;
+    if constexpr (STAGED)
+        fast_fwd_round<A, 0>(e, TwSharedCol<TW>{tws, 4, (unsigned)hi}, c);
+    else
+        fast_fwd_round<A, 0>(e, TwGlobal<TW>{W, 4, (unsigned)hi}, c);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) row0[((long long)(hi * 16 + k) << b) + col] = A::store_mid(e[k], c);
+}
+
+template <class A, bool STAGED>
+__device__ __forceinline__ void pp_inv_col_tile(const FastArgs& F, const int64_t (&raw)[16], int64_t* xb,
+                                                const typename A::TW* tws, const ColTile& tl) {
+    using T = typename A::T;
+    using TW = typename A::TW;
+    const int tau = threadIdx.x;
+    const int b = F.logN - 8;
+    const typename A::C c = make_const<A>((uint64_t)F.q[tl.limb]);
+    int64_t* __restrict__ row0 = F.a + tl.drow * F.a_stride + (long long)tl.ch * 16;
+    const TW* __restrict__ W = tw_row<A>(F, tl.limb);
+    T e[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) e[k] = A::load_mid(raw[k]);
+    const int hi = tau >> 4;
+    if constexpr (STAGED)
+        fast_inv_round<A, 4>(e, TwSharedCol<TW>{tws, 4, (unsigned)hi}, c);
+    else
+        fast_inv_round<A, 4>(e, TwGlobal<TW>{W, 4, (unsigned)hi}, c);
+    smx_store(xb, e, tau, 4);
+    __syncthreads();
+    smx_load(xb, e, tau, 8);
+    if constexpr (STAGED)
+        fast_inv_round<A, 4>(e, TwSharedCol<TW>{tws, 0, 0u}, c);
+    else
+        fast_inv_round<A, 4>(e, TwGlobal<TW>{W, 0, 0u}, c);
+    const TW s = scalar_tw<A>(F, tl.limb);
+    const int r0 = tau >> 4, col = tau & 15;
+#pragma unroll
+    for (int k = 0; k < 16; ++k)
+        row0[((long long)(r0 + 16 * k) << b) + col] = A::store_canon(A::mul(e[k], s, c), c, F.centred != 0);
+}
+
+template <bool FWD>
+__global__ void __launch_bounds__(NTT_THREADS, 2) fast_colpass_pp(const FastArgs F, long long total_tiles, int G) {
+    extern __shared__ __align__(16) int64_t sm[];
+    double* tws = reinterpret_cast<double*>(sm + 2 * SMEM_SLOTS);               // [2][256]
+    uint64_t* bar_tw = reinterpret_cast<uint64_t*>(tws + 2 * 256);               // [2]
+    const int tau = threadIdx.x;
+    const int b = F.logN - 8;
+    const int chunks = (1 << F.logN) / TILE;
+    const TileRange range = pp_tile_range(F, (int)(total_tiles / ((long long)chunks * G)), chunks * G);
+    const int t_begin = range.begin, t_end = range.end;
+    if (t_begin >= t_end) return;
+    auto staged = [&](int limb) { return (uint64_t)F.q[limb] < SMALL_PRIME_LIMIT && F.force_int != 1; };
+    if (tau == 0) {
+        mbar_init(&bar_tw[0], 1);
+        mbar_init(&bar_tw[1], 1);
+    }
+    __syncthreads();
+    // element k of a thread: forward reads rows (tau>>4) + 16k, inverse rows 16 (tau>>4) + k, column tau & 15
+    const long long off0 = FWD ? ((long long)(tau >> 4) << b) + (tau & 15) : ((long long)((tau >> 4) * 16) << b) + (tau & 15);
+    const long long kstep = FWD ? (16ll << b) : (1ll << b);
+    int64_t nxt[16];
+    {
+        const ColTile t0 = decode_col_tile(F, t_begin, G, chunks);
+        if (tau == 0 && staged(t0.limb)) pp_issue_col_twiddles(F, t0.limb, tws, &bar_tw[0]);
+        const int64_t* __restrict__ src = F.a + t0.drow * F.a_stride + (long long)t0.ch * 16 + off0;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) nxt[k] = src[k * kstep];
+    }
+    long long cur_group = -1;
+    unsigned gcount = 0, ph0 = 0, ph1 = 0, it = 0;
+#pragma unroll 1
+    for (int id = t_begin; id < t_end; ++id, ++it) {
+        const ColTile tl = decode_col_tile(F, id, G, chunks);
+        int64_t cur[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) cur[k] = nxt[k];
+        if (id + 1 < t_end) {
+            const ColTile tn = decode_col_tile(F, id + 1, G, chunks);
+            const int64_t* __restrict__ src = F.a + tn.drow * F.a_stride + (long long)tn.ch * 16 + off0;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) nxt[k] = src[k * kstep];
+        }
+        if (tl.group != cur_group) {
+            cur_group = tl.group;
+            __syncthreads();             // every warp is done with the limb before: its twiddle buffer can be refilled
+            const int next_first = (tl.group + 1) * G * chunks;
+            if (tau == 0 && next_first < t_end) {
+                const ColTile tg = decode_col_tile(F, next_first, G, chunks);
+                if (staged(tg.limb)) pp_issue_col_twiddles(F, tg.limb, tws + ((gcount + 1) & 1) * 256, &bar_tw[(gcount + 1) & 1]);
+            }
+            if (staged(tl.limb)) {
+                const unsigned bb = gcount & 1;
+                mbar_wait(&bar_tw[bb], (bb ? ph1 : ph0) & 1);
+                if (bb) ++ph1; else ++ph0;
+            }
+            ++gcount;
+        }
+        const double* tw = tws + ((gcount - 1) & 1) * 256;
+        int64_t* xb = sm + (it & 1) * SMEM_SLOTS;   // alternate exchange buffers: one barrier per tile is enough
+        const RowId rid{tl.drow, tl.limb};
+        if (fast_use_f64(F, rid)) {
+            if constexpr (FWD) pp_fwd_col_tile<ArithF64, true>(F, cur, xb, tw, tl);
+            else pp_inv_col_tile<ArithF64, true>(F, cur, xb, tw, tl);
+        } else {
+            if constexpr (FWD) pp_fwd_col_tile<ArithU64, false>(F, cur, xb, nullptr, tl);
+            else pp_inv_col_tile<ArithU64, false>(F, cur, xb, nullptr, tl);
+        }
+    }
 }
 
 // ---- table construction ----------------------------------------------------------------------------------------

@@ -11,7 +11,8 @@ from pathlib import Path
 
 _PKG = Path(__file__).resolve().parent
 _CSRC = _PKG.parent / "csrc"
-_LIBPATH = _CSRC / "libckks_b200.so"
+# CKKS_B200_LIB: load a differently-tuned build of the same sources (kernel experiments); default = the in-tree library
+_LIBPATH = Path(os.environ["CKKS_B200_LIB"]).resolve() if os.environ.get("CKKS_B200_LIB") else _CSRC / "libckks_b200.so"
 
 _i64p = ctypes.c_void_p
 _i64 = ctypes.c_int64
@@ -22,6 +23,8 @@ _vp = ctypes.c_void_p
 SIGNATURES = {
     "ckks_abi_version": [],
     "ckks_set_option": [_int, _int],
+    "ckks_get_option": [_int],
+    "ckks_launch_count": [],
     "ckks_mont_mult": [_i64p, _i64, _i64p, _i64, _i64p, _i64, _int, _int, _i64p, _i64p, _i64p, _i64p, _vp],
     "ckks_mont_enter": [_i64p, _i64, _i64p, _int, _int, _i64p, _i64p, _i64p, _i64p, _vp],
     "ckks_ntt": [_i64p, _i64, _int, _int, _i64p, _i64, _i64p, _i64p, _i64p, _i64p, _i64p, _i64p, _vp],
@@ -53,7 +56,7 @@ SIGNATURES = {
     "ckks_exec_keyswitch_stage": [_vp, _vp, _i64, _vp, _vp, _i64, _i64p, _i64p, _i64, _i64p, _i64p, _i64, _i64p, _vp],
     "ckks_exec_keyswitch_ws_elems": [_int, _int, _int, _int],
 }
-RESTYPES = {"ckks_exec_keyswitch_ws_elems": ctypes.c_int64}
+RESTYPES = {"ckks_exec_keyswitch_ws_elems": ctypes.c_int64, "ckks_launch_count": ctypes.c_int64}
 
 ERRORS = {-1: "CKKS_E_BADARG (null pointer / bad size)", -2: "CKKS_E_LOGN (logN outside [12,17])",
           -3: "CKKS_E_ALIGN (pointer/stride not 16-byte aligned)"}
@@ -82,29 +85,30 @@ def _load():
     return lib
 
 
-# kernels launched per entry point (for bench.py's gpu_launches accounting)
-KERNELS_PER_CALL = {"ckks_abi_version": 0, "ckks_set_option": 0, "ckks_ntt": 2, "ckks_intt": 2, "ckks_moddown": 2, "ckks_ntt_fast": 2,
-                    "ckks_intt_fast": 2, "ckks_exec_tensor_stage": 10, "ckks_exec_keyswitch_stage": 12,
-                    "ckks_exec_keyswitch_ws_elems": 0}
-
-
 class _Counted:
-    """the loaded library with a launch counter: lib.<entry>(...) -> int status"""
+    """the loaded library; `launches` = kernels launched so far, counted inside the library itself
+    (ckks_launch_count: one tick per kernel launch), so bench.py's gpu_launches is exact"""
 
     def __init__(self, cdll):
         self._cdll = cdll
-        self.launches = 0
         for name in SIGNATURES:
-            setattr(self, name, self._wrap(getattr(cdll, name), KERNELS_PER_CALL.get(name, 1)))
+            setattr(self, name, getattr(cdll, name))
 
-    def _wrap(self, fn, n):
-        def call(*args):
-            self.launches += n
-            return fn(*args)
-        return call
+    @property
+    def launches(self):
+        return int(self._cdll.ckks_launch_count())
 
 
 lib = _Counted(_load())
+OPTION_KEYS = (1, 2, 3, 4, 5, 6, 7, 8)
+_OPTION_DEFAULTS = {k: lib.ckks_get_option(k) for k in OPTION_KEYS}
+
+
+def option_defaults():
+    """the library's built-in knob values (before CKKS_B200_OPTIONS), e.g. to restore them after a test"""
+    return dict(_OPTION_DEFAULTS)
+
+
 # tuning switches of the library (ckks_set_option): CKKS_B200_OPTIONS="1=1,2=28"
 for _kv in filter(None, os.environ.get("CKKS_B200_OPTIONS", "").split(",")):
     _k, _v = _kv.split("=")

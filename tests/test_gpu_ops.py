@@ -220,11 +220,28 @@ def test_fused_keyswitch_pieces_bit_exact(logN, alpha, K):
         assert eq(got, ref2), "automorphism+canon"
 
 
+# kernel variants of the fast transforms selected by ckks_set_option (key, value); every one must give the same bits
+FAST_VARIANTS = {"default": [], "classic": [(3, 0), (4, 0)], "warp": [(3, 1), (4, 0)], "pp": [(3, 2), (4, 1)],
+                 "pp-3ctas": [(3, 2), (4, 1), (7, 3)], "swapped-grid": [(8, 1)], "warp+swapped": [(3, 1), (8, 1)]}   # 3 persistent CTAs in total: each walks many tiles and limbs
+
+
 @pytest.mark.parametrize("logN", [12, 13, 14, 15, 16, 17])
 @pytest.mark.parametrize("force_int", [False, True])
-def test_fast_transforms_equal_reference_sequences_after_reduction(logN, force_int):
+@pytest.mark.parametrize("variant", list(FAST_VARIANTS))
+def test_fast_transforms_equal_reference_sequences_after_reduction(logN, force_int, variant):
     """ckks_ntt_fast == {enter_ntt; reduce_2q}, ckks_intt_fast == intt_exit_reduce[_signed] (canonical outputs):
     FP64 error-free butterflies for the scale primes, Shoup/Harvey for the 60-bit primes."""
+    from liberate_b200._lib import lib, option_defaults
+    try:
+        for k, v in FAST_VARIANTS[variant]:
+            lib.ckks_set_option(k, v)
+        _check_fast_transforms(logN, force_int)
+    finally:
+        for k, v in option_defaults().items():
+            lib.ckks_set_option(k, v)
+
+
+def _check_fast_transforms(logN, force_int):
     from liberate_b200.ntt import fused
     P = O.Params(primes_for(logN, 3, 2), logN)
     t = packs(P)
@@ -270,9 +287,17 @@ def test_fast_transforms_equal_reference_sequences_after_reduction(logN, force_i
         O.C.intt(r, P.ipsi, P.Ninv, P._2q, *P.mont, exit_mode=mode)
         assert eq(y, r), f"intt_fast centred={centred}"
     # batched rows: 2 x C rows share the C limbs' constants (period = C)
-    big = T(np.concatenate([a, a]))
+    reps = 5
+    big = T(np.concatenate([a] * reps))
     fused.ntt_fast(big, sh_f, dbl_f, qd, period=C, force_int=force_int)
-    assert eq(big[:C], ref2) and eq(big[C:], ref2), "batched period"
+    for i in range(reps):
+        assert eq(big[i * C:(i + 1) * C], ref2), f"batched period, replica {i}"
+    big = T(np.concatenate([lazy] * reps))
+    fused.intt_fast(big, sh_i, dbl_i, qd, T(ex), T(shoup(ex)), period=C, centred=False, force_int=force_int)
+    r = lazy.copy()
+    O.C.intt(r, P.ipsi, P.Ninv, P._2q, *P.mont, exit_mode=2)
+    for i in range(reps):
+        assert eq(big[i * C:(i + 1) * C], r), f"batched inverse, replica {i}"
 
 
 @pytest.mark.parametrize("logN", [12, 14, 16, 17])
