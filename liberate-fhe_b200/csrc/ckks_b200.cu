@@ -439,7 +439,7 @@ static int launch_inv_block(const NttArgs& A, dim3 grid, cudaStream_t st) {
 int g_persist = 0;
 int g_prefetch = PREFETCH_ROWS_AHEAD;   // ckks_set_option(2, rows_ahead); 0 disables the L2 prefetch   // 1: persistent TMA-pipelined block pass (ckks_set_option(1, v))
 int g_skip = 0;   // ckks_set_option(5, mask): measurement only -- bit 0 skips the column pass, bit 1 the block pass
-int g_warp = 0;   // ckks_set_option(3, v): 1 = warp-independent block passes with 256-bit global accesses
+int g_warp = 1;   // ckks_set_option(3, v): 0 classic, 1 = warp-independent block passes with 256-bit global accesses (default), 2 = persistent
 inline bool aligned32(const void* p, long long stride) { return (((uintptr_t)p) & 31) == 0 && (stride & 3) == 0; }
 int sm_count() {
     static int n = 0;
@@ -454,6 +454,7 @@ int sm_count() {
 // persistent software-pipelined ("pp") kernels: rows must tile into G rows per limb and be 32-byte aligned
 int g_swap = 0;    // ckks_set_option(8, v): 1 = (row, chunk) grid order for the one-tile-per-CTA kernels
 inline dim3 tile_grid(dim3 grid) { return g_swap ? dim3(grid.y, grid.x) : grid; }
+int g_slab_mb = 100; // ckks_set_option(9, v): MB of extended rows per key-switch slab (L2 residency vs grid size)
 int g_colpp = 0;   // ckks_set_option(4, v): 1 = persistent software-pipelined column passes
 int g_pp_ctas = 2; // ckks_set_option(6, v): persistent CTAs per SM
 int g_pp_cap = 0;  // ckks_set_option(7, v): cap on the persistent grid (0 = none; tests use it to make every CTA walk many tiles)
@@ -536,6 +537,69 @@ static int launch_fast_inv_block(const FastArgs& F, dim3 grid, cudaStream_t st) 
     fast_inv_blockpass<B><<<tile_grid(grid), NTT_THREADS, FAST_SMEM_BYTES, st>>>(F);
     return launch_status();
 }
+static int launch_fast_fwd_block_any(const FastArgs& F, dim3 grid, cudaStream_t st, int logN) {
+    switch (logN - 8) {
+        case 4: return launch_fast_fwd_block<4>(F, grid, st);
+        case 5: return launch_fast_fwd_block<5>(F, grid, st);
+        case 6: return launch_fast_fwd_block<6>(F, grid, st);
+        case 7: return launch_fast_fwd_block<7>(F, grid, st);
+        case 8: return launch_fast_fwd_block<8>(F, grid, st);
+        case 9: return launch_fast_fwd_block<9>(F, grid, st);
+    }
+    return CKKS_E_LOGN;
+}
+static int launch_fast_inv_block_any(const FastArgs& F, dim3 grid, cudaStream_t st, int logN) {
+    switch (logN - 8) {
+        case 4: return launch_fast_inv_block<4>(F, grid, st);
+        case 5: return launch_fast_inv_block<5>(F, grid, st);
+        case 6: return launch_fast_inv_block<6>(F, grid, st);
+        case 7: return launch_fast_inv_block<7>(F, grid, st);
+        case 8: return launch_fast_inv_block<8>(F, grid, st);
+        case 9: return launch_fast_inv_block<9>(F, grid, st);
+    }
+    return CKKS_E_LOGN;
+}
+int g_ntt_slab_mb = 24;   // ckks_set_option(11, v): MB of rows per slab of a big batched transform
+
+// ---- side streams: independent slabs of one call run on up to MAX_PIPES internal streams so that the tail of one
+// kernel overlaps the head of the next slab's kernels (small grids leave SMs idle at wave boundaries otherwise).
+// fork(): the side streams wait for everything already queued on the caller's stream; join(): the caller's stream
+// waits for the side streams.  Streams and events are created once per device and reused.
+constexpr int MAX_PIPES = 4;
+int g_pipes = 2;   // ckks_set_option(10, v): side streams used by the slab pipelines (1 = everything on the caller's stream)
+struct SidePipes {
+    bool ready = false;
+    cudaStream_t s[MAX_PIPES];
+    cudaEvent_t fork_ev, join_ev[MAX_PIPES];
+};
+SidePipes g_side[64];
+SidePipes* side_pipes() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    SidePipes& p = g_side[dev];
+    if (!p.ready) {
+        for (int i = 0; i < MAX_PIPES; ++i) {
+            if (cudaStreamCreateWithFlags(&p.s[i], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+            if (cudaEventCreateWithFlags(&p.join_ev[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        }
+        if (cudaEventCreateWithFlags(&p.fork_ev, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        p.ready = true;
+    }
+    return &p;
+}
+int pipes_fork(SidePipes* p, cudaStream_t main_st, int n) {
+    if (cudaEventRecord(p->fork_ev, main_st) != cudaSuccess) return (int)cudaGetLastError();
+    for (int i = 0; i < n; ++i)
+        if (cudaStreamWaitEvent(p->s[i], p->fork_ev, 0) != cudaSuccess) return (int)cudaGetLastError();
+    return 0;
+}
+int pipes_join(SidePipes* p, cudaStream_t main_st, int n) {
+    for (int i = 0; i < n; ++i) {
+        if (cudaEventRecord(p->join_ev[i], p->s[i]) != cudaSuccess) return (int)cudaGetLastError();
+        if (cudaStreamWaitEvent(main_st, p->join_ev[i], 0) != cudaSuccess) return (int)cudaGetLastError();
+    }
+    return 0;
+}
 }  // namespace
 
 #define CHECK_PTRS(...)                                  \
@@ -544,6 +608,46 @@ static int launch_fast_inv_block(const FastArgs& F, dim3 grid, cudaStream_t st) 
         for (const void* x : _p)                         \
             if (!x) return CKKS_E_BADARG;                \
     } while (0)
+
+static int intt_fast_impl(int64_t* a, int64_t as, int rows, int period, int logN, const void* tw_u64, const double* tw_f64,
+                   const int64_t* q, const int64_t* scal, const uint64_t* scal_sh, int centred, int force_int,
+                   void* stream, int in_raw) {
+    CHECK_PTRS(a, tw_u64, q, scal, scal_sh);
+    if (rows <= 0 || period <= 0) return CKKS_E_BADARG;
+    if (!force_int && !tw_f64) return CKKS_E_BADARG;
+    if (logN < 12 || logN > 17) return CKKS_E_LOGN;
+    if (!row_ok(a, as) || !aligned16(tw_u64) || (tw_f64 && !aligned16(tw_f64))) return CKKS_E_ALIGN;
+    FastArgs F{a, as, reinterpret_cast<const ulonglong2*>(tw_u64), tw_f64, q, scal, scal_sh, period, logN, centred, force_int, 0, 0, 0, g_prefetch, g_swap, 0, in_raw, 0};
+    cudaStream_t st = S(stream);
+    const dim3 grid((1 << logN) / TILE, rows);
+    const long long bytes = (long long)rows * 8 << logN;
+    const int nslabs = (int)((bytes + ((long long)g_ntt_slab_mb << 20) - 1) / ((long long)g_ntt_slab_mb << 20));
+    SidePipes* pipes = (bytes > (96ll << 20) && g_pipes > 1 && !g_skip && !g_persist && g_warp != 2 && !g_colpp) ? side_pipes() : nullptr;
+    if (pipes) {   // row slabs on two internal streams, see ckks_ntt_fast
+        const int npipes = g_pipes < nslabs ? g_pipes : nslabs;
+        const int per = (rows + nslabs - 1) / nslabs;
+        int rc = pipes_fork(pipes, st, npipes);
+        if (rc) return rc;
+        int k = 0;
+        for (int r0 = 0; r0 < rows; r0 += per, ++k) {
+            const int r1 = r0 + per < rows ? r0 + per : rows;
+            FastArgs Fs = F;
+            Fs.a = a + (long long)r0 * as;
+            Fs.row0 = r0 % period;
+            const dim3 g((1 << logN) / TILE, r1 - r0);
+            cudaStream_t ss = pipes->s[k % npipes];
+            rc = launch_fast_inv_block_any(Fs, g, ss, logN);
+            if (rc) return rc;
+            rc = launch_fast_col(false, Fs, g, ss);
+            if (rc) return rc;
+        }
+        return pipes_join(pipes, st, npipes);
+    }
+    int rc = (g_skip & 2) ? 0 : launch_fast_inv_block_any(F, grid, st, logN);
+    if (rc) return rc;
+    if (g_skip & 1) return 0;
+    return launch_fast_col(false, F, grid, st);
+}
 
 extern "C" {
 
@@ -560,6 +664,9 @@ int ckks_get_option(int key) {
     if (key == 6) return g_pp_ctas;
     if (key == 7) return g_pp_cap;
     if (key == 8) return g_swap;
+    if (key == 9) return g_slab_mb;
+    if (key == 10) return g_pipes;
+    if (key == 11) return g_ntt_slab_mb;
     return CKKS_E_BADARG;
 }
 
@@ -572,6 +679,9 @@ int ckks_set_option(int key, int value) {
     if (key == 6) { if (value < 1 || value > 4) return CKKS_E_BADARG; g_pp_ctas = value; return 0; }
     if (key == 7) { g_pp_cap = value; return 0; }
     if (key == 8) { g_swap = value; return 0; }
+    if (key == 9) { if (value < 1) return CKKS_E_BADARG; g_slab_mb = value; return 0; }
+    if (key == 10) { if (value < 1 || value > MAX_PIPES) return CKKS_E_BADARG; g_pipes = value; return 0; }
+    if (key == 11) { if (value < 1) return CKKS_E_BADARG; g_ntt_slab_mb = value; return 0; }
     return CKKS_E_BADARG;
 }
 
@@ -717,50 +827,49 @@ int ckks_ntt_fast(int64_t* a, int64_t as, int rows, int period, int logN, const 
     if (!force_int && !tw_f64) return CKKS_E_BADARG;
     if (logN < 12 || logN > 17) return CKKS_E_LOGN;
     if (!row_ok(a, as) || !aligned16(tw_u64) || (tw_f64 && !aligned16(tw_f64))) return CKKS_E_ALIGN;
-    FastArgs F{a, as, reinterpret_cast<const ulonglong2*>(tw_u64), tw_f64, q, scal, scal_sh, period, logN, 0, force_int, 0, 0, 0, g_prefetch, g_swap};
+    FastArgs F{a, as, reinterpret_cast<const ulonglong2*>(tw_u64), tw_f64, q, scal, scal_sh, period, logN, 0, force_int, 0, 0, 0, g_prefetch, g_swap, 0, 0, 0};
     cudaStream_t st = S(stream);
     const dim3 grid((1 << logN) / TILE, rows);
+    // Big batches run as row slabs on two internal streams: the column pass of slab s+1 overlaps the block pass of
+    // slab s and, more importantly, the hand-off between the two passes of a slab stays in L2 instead of going through
+    // HBM twice (DRAM traffic = the algorithmic 16 B per coefficient).
+    const long long bytes = (long long)rows * 8 << logN;
+    const int nslabs = (int)((bytes + ((long long)g_ntt_slab_mb << 20) - 1) / ((long long)g_ntt_slab_mb << 20));
+    SidePipes* pipes = (bytes > (96ll << 20) && g_pipes > 1 && !g_skip && !g_persist && g_warp != 2 && !g_colpp) ? side_pipes() : nullptr;
+    if (pipes) {
+        const int npipes = g_pipes < nslabs ? g_pipes : nslabs;
+        const int per = (rows + nslabs - 1) / nslabs;
+        int rc = pipes_fork(pipes, st, npipes);
+        if (rc) return rc;
+        int k = 0;
+        for (int r0 = 0; r0 < rows; r0 += per, ++k) {
+            const int r1 = r0 + per < rows ? r0 + per : rows;
+            FastArgs Fs = F;
+            Fs.a = a + (long long)r0 * as;
+            Fs.row0 = r0 % period;
+            const dim3 g((1 << logN) / TILE, r1 - r0);
+            cudaStream_t ss = pipes->s[k % npipes];
+            rc = launch_fast_col(true, Fs, g, ss);
+            if (rc) return rc;
+            Fs.scal = nullptr;
+            rc = launch_fast_fwd_block_any(Fs, g, ss, logN);
+            if (rc) return rc;
+        }
+        return pipes_join(pipes, st, npipes);
+    }
     if (!(g_skip & 1)) {
         int rc = launch_fast_col(true, F, grid, st);
         if (rc) return rc;
     }
     if (g_skip & 2) return 0;
     F.scal = nullptr;
-    switch (logN - 8) {
-        case 4: return launch_fast_fwd_block<4>(F, grid, st);
-        case 5: return launch_fast_fwd_block<5>(F, grid, st);
-        case 6: return launch_fast_fwd_block<6>(F, grid, st);
-        case 7: return launch_fast_fwd_block<7>(F, grid, st);
-        case 8: return launch_fast_fwd_block<8>(F, grid, st);
-        case 9: return launch_fast_fwd_block<9>(F, grid, st);
-    }
-    return CKKS_E_LOGN;
+    return launch_fast_fwd_block_any(F, grid, st, logN);
 }
 
 int ckks_intt_fast(int64_t* a, int64_t as, int rows, int period, int logN, const void* tw_u64, const double* tw_f64,
                    const int64_t* q, const int64_t* scal, const uint64_t* scal_sh, int centred, int force_int,
                    void* stream) {
-    CHECK_PTRS(a, tw_u64, q, scal, scal_sh);
-    if (rows <= 0 || period <= 0) return CKKS_E_BADARG;
-    if (!force_int && !tw_f64) return CKKS_E_BADARG;
-    if (logN < 12 || logN > 17) return CKKS_E_LOGN;
-    if (!row_ok(a, as) || !aligned16(tw_u64) || (tw_f64 && !aligned16(tw_f64))) return CKKS_E_ALIGN;
-    FastArgs F{a, as, reinterpret_cast<const ulonglong2*>(tw_u64), tw_f64, q, scal, scal_sh, period, logN, centred, force_int, 0, 0, 0, g_prefetch, g_swap};
-    cudaStream_t st = S(stream);
-    const dim3 grid((1 << logN) / TILE, rows);
-    int rc = CKKS_E_LOGN;
-    if (g_skip & 2) rc = 0;
-    else switch (logN - 8) {
-        case 4: rc = launch_fast_inv_block<4>(F, grid, st); break;
-        case 5: rc = launch_fast_inv_block<5>(F, grid, st); break;
-        case 6: rc = launch_fast_inv_block<6>(F, grid, st); break;
-        case 7: rc = launch_fast_inv_block<7>(F, grid, st); break;
-        case 8: rc = launch_fast_inv_block<8>(F, grid, st); break;
-        case 9: rc = launch_fast_inv_block<9>(F, grid, st); break;
-    }
-    if (rc) return rc;
-    if (g_skip & 1) return 0;
-    return launch_fast_col(false, F, grid, st);
+    return intt_fast_impl(a, as, rows, period, logN, tw_u64, tw_f64, q, scal, scal_sh, centred, force_int, stream, 0);
 }
 
 // ---- level 2 -----------------------------------------------------------------------------------------
@@ -915,36 +1024,36 @@ int ckks_exec_keyswitch_stage(const ckks_level_t* lv, const int64_t* const* digi
         X.out = ext;
         X.E = E;
         X.N = N;
-        const long long slab_budget = 64ll << 20;   // bytes of extended rows per slab
+        X.raw = 1;   // scale-prime rows travel as raw doubles from the extension to the inverse transform
+        const long long slab_budget = (long long)g_slab_mb << 20;   // bytes of extended rows per slab
         const long long all_bytes = (long long)P * E * N * 8;
         const int nslabs = (int)((all_bytes + slab_budget - 1) / slab_budget);
         const int slab = (E + nslabs - 1) / nslabs;
-        cudaStream_t st = S(stream);
-        for (int t0 = 0; t0 < E; t0 += slab) {
+        cudaStream_t main_st = S(stream);
+        SidePipes* pipes = (nslabs > 1 && g_pipes > 1) ? side_pipes() : nullptr;
+        const int npipes = pipes ? (g_pipes < nslabs ? g_pipes : nslabs) : 0;
+        if (pipes) RC(pipes_fork(pipes, main_st, npipes));
+        int slab_no = 0;
+        for (int t0 = 0; t0 < E; t0 += slab, ++slab_no) {
+            cudaStream_t st = pipes ? pipes->s[slab_no % npipes] : main_st;
             const int t1 = (t0 + slab < E) ? t0 + slab : E;
             const dim3 eg((N / 2 + 255) / 256, P);
+            if (t1 - t0 > EXT_MAX_E) return CKKS_E_BADARG;
             if (lv->amax <= 2) k_extend_fast<2><<<eg, 256, 0, st>>>(X, t0, t1);
             else if (lv->amax <= 4) k_extend_fast<4><<<eg, 256, 0, st>>>(X, t0, t1);
             else k_extend_fast<8><<<eg, 256, 0, st>>>(X, t0, t1);
             RC(launch_status());
             FastArgs F{ext, N, reinterpret_cast<const ulonglong2*>(lv->twf_u64), lv->twf_f64, lv->q, nullptr, nullptr, E,
-                       lv->logN, 0, 0, t1 - t0, E, t0, g_prefetch, g_swap};
+                       lv->logN, 0, 0, t1 - t0, E, t0, g_prefetch, g_swap, 0, 1, 1};
             const dim3 grid(N / TILE, P * (t1 - t0));
             RC(launch_fast_col(true, F, grid, st));
-            switch (lv->logN - 8) {
-                case 4: RC(launch_fast_fwd_block<4>(F, grid, st)); break;
-                case 5: RC(launch_fast_fwd_block<5>(F, grid, st)); break;
-                case 6: RC(launch_fast_fwd_block<6>(F, grid, st)); break;
-                case 7: RC(launch_fast_fwd_block<7>(F, grid, st)); break;
-                case 8: RC(launch_fast_fwd_block<8>(F, grid, st)); break;
-                case 9: RC(launch_fast_fwd_block<9>(F, grid, st)); break;
-                default: return CKKS_E_LOGN;
-            }
+            RC(launch_fast_fwd_block_any(F, grid, st, lv->logN));
             InnerArgs I{ext, k0_ptrs, k1_ptrs, ksk_stride, acc, acc + (long long)E * N, lv->Rinv, lv->q, lv->_2q, lv->ql, lv->qh,
-                        lv->kl, lv->kh, P, E, N, t0};
+                        lv->kl, lv->kh, P, E, N, t0, 1};
             k_ksk_inner_fast<<<dim3((N / 2 + 255) / 256, t1 - t0), 256, 0, st>>>(I);
             RC(launch_status());
         }
+        if (pipes) RC(pipes_join(pipes, main_st, npipes));
     } else {
         k_extend_batched<<<ew_grid(N, P * E), EW_THREADS, 0, S(stream)>>>(digit_ptrs, digit_stride, lv->part_alpha, ext, N, E,
                                                                           N, lv->Rs, lv->Lenter, m);
@@ -953,8 +1062,8 @@ int ckks_exec_keyswitch_stage(const ckks_level_t* lv, const int64_t* const* digi
         RC(ckks_ksk_inner(ext, N, P, k0_ptrs, k1_ptrs, ksk_stride, acc, acc + (long long)E * N, N, E, N, lv->_2q, lv->ql,
                           lv->qh, lv->kl, lv->kh, stream));
     }
-    RC(ckks_intt_fast(acc, N, 2 * E, E, lv->logN, lv->twi_u64, lv->twi_f64, lv->q, lv->sExit, (const uint64_t*)lv->sExit_sh, 0, 0,
-                      stream));
+    RC(intt_fast_impl(acc, N, 2 * E, E, lv->logN, lv->twi_u64, lv->twi_f64, lv->q, lv->sExit, (const uint64_t*)lv->sExit_sh, 0, 0,
+                      stream, (lv->Hm && lv->Rinv) ? 1 : 0));
     int64_t* outs[2] = {out0, out1};
     const int64_t* adds[2] = {add0, add1};
     const int Ls = lv->Pinv ? lv->L_small : 0;   // leading ordinary rows handled by the FP64 kernel

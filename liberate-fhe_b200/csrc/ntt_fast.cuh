@@ -63,6 +63,9 @@ struct ArithF64 {
         if (!centred) r = (r < 0.0) ? __dadd_rn(r, c.q) : r;
         return d2i(r);
     }
+    // hand-off with the neighbouring fused kernels: raw != 0 means the buffer holds doubles (integer-valued, |v| < 2^51)
+    static __device__ __forceinline__ T load_in(int64_t x, int raw) { return raw ? load_mid(x) : load(x); }
+    static __device__ __forceinline__ int64_t store_out(T v, const C& c, int raw) { return raw ? store_mid(v, c) : store_canon(v, c, false); }
     static __device__ __forceinline__ T mul(T v, TW w, const C& c) { return f64_mulmod(v, w, c); }
     static __device__ __forceinline__ void ct(T& U, T& V, TW w, const C& c) {
         const T r = f64_mulmod(V, w, c);
@@ -181,6 +184,9 @@ struct ArithU64 {
         if (centred) r = (r > (int64_t)(c.q >> 1)) ? r - (int64_t)c.q : r;
         return r;
     }
+    // integer rows never use the raw-double hand-off: their buffers always hold canonical / lazy integers
+    static __device__ __forceinline__ T load_in(int64_t x, int raw) { return load(x); }
+    static __device__ __forceinline__ int64_t store_out(T v, const C& c, int raw) { return store_canon(v, c, false); }
     static __device__ __forceinline__ T mul(T v, TW w, const C& c) { return shoup_mul(v, w.x, w.y, c.q); }
     static __device__ __forceinline__ void ct(T& U, T& V, TW w, const C& c) {
         const T u = (U >= c.q2) ? U - c.q2 : U;
@@ -351,6 +357,8 @@ struct FastArgs {
     int slab_rows, group_rows, slab_t0;
     int prefetch;               // rows ahead whose tile is pulled into L2 by every CTA (0 = off)
     int swap_grid;              // one-tile-per-CTA kernels: blockIdx.x = row, blockIdx.y = chunk
+    int row0;                   // plain rows: limb of grid row r is (row0 + r) % period (row slabs of one batch)
+    int in_raw, out_raw;        // FP64 rows: the input / the forward output are raw doubles (fused key switch), not int64
 };
 
 // grid mapping of the one-tile-per-CTA kernels: (chunk, row) by default; swapped (row, chunk) when F.swap_grid is
@@ -386,7 +394,7 @@ __device__ __forceinline__ long long fast_row_ahead(const FastArgs& F, int ahead
 __device__ __forceinline__ bool fast_use_f64(const FastArgs& F, const RowId& rid);
 __device__ __forceinline__ RowId fast_row(const FastArgs& F) {
     const int r = grid_row(F);
-    if (F.slab_rows == 0) return RowId{r, r % F.period};
+    if (F.slab_rows == 0) return RowId{r, (F.row0 + r) % F.period};
     const int g = r / F.slab_rows, m = r - g * F.slab_rows;
     return RowId{(long long)g * F.group_rows + F.slab_t0 + m, F.slab_t0 + m};
 }
@@ -503,7 +511,7 @@ __device__ __forceinline__ void fast_fwd_col_body(const FastArgs& F, int64_t* sm
     {
         const int r0 = tau >> 4, col = tau & 15;
 #pragma unroll
-        for (int k = 0; k < 16; ++k) e[k] = A::load(row0[((long long)(r0 + 16 * k) << b) + col]);
+        for (int k = 0; k < 16; ++k) e[k] = A::load_in(row0[((long long)(r0 + 16 * k) << b) + col], F.in_raw);
         if (F.scal) {
             const TW s = scalar_tw<A>(F, limb);
 #pragma unroll
@@ -544,7 +552,9 @@ __global__ void __launch_bounds__(NTT_THREADS, FAST_CTAS_PER_SM) fast_fwd_colpas
 // ---- ModUp basis extension for the fast path ---------------------------------------------------------------------
 // One thread owns two coefficients of ONE partition, loads its Garner digits s_0..s_{alpha-1} (exact integers,
 // engine.py:654-705) once, and then walks over ALL E target limbs: by Horner's rule in the target field
-//      X = s_0 + m_0 (s_1 + m_1 (s_2 + ...)),   ext = X * R   (== extend, engine.py:707-743, up to congruence)
+//      X = s_0 + m_0 (s_1 + m_1 (s_2 + ...)),   ext = X (scale-prime targets) or X * R (60-bit targets)
+//      (== extend, engine.py:707-743, up to congruence and, for the scale primes, up to the Montgomery factor that
+//      k_ksk_inner_fast no longer divides out)
 // in FP64 for scale-prime targets (digits of scale-prime partitions are < 2^44; the single 60-bit digit of the
 // base-prime partition is split into 31-bit halves), with the reference's Montgomery chain for 60-bit targets.
 // The digits are read once instead of once per target; stores are coalesced 16-byte writes per target row.
@@ -561,19 +571,27 @@ struct ExtArgs {
     const int64_t *q, *_2q, *ql, *qh, *kl, *kh;
     int64_t* out;                       // [P*E][N], row p*E + t
     int E, N;
+    int raw;                            // scale-prime targets are written as raw doubles (read back with in_raw)
+};
+
+// per-target constants of the extension staged once per CTA (q, 1/q, 2^31 mod q, the Horner multipliers): a thread
+// walks over all E targets, and recomputing 1/q (an FP64 division) per target cost as much as the Horner chain itself
+constexpr int EXT_MAX_E = 128;
+struct ExtShared {
+    double q[EXT_MAX_E], qinv[EXT_MAX_E], c31[EXT_MAX_E];
+    double hm[7][EXT_MAX_E];
 };
 
 template <int AMAX>
-__device__ __forceinline__ void ext_target(const ExtArgs& X, int p, int t, int alpha, bool wide, const longlong2 (&s)[AMAX],
-                                           const double (&dx)[AMAX], const double (&dy)[AMAX], const double* __restrict__ hm,
+__device__ __forceinline__ void ext_target(const ExtArgs& X, const ExtShared& S, int p, int t, int tl, int alpha, bool wide,
+                                           const longlong2 (&s)[AMAX], const double (&dx)[AMAX], const double (&dy)[AMAX],
                                            const int64_t* __restrict__ le, int64_t* __restrict__ out) {
-    const uint64_t q = (uint64_t)X.q[t];
     longlong2 r;
-    if (q < SMALL_PRIME_LIMIT) {
-        const F64C c{(double)q, 1.0 / (double)q};
+    if (S.q[tl] < (double)SMALL_PRIME_LIMIT) {
+        const F64C c{S.q[tl], S.qinv[tl]};
         double ax = 0.0, ay = 0.0;
         if (wide) {
-            const double c31 = X.C31[t];
+            const double c31 = S.c31[tl];
             ax = __dadd_rn(f64_mulmod(dx[0], c31, c), dx[1]);
             ay = __dadd_rn(f64_mulmod(dy[0], c31, c), dy[1]);
         } else {
@@ -583,15 +601,16 @@ __device__ __forceinline__ void ext_target(const ExtArgs& X, int p, int t, int a
                     ax = dx[i];
                     ay = dy[i];
                 } else if (i < alpha - 1) {
-                    const double m = hm[(long long)i * X.E + t];
+                    const double m = S.hm[i][tl];
                     ax = __dadd_rn(f64_mulmod(ax, m, c), dx[i]);
                     ay = __dadd_rn(f64_mulmod(ay, m, c), dy[i]);
                 }
             }
         }
-        const double Rd = X.Rd[t];
-        r.x = d2i(f64_mulmod(ax, Rd, c));
-        r.y = d2i(f64_mulmod(ay, Rd, c));
+        // scale-prime targets stay PLAIN (no Montgomery factor): the transform is linear and the FP64 inner product
+        // then needs no R^-1 either -- X * (K R) is already the Montgomery-form product.  |ax| < 2^43: no reduction.
+        r.x = X.raw ? (int64_t)__double_as_longlong(ax) : d2i(ax);
+        r.y = X.raw ? (int64_t)__double_as_longlong(ay) : d2i(ay);
     } else {
         const LimbConst k = load_limb_const(X._2q, X.ql, X.qh, X.kl, X.kh, t);
         const int64_t q2 = (int64_t)k.q2, rs = X.Rs[t];
@@ -614,10 +633,23 @@ __device__ __forceinline__ void ext_target(const ExtArgs& X, int p, int t, int a
 // AMAX = capacity of the per-thread digit arrays (>= alpha, and >= 2 for the 31-bit split of a wide digit)
 template <int AMAX>
 __global__ void __launch_bounds__(256) k_extend_fast(const ExtArgs X, int t0, int t1) {
+    __shared__ ExtShared S;
     const int p = blockIdx.y;
+    const int alpha = X.alphas[p];
+    {   // stage the constants of targets [t0, t1) (t1 - t0 <= EXT_MAX_E, checked by the launcher)
+        const double* __restrict__ hm = X.Hm[p];
+        for (int i = threadIdx.x; i < t1 - t0; i += blockDim.x) {
+            const double q = (double)(uint64_t)X.q[t0 + i];
+            S.q[i] = q;
+            S.qinv[i] = 1.0 / q;
+            S.c31[i] = X.C31[t0 + i];
+#pragma unroll
+            for (int k = 0; k < 7; ++k) S.hm[k][i] = (k < alpha - 1 && k < AMAX - 1) ? hm[(long long)k * X.E + t0 + i] : 0.0;
+        }
+    }
+    __syncthreads();
     const long long j = 2ll * (blockIdx.x * 256 + threadIdx.x);
     if (j >= X.N) return;
-    const int alpha = X.alphas[p];
     const bool wide = X.wide[p] != 0;
     const int64_t* __restrict__ st = X.digit_ptrs[p];
     longlong2 s[AMAX];
@@ -633,15 +665,16 @@ __global__ void __launch_bounds__(256) k_extend_fast(const ExtArgs X, int t0, in
         dx[0] = (double)(int)(s[0].x >> 31); dy[0] = (double)(int)(s[0].y >> 31);
         dx[1] = (double)(int)(s[0].x & 0x7FFFFFFF); dy[1] = (double)(int)(s[0].y & 0x7FFFFFFF);
     }
-    const double* __restrict__ hm = X.Hm[p];
     const int64_t* __restrict__ le = X.Lenter[p];
     int64_t* __restrict__ out = X.out + ((long long)p * X.E) * X.N + j;
     int t = t0;
-    for (; t + 1 < t1; t += 2) {   // two independent targets in flight per iteration
-        ext_target<AMAX>(X, p, t, alpha, wide, s, dx, dy, hm, le, out);
-        ext_target<AMAX>(X, p, t + 1, alpha, wide, s, dx, dy, hm, le, out);
+    for (; t + 3 < t1; t += 4) {   // four independent targets (8 Horner chains) in flight per iteration
+        ext_target<AMAX>(X, S, p, t, t - t0, alpha, wide, s, dx, dy, le, out);
+        ext_target<AMAX>(X, S, p, t + 1, t + 1 - t0, alpha, wide, s, dx, dy, le, out);
+        ext_target<AMAX>(X, S, p, t + 2, t + 2 - t0, alpha, wide, s, dx, dy, le, out);
+        ext_target<AMAX>(X, S, p, t + 3, t + 3 - t0, alpha, wide, s, dx, dy, le, out);
     }
-    if (t < t1) ext_target<AMAX>(X, p, t, alpha, wide, s, dx, dy, hm, le, out);
+    for (; t < t1; ++t) ext_target<AMAX>(X, S, p, t, t - t0, alpha, wide, s, dx, dy, le, out);
 }
 
 // ---- evaluation-key inner product for the fast path ------------------------------------------------------------
@@ -656,6 +689,7 @@ struct InnerArgs {
     const double* Rinv;                 // [E] R^-1 mod q_t
     const int64_t *q, *_2q, *ql, *qh, *kl, *kh;
     int P, E, N, t0;
+    int raw;                            // scale-prime rows: ext holds raw doubles and acc is written as raw doubles
 };
 
 __global__ void __launch_bounds__(256) k_ksk_inner_fast(const InnerArgs X) {
@@ -671,17 +705,21 @@ __global__ void __launch_bounds__(256) k_ksk_inner_fast(const InnerArgs X) {
             const longlong2 e = *reinterpret_cast<const longlong2*>(X.ext + ((long long)p * X.E + t) * X.N + j);
             const longlong2 u = *reinterpret_cast<const longlong2*>(X.k0[p] + (long long)t * X.k_stride + j);
             const longlong2 v = *reinterpret_cast<const longlong2*>(X.k1[p] + (long long)t * X.k_stride + j);
-            const double ex = i2d(e.x), ey = i2d(e.y);
+            const double ex = X.raw ? __longlong_as_double(e.x) : i2d(e.x), ey = X.raw ? __longlong_as_double(e.y) : i2d(e.y);
             a0x = __dadd_rn(a0x, f64_mulmod(ex, i2d(u.x), c));
             a0y = __dadd_rn(a0y, f64_mulmod(ey, i2d(u.y), c));
             a1x = __dadd_rn(a1x, f64_mulmod(ex, i2d(v.x), c));
             a1y = __dadd_rn(a1y, f64_mulmod(ey, i2d(v.y), c));
         }
-        const double ri = X.Rinv[t];
-        r0.x = d2i(f64_mulmod(a0x, ri, c));
-        r0.y = d2i(f64_mulmod(a0y, ri, c));
-        r1.x = d2i(f64_mulmod(a1x, ri, c));
-        r1.y = d2i(f64_mulmod(a1y, ri, c));
+        // ext is plain for these rows (k_extend_fast), the key is in Montgomery form: the sum already is the
+        // Montgomery-form product; at most 13 terms below 0.54 q each, |a| < 2^45, which the inverse transform accepts
+        if (X.raw) {
+            r0 = make_longlong2(__double_as_longlong(a0x), __double_as_longlong(a0y));
+            r1 = make_longlong2(__double_as_longlong(a1x), __double_as_longlong(a1y));
+        } else {
+            r0 = make_longlong2(d2i(a0x), d2i(a0y));
+            r1 = make_longlong2(d2i(a1x), d2i(a1y));
+        }
     } else {
         const LimbConst k = load_limb_const(X._2q, X.ql, X.qh, X.kl, X.kh, t);
         const int64_t q2 = (int64_t)k.q2;
@@ -812,7 +850,7 @@ __device__ __forceinline__ void fast_fwd_block_body(const FastArgs& F, int64_t* 
     {   // canonical values back through shared memory for coalesced 128-bit stores
         int64_t r[16];
 #pragma unroll
-        for (int k = 0; k < 16; ++k) r[k] = A::store_canon(e[k], c, false);
+        for (int k = 0; k < 16; ++k) r[k] = A::store_out(e[k], c, F.out_raw);
         sm_store_field(sm, r, tau, 0);
     }
     __syncthreads();
@@ -887,7 +925,7 @@ __device__ __forceinline__ void fast_fwd_block_body_w(const FastArgs& F, int64_t
     {   // the thread's 16 contiguous canonical coefficients: four full-sector 256-bit stores
         int64_t r[16];
 #pragma unroll
-        for (int k = 0; k < 16; ++k) r[k] = A::store_canon(e[k], c, false);
+        for (int k = 0; k < 16; ++k) r[k] = A::store_out(e[k], c, F.out_raw);
         int64_t* o = g + tau * 16;
 #pragma unroll
         for (int j = 0; j < 4; ++j) stg256(o, r, j);
@@ -1011,7 +1049,7 @@ __device__ __forceinline__ void persist_fwd_block_compute(const FastArgs& F, typ
     {
         int64_t r[16];
 #pragma unroll
-        for (int k = 0; k < 16; ++k) r[k] = A::store_canon(e[k], c, false);
+        for (int k = 0; k < 16; ++k) r[k] = A::store_out(e[k], c, F.out_raw);
         sm_store_field(xb, r, tau, 0);
     }
     __syncthreads();
@@ -1199,7 +1237,7 @@ __device__ __forceinline__ void pp_fwd_block_tile(const FastArgs& F, const int64
     }
     int64_t r[16];
 #pragma unroll
-    for (int k = 0; k < 16; ++k) r[k] = A::store_canon(e[k], c, false);
+    for (int k = 0; k < 16; ++k) r[k] = A::store_out(e[k], c, F.out_raw);
     int64_t* o = g + tau * 16;
 #pragma unroll
     for (int j = 0; j < 4; ++j) stg256(o, r, j);
@@ -1312,7 +1350,7 @@ __device__ __forceinline__ void fast_inv_block_body(const FastArgs& F, int64_t* 
         int64_t r[16];
         sm_load_field(sm, r, tau, 0);
 #pragma unroll
-        for (int k = 0; k < 16; ++k) e[k] = A::load(r[k]);
+        for (int k = 0; k < 16; ++k) e[k] = A::load_in(r[k], F.in_raw);
     }
     if constexpr (STAGED) {
         mbar_wait(bar, 0);
@@ -1386,7 +1424,7 @@ __device__ __forceinline__ void fast_inv_block_body_w(const FastArgs& F, int64_t
 #pragma unroll
         for (int j = 0; j < 4; ++j) ldg256(in, r, j);
 #pragma unroll
-        for (int k = 0; k < 16; ++k) e[k] = A::load(r[k]);
+        for (int k = 0; k < 16; ++k) e[k] = A::load_in(r[k], F.in_raw);
     }
     if constexpr (STAGED) {
         mbar_wait(bar, 0);
@@ -1472,7 +1510,7 @@ __device__ __forceinline__ void pp_inv_block_tile(const FastArgs& F, const int64
     const TW* __restrict__ W = tw_row<A>(F, tl.limb);
     T e[16];
 #pragma unroll
-    for (int k = 0; k < 16; ++k) e[k] = A::load(raw[k]);
+    for (int k = 0; k < 16; ++k) e[k] = A::load_in(raw[k], F.in_raw);
     if constexpr (STAGED)
         fast_inv_round<A, 4>(e, TwSharedBlock<TW>{tws, 12 - B, B - 4, (unsigned)tau}, c);
     else
@@ -1690,7 +1728,7 @@ __device__ __forceinline__ void pp_fwd_col_tile(const FastArgs& F, const int64_t
     const TW* __restrict__ W = tw_row<A>(F, tl.limb);
     T e[16];
 #pragma unroll
-    for (int k = 0; k < 16; ++k) e[k] = A::load(raw[k]);
+    for (int k = 0; k < 16; ++k) e[k] = A::load_in(raw[k], F.in_raw);
     if (F.scal) {
         const TW s = scalar_tw<A>(F, tl.limb);
 #pragma unroll

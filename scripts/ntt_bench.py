@@ -13,7 +13,7 @@ ROOT = Path(__file__).resolve().parents[1]
 sys.path.insert(0, str(ROOT / "liberate-fhe_b200"))
 sys.path.insert(0, str(ROOT))
 
-from liberate_b200._lib import lib, check  # noqa: E402
+from liberate_b200._lib import lib, check, option_defaults  # noqa: E402
 
 
 def primes(logN, L):
@@ -64,7 +64,7 @@ def run(logN, L, iters, pool_bytes=320 << 20):
     out = {}
     variants = [("fwd", fwd, None), ("inv_exit_reduce", inv, None), ("fast_fwd", ffwd, None), ("fast_inv", finv, None),
                 ("fast_fwd_int", lambda b: ffwd(b, 1), None), ("fast_inv_int", lambda b: finv(b, 1), None),
-                ("fast_fwd_nopf", ffwd, (2, 0)), ("fast_fwd_pf56", ffwd, (2, 56)), ("fast_fwd_persist", ffwd, (1, 1))]
+                ("fast_fwd_classic", ffwd, (3, 0)), ("fast_fwd_1stream", ffwd, (10, 1))]
     for name, fn, opt in variants:
         if opt:
             lib.ckks_set_option(*opt)
@@ -79,8 +79,8 @@ def run(logN, L, iters, pool_bytes=320 << 20):
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / iters
         out[name] = dict(ms=ms, gbps=16.0 * L * N / (ms * 1e-3) / 1e9, limb_ntt_us=ms * 1e3 / L)
-        lib.ckks_set_option(1, 0)
-        lib.ckks_set_option(2, 28)
+        for k, v in option_defaults().items():
+            lib.ckks_set_option(k, v)
     return out
 
 
@@ -88,7 +88,7 @@ if __name__ == "__main__":
     quick = "--quick" in sys.argv
     res = []
     for logN in ([16] if quick else [14, 15, 16, 17]):
-        for L in ([36] if quick else [4, 36, 60]):
+        for L in ([36] if quick else [1, 4, 16, 36, 60]):
             r = run(logN, L, iters=20 if quick else 50)
             res.append(dict(logN=logN, L=L, **r))
             print(logN, L, {k: (round(v["gbps"], 1), round(v["limb_ntt_us"], 3)) for k, v in r.items()}, flush=True)
