@@ -137,6 +137,14 @@ class ClockSampler:
                 "samples": len(sm), "source": "nvml" if self.nvml else "nvidia-smi"}
 
 
+def roofline_traffic():
+    """DRAM bytes per launch of the roofline kernel pair from the committed ncu capture (profiles/), or None"""
+    try:
+        return float(json.loads((ROOT / "profiles" / "r01_roofline_traffic.json").read_text())["per_launch_traffic_bytes"])
+    except Exception:
+        return None
+
+
 def gold_params():
     from liberate_b200.fhe.presets import params
     return {k: v for k, v in params[PRESET].items() if k != "devices"}
@@ -414,10 +422,13 @@ def run_ours(args):
                 "mode": "every step copies its operands H2D and its product D2H (pinned host memory) on copy streams, "
                         "2 steps in flight", "serial_value": 1e3 / ms_e2e_serial},
         "gpu_launches": launches,
-        "roofline": {"bound": "hbm", "kernel": "fast_fwd_colpass + fast_fwd_blockpass (the key switch's batched forward NTT)",
+        "roofline": {"bound": "hbm", "kernel": "fast_fwd_colpass + fast_fwd_blockpass_w (ckks_ntt_fast: the key switch's batched forward NTT, 380 limbs)",
                      "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "limbs_per_launch": rows, "ms_per_launch": ms_ntt,
-                     "note": "algorithmic bytes = 16 B per coefficient per transform (SURVEY 8d); instruction-issue bound, see DESIGN.md 6"},
+                     "traffic": roofline_traffic(), "algorithmic_bytes": 16.0 * rows * N,
+                     "limbs_per_launch": rows, "ms_per_launch": ms_ntt,
+                     "note": "algorithmic bytes = 16 B per coefficient per transform (SURVEY 8d); traffic = dram read+write "
+                             "per launch from profiles/r01_roofline_traffic.json (ncu, warm caches); FP64-pipe bound: the "
+                             "register-only butterfly ceiling is 56 % of the HBM roofline, see DESIGN.md 6"},
     }
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
