@@ -559,6 +559,7 @@ static int launch_fast_inv_block_any(const FastArgs& F, dim3 grid, cudaStream_t 
     }
     return CKKS_E_LOGN;
 }
+int g_fuse_rescale = 1;   // ckks_set_option(12, v): rescale fused into the tensor stage's column pass
 int g_ntt_slab_mb = 24;   // ckks_set_option(11, v): MB of rows per slab of a big batched transform
 
 // ---- side streams: independent slabs of one call run on up to MAX_PIPES internal streams so that the tail of one
@@ -667,6 +668,7 @@ int ckks_get_option(int key) {
     if (key == 9) return g_slab_mb;
     if (key == 10) return g_pipes;
     if (key == 11) return g_ntt_slab_mb;
+    if (key == 12) return g_fuse_rescale;
     return CKKS_E_BADARG;
 }
 
@@ -682,6 +684,7 @@ int ckks_set_option(int key, int value) {
     if (key == 9) { if (value < 1) return CKKS_E_BADARG; g_slab_mb = value; return 0; }
     if (key == 10) { if (value < 1 || value > MAX_PIPES) return CKKS_E_BADARG; g_pipes = value; return 0; }
     if (key == 11) { if (value < 1) return CKKS_E_BADARG; g_ntt_slab_mb = value; return 0; }
+    if (key == 12) { g_fuse_rescale = value; return 0; }
     return CKKS_E_BADARG;
 }
 
@@ -986,10 +989,30 @@ int ckks_exec_tensor_stage(const ckks_level_t* lv, const int64_t* a0, const int6
     const long long LN = (long long)L * N;
     const int64_t* in[4] = {a0, a1, b0, b1};
     const int64_t* r0[4] = {r0a0, r0a1, r0b0, r0b1};
-    for (int c = 0; c < 4; ++c)
-        RC(ckks_rescale(in[c], in_stride, r0[c], x + c * LN, N, L, N, lv->rescale_scale, lv->round_at, 1, lv->_2q, lv->ql,
-                        lv->qh, lv->kl, lv->kh, stream));
-    RC(ckks_ntt_fast(x, N, 4 * L, L, lv->logN, lv->twf_u64, lv->twf_f64, lv->q, lv->sR, (const uint64_t*)lv->sR_sh, 0, stream));
+    if (g_fuse_rescale && aligned16(in[0]) && aligned16(in[1]) && aligned16(in[2]) && aligned16(in[3])) {
+        // rescale fused into the load of the batched column pass (no rescaled polynomial is ever written to HBM)
+        RescaleIn R{};
+        for (int c = 0; c < 4; ++c) { R.in[c] = in[c]; R.r0[c] = r0[c]; }
+        R.in_stride = in_stride;
+        R.scale = lv->rescale_scale;
+        R.round_at = lv->round_at;
+        R._2q = lv->_2q; R.ql = lv->ql; R.qh = lv->qh; R.kl = lv->kl; R.kh = lv->kh;
+        R.L = L;
+        FastArgs F{x, N, reinterpret_cast<const ulonglong2*>(lv->twf_u64), lv->twf_f64, lv->q, lv->sR,
+                   (const uint64_t*)lv->sR_sh, L, lv->logN, 0, 0, 0, 0, 0, 0, g_swap, 0, 0, 0};
+        const dim3 grid(N / TILE, 4 * L);
+        cudaFuncSetAttribute(fast_fwd_colpass_rescale<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, FAST_SMEM_BYTES);
+        fast_fwd_colpass_rescale<0><<<tile_grid(grid), NTT_THREADS, FAST_SMEM_BYTES, S(stream)>>>(F, R);
+        RC(launch_status());
+        F.scal = nullptr;
+        F.prefetch = g_prefetch;
+        RC(launch_fast_fwd_block_any(F, grid, S(stream), lv->logN));
+    } else {
+        for (int c = 0; c < 4; ++c)
+            RC(ckks_rescale(in[c], in_stride, r0[c], x + c * LN, N, L, N, lv->rescale_scale, lv->round_at, 1, lv->_2q, lv->ql,
+                            lv->qh, lv->kl, lv->kh, stream));
+        RC(ckks_ntt_fast(x, N, 4 * L, L, lv->logN, lv->twf_u64, lv->twf_f64, lv->q, lv->sR, (const uint64_t*)lv->sR_sh, 0, stream));
+    }
     RC(ckks_tensor_product(x, x + LN, x + 2 * LN, x + 3 * LN, N, d, d + LN, d + 2 * LN, N, L, N, lv->_2q, lv->ql, lv->qh,
                            lv->kl, lv->kh, stream));
     RC(ckks_intt_fast(d, N, 3 * L, L, lv->logN, lv->twi_u64, lv->twi_f64, lv->q, lv->sExit, (const uint64_t*)lv->sExit_sh, 0, 0,

@@ -490,8 +490,67 @@ __device__ __forceinline__ void stage_col_twiddles(const double* __restrict__ W,
 }
 
 // ---- forward pass A (column pass, stages 0..7) -------------------------------------------------------------
-template <class A, bool STAGED>
-__device__ __forceinline__ void fast_fwd_col_body(const FastArgs& F, int64_t* sm, int limb, long long drow) {
+// RESC: the rescale of cc_mult (engine.py:1026-1038) fused into the load.  Row r of the batch is polynomial r / L,
+// limb r % L; its coefficients are read from the INPUT ciphertext rows (in[poly], the rows that survive) together with
+// the dropped limb r0[poly], and  x = ((in - r0) q0^-1 + [r0 > round_at]) R  goes straight into the first butterflies:
+// one exact FP64 product (scale = q0^-1 R mod q is the reference's own table) instead of a separate kernel that
+// writes the rescaled polynomial to HBM and reads it back.  60-bit rows evaluate the reference's integer formula.
+struct RescaleIn {
+    const int64_t* in[4];      // [L][N] rows of the four polynomials, in_stride apart
+    long long in_stride;
+    const int64_t* r0[4];      // [N] dropped limb of each polynomial
+    const int64_t* scale;      // [L] q0^-1 R mod q_t
+    long long round_at;
+    const int64_t *_2q, *ql, *qh, *kl, *kh;
+    int L;
+};
+
+template <class A>
+__device__ __forceinline__ void rescale_load(const FastArgs& F, const RescaleIn& R, typename A::T (&e)[16], int limb,
+                                             long long drow, const typename A::C& c);
+template <>
+__device__ __forceinline__ void rescale_load<ArithF64>(const FastArgs& F, const RescaleIn& R, double (&e)[16], int limb,
+                                                       long long drow, const F64C& c) {
+    const int tau = threadIdx.x, b = F.logN - 8;
+    const int g = (int)(drow / R.L);
+    const long long base = (long long)grid_chunk(F) * 16 + ((long long)(tau >> 4) << b) + (tau & 15);
+    const int64_t* __restrict__ src = R.in[g] + (long long)limb * R.in_stride + base;
+    const int64_t* __restrict__ z = R.r0[g] + base;
+    const double s1 = (double)R.scale[limb], rm = (double)F.scal[limb];
+    int64_t x[16], y[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        x[k] = src[(long long)(16 * k) << b];
+        y[k] = z[(long long)(16 * k) << b];
+    }
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        const double v = f64_mulmod(i2d(x[k] - y[k]), s1, c);
+        e[k] = (y[k] > R.round_at) ? __dadd_rn(v, rm) : v;
+    }
+}
+template <>
+__device__ __forceinline__ void rescale_load<ArithU64>(const FastArgs& F, const RescaleIn& R, uint64_t (&e)[16], int limb,
+                                                       long long drow, const U64C& c) {
+    const int tau = threadIdx.x, b = F.logN - 8;
+    const int g = (int)(drow / R.L);
+    const long long base = (long long)grid_chunk(F) * 16 + ((long long)(tau >> 4) << b) + (tau & 15);
+    const int64_t* __restrict__ src = R.in[g] + (long long)limb * R.in_stride + base;
+    const int64_t* __restrict__ z = R.r0[g] + base;
+    const LimbConst k = load_limb_const(R._2q, R.ql, R.qh, R.kl, R.kh, limb);
+    const int64_t sc = R.scale[limb], q = (int64_t)c.q;
+    const ulonglong2 s = scalar_tw<ArithU64>(F, limb);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const int64_t x = src[(long long)(16 * i) << b], y = z[(long long)(16 * i) << b];
+        int64_t o = reduce_q(mont_mul_ss(x - y, sc, k.q4, k.k) + (y > R.round_at ? 1 : 0), q);
+        o += (o < 0) ? q : 0;
+        e[i] = ArithU64::mul((uint64_t)o, s, c);
+    }
+}
+
+template <class A, bool STAGED, bool RESC>
+__device__ __forceinline__ void fast_fwd_col_body(const FastArgs& F, const RescaleIn& R, int64_t* sm, int limb, long long drow) {
     using T = typename A::T;
     using TW = typename A::TW;
     const int tau = threadIdx.x;
@@ -502,20 +561,24 @@ __device__ __forceinline__ void fast_fwd_col_body(const FastArgs& F, int64_t* sm
     TW* tws = reinterpret_cast<TW*>(sm + SMEM_SLOTS);
     uint64_t* bar = reinterpret_cast<uint64_t*>(sm + SMEM_SLOTS + FAST_TW_SLOTS);
     if constexpr (STAGED) stage_col_twiddles(reinterpret_cast<const double*>(W), reinterpret_cast<double*>(tws), bar);
-    {
+    if constexpr (!RESC) {
         unsigned ca = 0;
         const long long ra = F.prefetch ? fast_row_ahead(F, F.prefetch, ca) : -1;
         if (ra >= 0) l2_prefetch_line(F.a + ra * F.a_stride + (long long)ca * 16 + ((long long)tau << b));
     }
     T e[16];
     {
-        const int r0 = tau >> 4, col = tau & 15;
+        if constexpr (RESC) {
+            rescale_load<A>(F, R, e, limb, drow, c);
+        } else {
+            const int r0 = tau >> 4, col = tau & 15;
 #pragma unroll
-        for (int k = 0; k < 16; ++k) e[k] = A::load_in(row0[((long long)(r0 + 16 * k) << b) + col], F.in_raw);
-        if (F.scal) {
-            const TW s = scalar_tw<A>(F, limb);
+            for (int k = 0; k < 16; ++k) e[k] = A::load_in(row0[((long long)(r0 + 16 * k) << b) + col], F.in_raw);
+            if (F.scal) {
+                const TW s = scalar_tw<A>(F, limb);
 #pragma unroll
-            for (int k = 0; k < 16; ++k) e[k] = A::mul(e[k], s, c);
+                for (int k = 0; k < 16; ++k) e[k] = A::mul(e[k], s, c);
+            }
         }
         if constexpr (STAGED) {
             mbar_wait(bar, 0);
@@ -543,10 +606,23 @@ __global__ void __launch_bounds__(NTT_THREADS, FAST_CTAS_PER_SM) fast_fwd_colpas
     extern __shared__ __align__(16) int64_t sm[];
     const RowId rid = fast_row(F);
     const int limb = rid.limb;
+    const RescaleIn none{};
     if (fast_use_f64(F, rid))
-        fast_fwd_col_body<ArithF64, true>(F, sm, limb, rid.data_row);
+        fast_fwd_col_body<ArithF64, true, false>(F, none, sm, limb, rid.data_row);
     else
-        fast_fwd_col_body<ArithU64, false>(F, sm, limb, rid.data_row);
+        fast_fwd_col_body<ArithU64, false, false>(F, none, sm, limb, rid.data_row);
+}
+
+// the tensor stage's column pass: rescale fused into the load (rows = 4 polynomials x L limbs, period L, F.scal = R mod q)
+template <int DUMMY>
+__global__ void __launch_bounds__(NTT_THREADS, FAST_CTAS_PER_SM) fast_fwd_colpass_rescale(const FastArgs F, const RescaleIn R) {
+    extern __shared__ __align__(16) int64_t sm[];
+    const RowId rid = fast_row(F);
+    const int limb = rid.limb;
+    if (fast_use_f64(F, rid))
+        fast_fwd_col_body<ArithF64, true, true>(F, R, sm, limb, rid.data_row);
+    else
+        fast_fwd_col_body<ArithU64, false, true>(F, R, sm, limb, rid.data_row);
 }
 
 // ---- ModUp basis extension for the fast path ---------------------------------------------------------------------
