@@ -296,7 +296,30 @@ def run_ours(args):
     time.sleep(0.1)
     if args.profile_range:
         torch.cuda.profiler.start()
-    ms, launches, prod = timed(lambda: eng.mult(ct_a, ct_b, evk), args.steps, args.warmup)
+    use_graph = args.graph in ("on", "auto")
+    graphed = None
+    if use_graph:
+        try:
+            graphed = eng.capture(eng.mult, ct_a, ct_b, evk)
+        except Exception as e:      # capture is an optimisation: fall back to eager launches, and say so
+            if world > 1:
+                raise               # (ranks must agree on the collectives they issue: no per-rank fallback)
+            print(f"[bench] CUDA graph capture failed ({e!r}); running eagerly", file=sys.stderr)
+            use_graph = False
+    if graphed is not None:        # same kernels and collectives, replayed as ONE graph launch per step
+        n_kernels = lib.launches
+        eng.mult(ct_a, ct_b, evk)
+        n_kernels = lib.launches - n_kernels
+
+        def step():
+            graphed.replay()
+            return graphed.result
+    else:
+        def step():
+            return eng.mult(ct_a, ct_b, evk)
+    ms, launches, prod = timed(step, args.steps, args.warmup)
+    if graphed is not None:
+        launches = n_kernels        # kernels inside one replay (the library's counter only sees eager launches)
     if args.profile_range:
         torch.cuda.profiler.stop()
 
@@ -338,6 +361,8 @@ def run_ours(args):
                for h in (ha, hb)] for _ in range(DEPTH)]
     out_hosts = [out_host] + [[[torch.empty_like(t).pin_memory() if t is not None else None for t in poly]
                                for poly in out_host] for _ in range(DEPTH - 1)]
+    res_buf = [[[torch.empty_like(t) if t is not None else None for t in poly] for poly in prod.data]
+               for _ in range(DEPTH)] if graphed is not None else None
     ev_in = [torch.cuda.Event() for _ in range(DEPTH)]
     ev_used = [torch.cuda.Event() for _ in range(DEPTH)]
     ev_out = [torch.cuda.Event() for _ in range(DEPTH)]
@@ -355,7 +380,22 @@ def run_ours(args):
                             td.copy_(th, non_blocking=True)
             ev_in[k].record(s_in)
         main.wait_event(ev_in[k])
-        r = eng.mult(ct_a._replace(data=dev_in[k][0]), ct_b._replace(data=dev_in[k][1]), evk)
+        if graphed is not None:     # the graph reads the captured operand tensors: refresh them in place, then replay
+            for src, dst in ((dev_in[k][0], ct_a.data), (dev_in[k][1], ct_b.data)):
+                for sp, dp in zip(src, dst):
+                    for ts, td in zip(sp, dp):
+                        if ts is not None:
+                            td.copy_(ts, non_blocking=True)
+            graphed.replay()
+            # the graph rewrites its result tensors on every replay: hand a per-slot copy to the D2H stream
+            main.wait_event(ev_out[k])
+            for poly, bp in zip(graphed.result.data, res_buf[k]):
+                for t, bt in zip(poly, bp):
+                    if t is not None:
+                        bt.copy_(t, non_blocking=True)
+            r = graphed.result._replace(data=res_buf[k])
+        else:
+            r = eng.mult(ct_a._replace(data=dev_in[k][0]), ct_b._replace(data=dev_in[k][1]), evk)
         ev_used[k].record(main)
         with torch.cuda.stream(s_out):
             s_out.wait_event(ev_used[k])
@@ -415,7 +455,7 @@ def run_ours(args):
         "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int64",
         "data": "synthetic",
         "config": {"workload": "gold preset (logN=16, 35 ordinary + 4 special limbs) ct*ct mult + relinearize, level-0 inputs",
-                   "parallelism": f"rns-limb-shard{world}", "l2": "working set 507 MB > 126 MB L2, no flush needed",
+                   "parallelism": f"rns-limb-shard{world}", "cuda_graph": bool(use_graph), "l2": "working set 507 MB > 126 MB L2, no flush needed",
                    "arithmetic": "results bit-identical to the reference; FP64 error-free + Shoup butterflies inside the fused path"},
         "clocks": clocks,
         "e2e": {"value": 1e3 / ms_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -434,9 +474,16 @@ def run_ours(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(eng, ct_a, ct_b, evk, prod)
     if rank == 0:
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if dist is not None:
+        torch.cuda.synchronize()
         dist.barrier()
+        if graphed is not None:
+            # a captured graph keeps NCCL work alive; tearing the process group down under it can block for minutes.
+            # Every rank has printed / synchronised: leave without the NCCL teardown.
+            sys.stdout.flush()
+            sys.stderr.flush()
+            os._exit(0)
         dist.destroy_process_group()
 
 
@@ -467,6 +514,8 @@ if __name__ == "__main__":
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference_gpu"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
+                    help="replay the step (engine.capture) as a CUDA graph; auto = on")
     ap.add_argument("--profile-roofline", action="store_true", help="cudaProfilerStart/Stop around two launches of the roofline kernel pair")
     ap.add_argument("--profile-range", action="store_true", help="cudaProfilerStart/Stop around the timed steps (ncu --profile-from-start off)")
     args = ap.parse_args()

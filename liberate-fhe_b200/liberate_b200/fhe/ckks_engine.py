@@ -1073,6 +1073,31 @@ class ckks_engine:
     def mult(self, a, b, evk=None, relin=True):
         return self._dispatch(self.mult_dispatch_dict, a, b, evk, relin)
 
+    def capture(self, fn, *args, warmup=3):
+        """CUDA-graph capture of one engine call on FIXED operand tensors (B200 addition, no reference counterpart):
+
+            g = engine.capture(engine.mult, ct_a, ct_b, evk)     # also rotate_single, add, ...
+            g.replay(); out = g.result                           # re-reads ct_a / ct_b in place, rewrites `out`
+
+        A captured mult is one graph launch instead of ~25 kernel launches, a handful of torch ops and (one process
+        per GPU) two NCCL collectives issued from Python: with the limbs sharded over 8 GPUs the step is launch-bound
+        otherwise.  Every rank must capture and replay the same calls in the same order.  Refresh the operands by
+        copying new data INTO the captured tensors (`t.copy_(new)`) before `replay()`."""
+        dev = torch.device(self.ntt.devices[self.local_ids[0]])
+        with torch.cuda.device(dev):
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(max(1, warmup)):       # first calls build plans, workspaces, pointer tables, NCCL channels
+                    fn(*args)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                result = fn(*args)
+        graph.result = result
+        return graph
+
     def add(self, a, b):
         return self._dispatch(self.add_dispatch_dict, a, b)
 
