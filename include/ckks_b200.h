@@ -34,7 +34,9 @@ int ckks_abi_version(void);
 int ckks_set_option(int key, int value);   /* key 2 = L2 prefetch distance in rows (default 28, 0 = off) */
 /* key 3 = block passes: 0 one tile per CTA, 1 warp-independent + 256-bit accesses, 2 persistent software-pipelined;
  * key 4 = 1: persistent software-pipelined column passes; key 5 = measurement only, skip column (1) / block (2) pass;
- * key 6 = persistent CTAs per SM (1..4); key 7 = cap on the persistent grid (0 = none)  -- keys 3/4 need 32-byte aligned rows */
+ * key 6 = persistent CTAs per SM (1..4); key 7 = cap on the persistent grid (0 = none)  -- keys 3/4 need 32-byte aligned rows;
+ * key 8 = (row, chunk) grid order; key 9 = MB of extended rows per key-switch slab; key 10 = internal side streams (1..4);
+ * key 11 = MB per row slab of a big batched transform; key 12 / 13 = rescale / tensor product fused into the tensor stage */
 int ckks_get_option(int key);               /* current value of a knob (negative: unknown key) */
 int64_t ckks_launch_count(void);            /* kernels launched by the library since it was loaded */
 
@@ -181,27 +183,36 @@ typedef struct {
     const double* Rinv;                                       /* [E] R^-1 mod q_t (FP64 inner product), or NULL  */
     const double* Pinv;                                       /* [K][E] P_i^-1 mod q_t (FP64 ModDown), or NULL   */
     int32_t L_small, amax;                                    /* leading ordinary rows with q < 2^42; max alpha  */
+    /* optional (NULL = separate tensor-product kernel): exit scalars of the inverse transform that has the tensor
+     * product fused into its load: N^-1 R^-2 for rows with q < 2^42 (FP64 product), N^-1 R^-1 for the others */
+    const int64_t *sExitT, *sExitT_sh;
+    /* optional (NULL = transform every row): [nparts] first row, among this device's live rows, of the limbs each
+     * partition is made of, or -1 when the partition lives on another device.  With d2hat (below) the key switch does
+     * not extend / transform those rows: NTT(extension of a partition to its own limbs) is the tensor product's d2. */
+    const int32_t* part_row0;
 } ckks_level_t;
 
 /* rescale x4 -> batched enter+NTT -> tensor product -> batched iNTT+exit -> Garner digits of d2
  * (cc_mult + the first half of relinearize, engine.py:1072-1129, 654-705).  a0..b1: the rows that survive the rescale
  * ([L][N], in_stride); r0*: the dropped limb of each polynomial ([N], on this device).  x: workspace [4][L][N];
- * d: out [3][L][N] plain canonical d0,d1,d2; digits: out [L][N] (rows of the local partitions). */
+ * d: out [3][L][N] plain canonical d0,d1,d2; digits: out [L][N] (rows of the local partitions);
+ * d2hat: optional out [L][N], the NTT-domain d2 (lazy Montgomery form) for ckks_exec_keyswitch_stage. */
 int ckks_exec_tensor_stage(const ckks_level_t* lv, const int64_t* a0, const int64_t* a1, const int64_t* b0,
                            const int64_t* b1, int64_t in_stride, const int64_t* r0a0, const int64_t* r0a1,
                            const int64_t* r0b0, const int64_t* r0b1, int64_t* x, int64_t* d, int64_t* digits,
-                           void* stream);
+                           int64_t* d2hat, void* stream);
 /* Garner digits of the local partitions of a [L][N] polynomial (pre_extend for every partition, one launch) */
 int ckks_exec_digits(const ckks_level_t* lv, const int64_t* a, int64_t a_stride, int64_t* digits, int64_t d_stride,
                      void* stream);
 /* extend (all partitions) -> batched NTT -> evk inner product -> batched iNTT+exit -> ModDown (+add, reduce)
  * (create_switcher engine.py:812-904 + the relinearize / switch_key tails).  digit_ptrs: device [nparts] pointers to
  * each partition's [alpha][N] digit block (rows digit_stride apart) -- local or received from a peer;
- * ws: ckks_exec_keyswitch_ws_elems(...) int64 elements. */
+ * ws: ckks_exec_keyswitch_ws_elems(...) int64 elements.  d2hat: NULL, or the tensor stage's NTT-domain polynomial whose
+ * digits these are (relinearize only): rows a partition owns are then taken from it instead of being re-transformed. */
 int ckks_exec_keyswitch_stage(const ckks_level_t* lv, const int64_t* const* digit_ptrs, int64_t digit_stride,
                               const int64_t* const* k0_ptrs, const int64_t* const* k1_ptrs, int64_t ksk_stride,
                               const int64_t* add0, const int64_t* add1, int64_t add_stride, int64_t* out0,
-                              int64_t* out1, int64_t out_stride, int64_t* ws, void* stream);
+                              int64_t* out1, int64_t out_stride, int64_t* ws, const int64_t* d2hat, void* stream);
 int64_t ckks_exec_keyswitch_ws_elems(int L, int K, int nparts, int N);
 
 #ifdef __cplusplus

@@ -10,7 +10,7 @@
 
 using namespace ckks;
 
-#define CKKS_ABI_VERSION 1
+#define CKKS_ABI_VERSION 2
 
 namespace {
 
@@ -153,7 +153,8 @@ __global__ void k_rescale(const int64_t* __restrict__ in, long long is, const in
 
 __global__ void k_tensor(const int64_t* __restrict__ x0, const int64_t* __restrict__ x1, const int64_t* __restrict__ y0,
                          const int64_t* __restrict__ y1, long long is, int64_t* __restrict__ d0,
-                         int64_t* __restrict__ d1, int64_t* __restrict__ d2, long long os, int N, MontPack m) {
+                         int64_t* __restrict__ d1, int64_t* __restrict__ d2, long long os, int N, MontPack m,
+                         int64_t* __restrict__ d2hat) {
     const int i = blockIdx.y;
     const int j = 2 * (blockIdx.x * EW_THREADS + threadIdx.x);
     if (j >= N) return;
@@ -171,6 +172,7 @@ __global__ void k_tensor(const int64_t* __restrict__ x0, const int64_t* __restri
     st2(d0 + oo, r0);
     st2(d1 + oo, r1);
     st2(d2 + oo, r2);
+    if (d2hat) st2(d2hat + (long long)i * N + j, r2);   // NTT-domain d2 kept for the key switch (own-partition rows)
 }
 
 constexpr int MAX_ALPHA = 8;
@@ -559,6 +561,26 @@ static int launch_fast_inv_block_any(const FastArgs& F, dim3 grid, cudaStream_t 
     }
     return CKKS_E_LOGN;
 }
+template <int B>
+static int launch_inv_block_tensor_b(const FastArgs& F, const TensorIn& Tn, dim3 grid, cudaStream_t st) {
+    cudaFuncSetAttribute(fast_inv_blockpass_tensor<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, FAST_SMEM_BYTES);
+    fast_inv_blockpass_tensor<B><<<tile_grid(grid), NTT_THREADS, FAST_SMEM_BYTES, st>>>(F, Tn);
+    return launch_status();
+}
+static int launch_inv_block_tensor(const FastArgs& F, const TensorIn& Tn, dim3 grid, cudaStream_t st, int logN) {
+    switch (logN - 8) {
+        case 4: return launch_inv_block_tensor_b<4>(F, Tn, grid, st);
+        case 5: return launch_inv_block_tensor_b<5>(F, Tn, grid, st);
+        case 6: return launch_inv_block_tensor_b<6>(F, Tn, grid, st);
+        case 7: return launch_inv_block_tensor_b<7>(F, Tn, grid, st);
+        case 8: return launch_inv_block_tensor_b<8>(F, Tn, grid, st);
+        case 9: return launch_inv_block_tensor_b<9>(F, Tn, grid, st);
+    }
+    return CKKS_E_LOGN;
+}
+int g_own_skip = 0;       // ckks_set_option(14, v): key switch takes every partition's own limbs from the tensor product's NTT-domain d2
+                          // (9 % fewer rows to extend / transform, but measured 732 vs 726 us per gold mult: off)
+int g_fuse_tensor = 0;    // ckks_set_option(13, v): tensor product fused into the tensor stage's inverse block pass (measured: 10 us SLOWER)
 int g_fuse_rescale = 1;   // ckks_set_option(12, v): rescale fused into the tensor stage's column pass
 int g_ntt_slab_mb = 24;   // ckks_set_option(11, v): MB of rows per slab of a big batched transform
 
@@ -669,6 +691,8 @@ int ckks_get_option(int key) {
     if (key == 10) return g_pipes;
     if (key == 11) return g_ntt_slab_mb;
     if (key == 12) return g_fuse_rescale;
+    if (key == 13) return g_fuse_tensor;
+    if (key == 14) return g_own_skip;
     return CKKS_E_BADARG;
 }
 
@@ -685,6 +709,8 @@ int ckks_set_option(int key, int value) {
     if (key == 10) { if (value < 1 || value > MAX_PIPES) return CKKS_E_BADARG; g_pipes = value; return 0; }
     if (key == 11) { if (value < 1) return CKKS_E_BADARG; g_ntt_slab_mb = value; return 0; }
     if (key == 12) { g_fuse_rescale = value; return 0; }
+    if (key == 13) { g_fuse_tensor = value; return 0; }
+    if (key == 14) { g_own_skip = value; return 0; }
     return CKKS_E_BADARG;
 }
 
@@ -896,7 +922,7 @@ int ckks_tensor_product(const int64_t* x0, const int64_t* x1, const int64_t* y0,
         !row_ok(d1, os) || !row_ok(d2, os))
         return CKKS_E_ALIGN;
     k_tensor<<<ew_grid(N, C), EW_THREADS, 0, S(stream)>>>(x0, x1, y0, y1, is, d0, d1, d2, os, N,
-                                                          MontPack{_2q, ql, qh, kl, kh});
+                                                          MontPack{_2q, ql, qh, kl, kh}, nullptr);
     return launch_status();
 }
 
@@ -983,12 +1009,14 @@ int ckks_exec_digits(const ckks_level_t* lv, const int64_t* a, int64_t as, int64
 int ckks_exec_tensor_stage(const ckks_level_t* lv, const int64_t* a0, const int64_t* a1, const int64_t* b0,
                            const int64_t* b1, int64_t in_stride, const int64_t* r0a0, const int64_t* r0a1,
                            const int64_t* r0b0, const int64_t* r0b1, int64_t* x, int64_t* d, int64_t* digits,
-                           void* stream) {
+                           int64_t* d2hat, void* stream) {
     CHECK_PTRS(lv, a0, a1, b0, b1, r0a0, r0a1, r0b0, r0b1, x, d, digits);
+    if (!g_own_skip) d2hat = nullptr;
     const int L = lv->L, N = 1 << lv->logN;
     const long long LN = (long long)L * N;
     const int64_t* in[4] = {a0, a1, b0, b1};
     const int64_t* r0[4] = {r0a0, r0a1, r0b0, r0b1};
+    bool fused_tensor = false;
     if (g_fuse_rescale && aligned16(in[0]) && aligned16(in[1]) && aligned16(in[2]) && aligned16(in[3])) {
         // rescale fused into the load of the batched column pass (no rescaled polynomial is ever written to HBM)
         RescaleIn R{};
@@ -1006,6 +1034,8 @@ int ckks_exec_tensor_stage(const ckks_level_t* lv, const int64_t* a0, const int6
         RC(launch_status());
         F.scal = nullptr;
         F.prefetch = g_prefetch;
+        fused_tensor = g_fuse_tensor && lv->sExitT && lv->sExitT_sh && g_warp == 1;
+        F.out_raw = fused_tensor ? 1 : 0;   // scale-prime rows stay raw doubles for the fused tensor product
         RC(launch_fast_fwd_block_any(F, grid, S(stream), lv->logN));
     } else {
         for (int c = 0; c < 4; ++c)
@@ -1013,18 +1043,33 @@ int ckks_exec_tensor_stage(const ckks_level_t* lv, const int64_t* a0, const int6
                             lv->qh, lv->kl, lv->kh, stream));
         RC(ckks_ntt_fast(x, N, 4 * L, L, lv->logN, lv->twf_u64, lv->twf_f64, lv->q, lv->sR, (const uint64_t*)lv->sR_sh, 0, stream));
     }
-    RC(ckks_tensor_product(x, x + LN, x + 2 * LN, x + 3 * LN, N, d, d + LN, d + 2 * LN, N, L, N, lv->_2q, lv->ql, lv->qh,
-                           lv->kl, lv->kh, stream));
-    RC(ckks_intt_fast(d, N, 3 * L, L, lv->logN, lv->twi_u64, lv->twi_f64, lv->q, lv->sExit, (const uint64_t*)lv->sExit_sh, 0, 0,
-                      stream));
+    if (fused_tensor) {
+        // tensor product fused into the load of the batched inverse block pass (d0, d1, d2 never exist in the NTT domain in HBM)
+        TensorIn Tn{x, LN, lv->_2q, lv->ql, lv->qh, lv->kl, lv->kh, nullptr, L};   // (its d2hat form differs: not used for the own-row skip)
+        d2hat = nullptr;
+        FastArgs Fi{d, N, reinterpret_cast<const ulonglong2*>(lv->twi_u64), lv->twi_f64, lv->q, lv->sExitT,
+                    (const uint64_t*)lv->sExitT_sh, L, lv->logN, 0, 0, 0, 0, 0, 0, g_swap, 0, 0, 0};
+        const dim3 grid(N / TILE, 3 * L);
+        RC(launch_inv_block_tensor(Fi, Tn, grid, S(stream), lv->logN));
+        Fi.prefetch = g_prefetch;
+        RC(launch_fast_col(false, Fi, grid, S(stream)));
+    } else {
+        k_tensor<<<ew_grid(N, L), EW_THREADS, 0, S(stream)>>>(x, x + LN, x + 2 * LN, x + 3 * LN, N, d, d + LN, d + 2 * LN, N, N,
+                                                              MontPack{lv->_2q, lv->ql, lv->qh, lv->kl, lv->kh}, d2hat);
+        RC(launch_status());
+        RC(ckks_intt_fast(d, N, 3 * L, L, lv->logN, lv->twi_u64, lv->twi_f64, lv->q, lv->sExit, (const uint64_t*)lv->sExit_sh, 0, 0,
+                          stream));
+    }
     return ckks_exec_digits(lv, d + 2 * LN, N, digits, N, stream);
 }
 
 int ckks_exec_keyswitch_stage(const ckks_level_t* lv, const int64_t* const* digit_ptrs, int64_t digit_stride,
                               const int64_t* const* k0_ptrs, const int64_t* const* k1_ptrs, int64_t ksk_stride,
                               const int64_t* add0, const int64_t* add1, int64_t add_stride, int64_t* out0,
-                              int64_t* out1, int64_t out_stride, int64_t* ws, void* stream) {
+                              int64_t* out1, int64_t out_stride, int64_t* ws, const int64_t* d2hat, void* stream) {
     CHECK_PTRS(lv, digit_ptrs, k0_ptrs, k1_ptrs, out0, out1, ws);
+    // own-partition skip: only with the default one-tile-per-CTA kernels, the partition table and d2hat from the tensor stage
+    const int32_t* own_row0 = (g_own_skip && d2hat && lv->part_row0 && !g_persist && g_warp != 2 && !g_colpp) ? lv->part_row0 : nullptr;
     const int L = lv->L, K = lv->K, E = L + K, P = lv->nparts, N = 1 << lv->logN;
     int64_t* ext = ws;                                  // [P*E][N]
     int64_t* acc = ext + (long long)P * E * N;          // [2E][N]
@@ -1048,6 +1093,7 @@ int ckks_exec_keyswitch_stage(const ckks_level_t* lv, const int64_t* const* digi
         X.E = E;
         X.N = N;
         X.raw = 1;   // scale-prime rows travel as raw doubles from the extension to the inverse transform
+        X.own_row0 = own_row0;
         const long long slab_budget = (long long)g_slab_mb << 20;   // bytes of extended rows per slab
         const long long all_bytes = (long long)P * E * N * 8;
         const int nslabs = (int)((all_bytes + slab_budget - 1) / slab_budget);
@@ -1067,12 +1113,12 @@ int ckks_exec_keyswitch_stage(const ckks_level_t* lv, const int64_t* const* digi
             else k_extend_fast<8><<<eg, 256, 0, st>>>(X, t0, t1);
             RC(launch_status());
             FastArgs F{ext, N, reinterpret_cast<const ulonglong2*>(lv->twf_u64), lv->twf_f64, lv->q, nullptr, nullptr, E,
-                       lv->logN, 0, 0, t1 - t0, E, t0, g_prefetch, g_swap, 0, 1, 1};
+                       lv->logN, 0, 0, t1 - t0, E, t0, g_prefetch, g_swap, 0, 1, 1, own_row0, lv->part_alpha};
             const dim3 grid(N / TILE, P * (t1 - t0));
             RC(launch_fast_col(true, F, grid, st));
             RC(launch_fast_fwd_block_any(F, grid, st, lv->logN));
             InnerArgs I{ext, k0_ptrs, k1_ptrs, ksk_stride, acc, acc + (long long)E * N, lv->Rinv, lv->q, lv->_2q, lv->ql, lv->qh,
-                        lv->kl, lv->kh, P, E, N, t0, 1};
+                        lv->kl, lv->kh, P, E, N, t0, 1, own_row0, lv->part_alpha, d2hat};
             k_ksk_inner_fast<<<dim3((N / 2 + 255) / 256, t1 - t0), 256, 0, st>>>(I);
             RC(launch_status());
         }

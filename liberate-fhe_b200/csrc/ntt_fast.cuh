@@ -359,6 +359,10 @@ struct FastArgs {
     int swap_grid;              // one-tile-per-CTA kernels: blockIdx.x = row, blockIdx.y = chunk
     int row0;                   // plain rows: limb of grid row r is (row0 + r) % period (row slabs of one batch)
     int in_raw, out_raw;        // FP64 rows: the input / the forward output are raw doubles (fused key switch), not int64
+    // slab views of a key switch: partition g owns target limbs [own_row0[g], own_row0[g] + own_alpha[g]) (own_row0 < 0:
+    // none on this device).  Those rows are NOT transformed: their NTT is the tensor product's d2 itself.
+    const int32_t* own_row0;
+    const int32_t* own_alpha;
 };
 
 // grid mapping of the one-tile-per-CTA kernels: (chunk, row) by default; swapped (row, chunk) when F.swap_grid is
@@ -372,6 +376,16 @@ struct RowId {
     long long data_row;
     int limb;
 };
+__device__ __forceinline__ bool own_target(const int32_t* row0, const int32_t* alpha, int part, int t) {
+    if (!row0) return false;
+    const int r0 = row0[part];
+    return r0 >= 0 && t >= r0 && t < r0 + alpha[part];
+}
+__device__ __forceinline__ bool fast_skip_own(const FastArgs& F) {   // CTA-uniform
+    if (!F.own_row0 || F.slab_rows == 0) return false;
+    const int r = grid_row(F), g = r / F.slab_rows;
+    return own_target(F.own_row0, F.own_alpha, g, F.slab_t0 + (r - g * F.slab_rows));
+}
 // the tile that a CTA dispatched about `ahead` rows x (chunks per row) tiles later will load: data row (or -1) and chunk
 __device__ __forceinline__ long long fast_row_ahead(const FastArgs& F, int ahead, unsigned& chunk) {
     int r;
@@ -604,6 +618,7 @@ __device__ __forceinline__ void fast_fwd_col_body(const FastArgs& F, const Resca
 template <int DUMMY>
 __global__ void __launch_bounds__(NTT_THREADS, FAST_CTAS_PER_SM) fast_fwd_colpass(const FastArgs F) {
     extern __shared__ __align__(16) int64_t sm[];
+    if (fast_skip_own(F)) return;
     const RowId rid = fast_row(F);
     const int limb = rid.limb;
     const RescaleIn none{};
@@ -648,6 +663,7 @@ struct ExtArgs {
     int64_t* out;                       // [P*E][N], row p*E + t
     int E, N;
     int raw;                            // scale-prime targets are written as raw doubles (read back with in_raw)
+    const int32_t* own_row0;            // [P] or nullptr: first own target limb of each partition (skipped), < 0 = none
 };
 
 // per-target constants of the extension staged once per CTA (q, 1/q, 2^31 mod q, the Horner multipliers): a thread
@@ -662,6 +678,7 @@ template <int AMAX>
 __device__ __forceinline__ void ext_target(const ExtArgs& X, const ExtShared& S, int p, int t, int tl, int alpha, bool wide,
                                            const longlong2 (&s)[AMAX], const double (&dx)[AMAX], const double (&dy)[AMAX],
                                            const int64_t* __restrict__ le, int64_t* __restrict__ out) {
+    if (own_target(X.own_row0, X.alphas, p, t)) return;   // the key switch takes this row from the tensor product
     longlong2 r;
     if (S.q[tl] < (double)SMALL_PRIME_LIMIT) {
         const F64C c{S.q[tl], S.qinv[tl]};
@@ -766,6 +783,8 @@ struct InnerArgs {
     const int64_t *q, *_2q, *ql, *qh, *kl, *kh;
     int P, E, N, t0;
     int raw;                            // scale-prime rows: ext holds raw doubles and acc is written as raw doubles
+    const int32_t *own_row0, *alphas;   // [P] own target rows of each partition (see FastArgs), or nullptr
+    const int64_t* d2hat;               // [L][N] NTT-domain d2 = NTT(X) R (lazy integers) used for the own rows
 };
 
 __global__ void __launch_bounds__(256) k_ksk_inner_fast(const InnerArgs X) {
@@ -778,10 +797,19 @@ __global__ void __launch_bounds__(256) k_ksk_inner_fast(const InnerArgs X) {
         const F64C c{(double)q, 1.0 / (double)q};
         double a0x = 0.0, a0y = 0.0, a1x = 0.0, a1y = 0.0;
         for (int p = 0; p < X.P; ++p) {
-            const longlong2 e = *reinterpret_cast<const longlong2*>(X.ext + ((long long)p * X.E + t) * X.N + j);
+            const bool own = own_target(X.own_row0, X.alphas, p, t);
+            const longlong2 e = own ? *reinterpret_cast<const longlong2*>(X.d2hat + (long long)t * X.N + j)
+                                    : *reinterpret_cast<const longlong2*>(X.ext + ((long long)p * X.E + t) * X.N + j);
             const longlong2 u = *reinterpret_cast<const longlong2*>(X.k0[p] + (long long)t * X.k_stride + j);
             const longlong2 v = *reinterpret_cast<const longlong2*>(X.k1[p] + (long long)t * X.k_stride + j);
-            const double ex = X.raw ? __longlong_as_double(e.x) : i2d(e.x), ey = X.raw ? __longlong_as_double(e.y) : i2d(e.y);
+            double ex, ey;
+            if (own) {   // d2hat carries the Montgomery factor; the extended rows of this kernel are plain
+                ex = f64_mulmod(i2d(e.x), X.Rinv[t], c);
+                ey = f64_mulmod(i2d(e.y), X.Rinv[t], c);
+            } else {
+                ex = X.raw ? __longlong_as_double(e.x) : i2d(e.x);
+                ey = X.raw ? __longlong_as_double(e.y) : i2d(e.y);
+            }
             a0x = __dadd_rn(a0x, f64_mulmod(ex, i2d(u.x), c));
             a0y = __dadd_rn(a0y, f64_mulmod(ey, i2d(u.y), c));
             a1x = __dadd_rn(a1x, f64_mulmod(ex, i2d(v.x), c));
@@ -802,7 +830,9 @@ __global__ void __launch_bounds__(256) k_ksk_inner_fast(const InnerArgs X) {
         r0 = make_longlong2(0, 0);
         r1 = make_longlong2(0, 0);
         for (int p = 0; p < X.P; ++p) {
-            const longlong2 e = *reinterpret_cast<const longlong2*>(X.ext + ((long long)p * X.E + t) * X.N + j);
+            const bool own = own_target(X.own_row0, X.alphas, p, t);
+            const longlong2 e = own ? *reinterpret_cast<const longlong2*>(X.d2hat + (long long)t * X.N + j)
+                                    : *reinterpret_cast<const longlong2*>(X.ext + ((long long)p * X.E + t) * X.N + j);
             const longlong2 u = *reinterpret_cast<const longlong2*>(X.k0[p] + (long long)t * X.k_stride + j);
             const longlong2 v = *reinterpret_cast<const longlong2*>(X.k1[p] + (long long)t * X.k_stride + j);
             r0.x = lazy_add(r0.x, mont_mul_ss(e.x, u.x, k.q4, k.k), q2);
@@ -1011,6 +1041,7 @@ __device__ __forceinline__ void fast_fwd_block_body_w(const FastArgs& F, int64_t
 template <int B>
 __global__ void __launch_bounds__(NTT_THREADS, FAST_CTAS_PER_SM) fast_fwd_blockpass_w(const FastArgs F) {
     extern __shared__ __align__(16) int64_t sm[];
+    if (fast_skip_own(F)) return;
     const RowId rid = fast_row(F);
     const int limb = rid.limb;
     if (fast_use_f64(F, rid))
@@ -1022,6 +1053,7 @@ __global__ void __launch_bounds__(NTT_THREADS, FAST_CTAS_PER_SM) fast_fwd_blockp
 template <int B>
 __global__ void __launch_bounds__(NTT_THREADS, FAST_CTAS_PER_SM) fast_fwd_blockpass(const FastArgs F) {
     extern __shared__ __align__(16) int64_t sm[];
+    if (fast_skip_own(F)) return;
     const RowId rid = fast_row(F);
     const int limb = rid.limb;
     if (fast_use_f64(F, rid))
@@ -1472,11 +1504,114 @@ __device__ __forceinline__ void fast_inv_block_body(const FastArgs& F, int64_t* 
     }
 }
 
+// ---- tensor product of cc_mult (engine.py:1095-1101) fused into the load of the inverse block pass ---------------------
+// Row r of the [3L] batch is d_(r / L), limb r % L:  d0 = x0 y0,  d1 = x0 y1 + x1 y0,  d2 = x1 y1, where x[4][L][N] holds
+// the NTT-domain polynomials x0, x1, y0, y1 (Montgomery form: transforms of x R).  Scale-prime rows multiply in FP64
+// (x holds raw doubles there; the product carries R^2, removed by the exit scalar N^-1 R^-2), 60-bit rows use the
+// reference's Montgomery product (exit scalar N^-1 R^-1).  If d2hat != nullptr the NTT-domain d2 is also kept
+// (row-major [L][N]) for the key switch, which then skips the transform of every partition's own limbs.
+struct TensorIn {
+    const int64_t* x;          // [4][L][N]
+    long long poly_stride;     // L * N
+    const int64_t *_2q, *ql, *qh, *kl, *kh;
+    int64_t* d2hat;            // optional [L][N]
+    int L;
+};
+__device__ __forceinline__ void ldg256v(const int64_t* p, int64_t (&r)[4]) {
+    asm volatile("ld.global.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(r[0]), "=l"(r[1]), "=l"(r[2]), "=l"(r[3]) : "l"(p));
+}
+__device__ __forceinline__ void stg256v(int64_t* p, const int64_t (&r)[4]) {
+    asm volatile("st.global.v4.b64 [%0], {%1,%2,%3,%4};" ::"l"(p), "l"(r[0]), "l"(r[1]), "l"(r[2]), "l"(r[3]) : "memory");
+}
+template <class A>
+__device__ __forceinline__ void tensor_load(const FastArgs& F, const TensorIn& Tn, typename A::T (&e)[16], int limb,
+                                            long long drow, long long off, const typename A::C& c);
+template <>
+__device__ __forceinline__ void tensor_load<ArithF64>(const FastArgs& F, const TensorIn& Tn, double (&e)[16], int limb,
+                                                      long long drow, long long off, const F64C& c) {
+    const int g = (int)(drow / Tn.L);
+    const int64_t* base = Tn.x + (long long)limb * F.a_stride + off;
+    const int64_t* pa = base + ((g == 2) ? 1 : 0) * Tn.poly_stride;
+    const int64_t* pb = base + ((g == 0) ? 2 : 3) * Tn.poly_stride;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {      // four coefficients at a time keeps the live operand registers low
+        int64_t a[4], b[4];
+        ldg256v(pa + 4 * j, a);
+        ldg256v(pb + 4 * j, b);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) e[4 * j + i] = f64_mulmod(__longlong_as_double(a[i]), __longlong_as_double(b[i]), c);
+    }
+    if (g == 1) {
+        const int64_t* pc = base + 1 * Tn.poly_stride;
+        const int64_t* pd = base + 2 * Tn.poly_stride;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int64_t a[4], b[4];
+            ldg256v(pc + 4 * j, a);
+            ldg256v(pd + 4 * j, b);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                e[4 * j + i] = __dadd_rn(e[4 * j + i], f64_mulmod(__longlong_as_double(a[i]), __longlong_as_double(b[i]), c));
+        }
+    }
+    if (g == 2 && Tn.d2hat) {
+        int64_t* o = Tn.d2hat + (long long)limb * F.a_stride + off;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int64_t r[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) r[i] = (int64_t)__double_as_longlong(e[4 * j + i]);
+            stg256v(o + 4 * j, r);
+        }
+    }
+}
+template <>
+__device__ __forceinline__ void tensor_load<ArithU64>(const FastArgs& F, const TensorIn& Tn, uint64_t (&e)[16], int limb,
+                                                      long long drow, long long off, const U64C& c) {
+    const int g = (int)(drow / Tn.L);
+    const int64_t* base = Tn.x + (long long)limb * F.a_stride + off;
+    const int64_t* pa = base + ((g == 2) ? 1 : 0) * Tn.poly_stride;
+    const int64_t* pb = base + ((g == 0) ? 2 : 3) * Tn.poly_stride;
+    const LimbConst k = load_limb_const(Tn._2q, Tn.ql, Tn.qh, Tn.kl, Tn.kh, limb);
+    const int64_t q2 = (int64_t)k.q2;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        int64_t a[4], b[4];
+        ldg256v(pa + 4 * j, a);
+        ldg256v(pb + 4 * j, b);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) e[4 * j + i] = (uint64_t)mont_mul_ss(a[i], b[i], k.q4, k.k);   // lazy, in [0, 2q)
+    }
+    if (g == 1) {
+        const int64_t* pc = base + 1 * Tn.poly_stride;
+        const int64_t* pd = base + 2 * Tn.poly_stride;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int64_t a[4], b[4];
+            ldg256v(pc + 4 * j, a);
+            ldg256v(pd + 4 * j, b);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                e[4 * j + i] = (uint64_t)lazy_add((int64_t)e[4 * j + i], mont_mul_ss(a[i], b[i], k.q4, k.k), q2);
+        }
+    }
+    if (g == 2 && Tn.d2hat) {
+        int64_t* o = Tn.d2hat + (long long)limb * F.a_stride + off;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int64_t r[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) r[i] = (int64_t)e[4 * j + i];
+            stg256v(o + 4 * j, r);
+        }
+    }
+}
+
 // ---- inverse pass B', WARP-INDEPENDENT form (see fast_fwd_block_body_w) ------------------------------------------------
 // A thread starts from its 16 contiguous coefficients (four 256-bit loads), exchanges stay inside the warp; for
 // B == 9 the last level (distance 256) is taken as the top stage of field [8:5], which keeps it warp-private too.
-template <class A, int B, bool STAGED>
-__device__ __forceinline__ void fast_inv_block_body_w(const FastArgs& F, int64_t* sm, int limb, long long drow) {
+template <class A, int B, bool STAGED, bool TENS>
+__device__ __forceinline__ void fast_inv_block_body_w(const FastArgs& F, const TensorIn& Tn, int64_t* sm, int limb, long long drow) {
     using T = typename A::T;
     using TW = typename A::TW;
     const int tau = threadIdx.x;
@@ -1494,7 +1629,9 @@ __device__ __forceinline__ void fast_inv_block_body_w(const FastArgs& F, int64_t
         if (ra >= 0) l2_prefetch_bulk(F.a + ra * F.a_stride + (long long)ca * TILE, TILE * 8u);
     }
     T e[16];
-    {
+    if constexpr (TENS) {
+        tensor_load<A>(F, Tn, e, limb, drow, (long long)chunk * TILE + tau * 16, c);
+    } else {
         int64_t r[16];
         const int64_t* in = g + tau * 16;
 #pragma unroll
@@ -1556,10 +1693,23 @@ __global__ void __launch_bounds__(NTT_THREADS, FAST_CTAS_PER_SM) fast_inv_blockp
     extern __shared__ __align__(16) int64_t sm[];
     const RowId rid = fast_row(F);
     const int limb = rid.limb;
+    const TensorIn none{};
     if (fast_use_f64(F, rid))
-        fast_inv_block_body_w<ArithF64, B, true>(F, sm, limb, rid.data_row);
+        fast_inv_block_body_w<ArithF64, B, true, false>(F, none, sm, limb, rid.data_row);
     else
-        fast_inv_block_body_w<ArithU64, B, false>(F, sm, limb, rid.data_row);
+        fast_inv_block_body_w<ArithU64, B, false, false>(F, none, sm, limb, rid.data_row);
+}
+
+// the tensor stage's inverse block pass: tensor product fused into the load (rows = 3 x L, period L)
+template <int B>
+__global__ void __launch_bounds__(NTT_THREADS, FAST_CTAS_PER_SM) fast_inv_blockpass_tensor(const FastArgs F, const TensorIn Tn) {
+    extern __shared__ __align__(16) int64_t sm[];
+    const RowId rid = fast_row(F);
+    const int limb = rid.limb;
+    if (fast_use_f64(F, rid))
+        fast_inv_block_body_w<ArithF64, B, true, true>(F, Tn, sm, limb, rid.data_row);
+    else
+        fast_inv_block_body_w<ArithU64, B, false, true>(F, Tn, sm, limb, rid.data_row);
 }
 
 template <int B>

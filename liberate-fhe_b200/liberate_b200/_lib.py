@@ -51,9 +51,9 @@ SIGNATURES = {
     "ckks_moddown": [_i64p, _i64, _int, _int, _int, _i64p, _i64p, _i64p, _i64, _i64p, _i64, _i64p,
                      _i64p, _i64p, _i64p, _i64p, _i64p, _vp],
     "ckks_automorphism": [_i64p, _i64, _i64p, _i64, _int, _int, _i64, _int, _i64p, _vp],
-    "ckks_exec_tensor_stage": [_vp, _i64p, _i64p, _i64p, _i64p, _i64, _i64p, _i64p, _i64p, _i64p, _i64p, _i64p, _i64p, _vp],
+    "ckks_exec_tensor_stage": [_vp, _i64p, _i64p, _i64p, _i64p, _i64, _i64p, _i64p, _i64p, _i64p, _i64p, _i64p, _i64p, _i64p, _vp],
     "ckks_exec_digits": [_vp, _i64p, _i64, _i64p, _i64, _vp],
-    "ckks_exec_keyswitch_stage": [_vp, _vp, _i64, _vp, _vp, _i64, _i64p, _i64p, _i64, _i64p, _i64p, _i64, _i64p, _vp],
+    "ckks_exec_keyswitch_stage": [_vp, _vp, _i64, _vp, _vp, _i64, _i64p, _i64p, _i64, _i64p, _i64p, _i64, _i64p, _i64p, _vp],
     "ckks_exec_keyswitch_ws_elems": [_int, _int, _int, _int],
 }
 RESTYPES = {"ckks_exec_keyswitch_ws_elems": ctypes.c_int64, "ckks_launch_count": ctypes.c_int64}
@@ -100,7 +100,7 @@ class _Counted:
 
 
 lib = _Counted(_load())
-OPTION_KEYS = (1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12)
+OPTION_KEYS = (1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14)
 _OPTION_DEFAULTS = {k: lib.ckks_get_option(k) for k in OPTION_KEYS}
 
 

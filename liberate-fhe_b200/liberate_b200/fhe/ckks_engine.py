@@ -727,7 +727,7 @@ class ckks_engine:
             out1[d] = torch.empty((plan.L, plan.N), dtype=torch.int64, device=dev)
             k0p, k1p, ks = plan.key_pointer_tables(self, evk)
             executor.keyswitch_stage(plan, plan.digit_pointer_table(blocks[d]), k0p, k1p, ks, plan.d[0], plan.d[1],
-                                     out0[d], out1[d])
+                                     out0[d], out1[d], d2hat=plan.d2hat)
         return self._ct((out0, out1), nxt, "ct")
 
     def switch_key(self, ct: data_struct, ksk: data_struct) -> data_struct:

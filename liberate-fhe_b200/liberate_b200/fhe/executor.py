@@ -27,7 +27,8 @@ class LevelT(ctypes.Structure):
                 ("loc_row0", _vp), ("loc_alpha", _vp), ("loc_Y", _vp), ("loc_Ltri", _vp),
                 ("rescale_scale", _vp), ("round_at", ctypes.c_int64),
                 ("part_wide", _vp), ("Hm", _vp), ("Rd", _vp), ("C31", _vp),
-                ("Rinv", _vp), ("Pinv", _vp), ("L_small", ctypes.c_int32), ("amax", ctypes.c_int32)]
+                ("Rinv", _vp), ("Pinv", _vp), ("L_small", ctypes.c_int32), ("amax", ctypes.c_int32),
+                ("sExitT", _vp), ("sExitT_sh", _vp), ("part_row0", _vp)]
 
 
 def _p(t):
@@ -95,8 +96,11 @@ class LevelPlan:
         d.twi_u64, d.twi_f64 = _p(hold(sh_i[sl])), _p(hold(dbl_i[sl]))
         d.sR, d.sR_sh = _p(T(ntt.fs_R[0])), _p(T(ntt.fs_R[1]))
         d.sExit, d.sExit_sh = _p(T(ntt.fs_exit[0])), _p(T(ntt.fs_exit[1]))
+        d.sExitT, d.sExitT_sh = _p(T(ntt.fs_exit_tensor[0])), _p(T(ntt.fs_exit_tensor[1]))
         d.PiR = _p(hold(eng._moddown_table(level, dev)))
         d.part_alpha, d.Lenter = _p(part_alpha), _p(lenter_ptrs)
+        # first live row of every partition's own limbs on this device (-1: the partition lives elsewhere)
+        d.part_row0 = _p(i32([ntt.p.parts[level][dev][owners[s][1]][0] if owners[s][0] == dev else -1 for s in self.sids]))
         d.loc_row0, d.loc_alpha, d.loc_Y, d.loc_Ltri = _p(loc_row0), _p(loc_alpha), _p(loc_Y), _p(loc_L)
         if level > 0 and dev < len(eng.rescale_scales[level - 1]):
             d.rescale_scale = _p(hold(eng.rescale_scales[level - 1][dev]))
@@ -142,6 +146,7 @@ class LevelPlan:
         self.x = ws.get("x", 4 * L * N).view(4, L, N)
         self.d = ws.get("d", 3 * L * N).view(3, L, N)
         self.digits = ws.get("digits", max(L, 1) * N).view(max(L, 1), N)
+        self.d2hat = ws.get("d2hat", max(L, 1) * N).view(max(L, 1), N)   # NTT-domain d2 of the last tensor stage
         self.ks_ws = ws.get("ks", int(lib.ckks_exec_keyswitch_ws_elems(L, K, len(self.sids), N)))
         self.peer = {}                 # sid -> persistent copy of a remote partition's digits on this device
         self._digit_ptrs = None
@@ -185,15 +190,16 @@ def tensor_stage(plan, polys, r0s):
     """polys: 4 tensors [L,N] (rows surviving the rescale, common row stride); r0s: 4 tensors [N] on this device"""
     s = polys[0].stride(0)
     check(lib.ckks_exec_tensor_stage(plan.ref, *[_p(t) for t in polys], s, *[_p(t) for t in r0s], _p(plan.x), _p(plan.d),
-                                     _p(plan.digits), _stream(plan.x)), "exec_tensor_stage")
+                                     _p(plan.digits), _p(plan.d2hat), _stream(plan.x)), "exec_tensor_stage")
 
 
 def digits_stage(plan, a):
     check(lib.ckks_exec_digits(plan.ref, _p(a), a.stride(0), _p(plan.digits), plan.N, _stream(a)), "exec_digits")
 
 
-def keyswitch_stage(plan, digit_ptrs, k0p, k1p, kstride, add0, add1, out0, out1):
+def keyswitch_stage(plan, digit_ptrs, k0p, k1p, kstride, add0, add1, out0, out1, d2hat=None):
+    """d2hat: plan.d2hat when the digits come from the tensor stage that has just run on this plan (relinearize)"""
     add = add0 if add0 is not None else add1
     check(lib.ckks_exec_keyswitch_stage(plan.ref, _p(digit_ptrs), plan.N, _p(k0p), _p(k1p), kstride, _p(add0), _p(add1),
                                         add.stride(0) if add is not None else 0, _p(out0), _p(out1), plan.N,
-                                        _p(plan.ks_ws), _stream(out0)), "exec_keyswitch_stage")
+                                        _p(plan.ks_ws), _p(d2hat), _stream(out0)), "exec_keyswitch_stage")

@@ -91,6 +91,10 @@ class ntt_context:
         Rinv = [pow(R, -1, q) for q in c.q]
         self.fs_R = self._fast_scalar([R % q for q in c.q])                                   # "enter": x R
         self.fs_exit = self._fast_scalar([ni * ri % q for ni, ri, q in zip(c.N_inv, Rinv, c.q)])  # x N^-1 R^-1
+        # exit of the inverse transform with the tensor product fused into its load: the FP64 product of two
+        # Montgomery-form operands (scale primes, q < 2^42) carries R^2, the integer Montgomery product only R
+        self.fs_exit_tensor = self._fast_scalar([ni * ri * (ri if q < (1 << 42) else 1) % q
+                                                 for ni, ri, q in zip(c.N_inv, Rinv, c.q)])
         self.fs_ninv = self._fast_scalar(list(c.N_inv))                                        # x N^-1
 
     def _fast_scalar(self, values):

@@ -126,3 +126,23 @@ def test_captured_graph_replays_the_same_bits(D):
     g2.replay()
     assert same(g2.result, want3), "replayed rotate differs from the eager rotate"
     torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("opts", [[(12, 0)], [(13, 1)], [(14, 1)], [(13, 1), (14, 1)], [(10, 1), (9, 400)], [(9, 1)]],
+                         ids=["no-rescale-fusion", "tensor-fusion", "own-skip", "tensor+own", "one-stream", "many-slabs"])
+def test_optional_fused_paths_reproduce_reference_tensors(opts):
+    """every ckks_set_option variant of the executor (rescale / tensor-product fusion, own-partition skip, slab and
+    side-stream settings) must hit the same golden digests as the default path"""
+    from liberate_b200._lib import lib, option_defaults
+    g = json.loads((GOLDEN / "engine_D2.json").read_text())
+    full = np.load(GOLDEN / "engine_D2_full.npz")
+    try:
+        for k, v in opts:
+            lib.ckks_set_option(k, v)
+        eng = make_engine(2, g["params"], "executor")
+        chk = Checker(g["digests"], full, eng.ntt.devices)
+        flows.hot_path_flow(eng, chk)
+        assert not chk.failures, chk.failures[:8]
+    finally:
+        for k, v in option_defaults().items():
+            lib.ckks_set_option(k, v)
