@@ -215,6 +215,27 @@ int ckks_exec_keyswitch_stage(const ckks_level_t* lv, const int64_t* const* digi
                               int64_t* out1, int64_t out_stride, int64_t* ws, const int64_t* d2hat, void* stream);
 int64_t ckks_exec_keyswitch_ws_elems(int L, int K, int nparts, int N);
 
+/* ---- sampler: ChaCha20 counter mode (replaces src/liberate/csprng/: chacha20 / randint / discrete_gaussian / randround
+ * extensions, csprng.py:18-323).  Same stream as the reference for the same key and nonce, but stateless: the block
+ * of channel c, position l has the 64-bit counter ctr_base[c] + l + epoch[c][l] * inc, and epoch[c][l] (device, uint32,
+ * incremented by the call) replaces the reference's [blocks,16] int64 state tensor.  One block gives four samples, so a
+ * channel of N coefficients has L = N/4 blocks.  key_nonce: HOST pointer to 8 key words + 2 nonce words.
+ * out pointers must be 32-byte aligned. */
+/* randbytes (csprng.py:216-236, chacha20_cuda_kernel.cu): out[C][L][16] = the 16 output words of every block */
+int ckks_rng_bytes(int64_t* out, int C, int L, const uint32_t* key_nonce, const uint64_t* ctr_base, uint32_t* epoch,
+                   uint64_t inc, void* stream);
+/* randint (csprng.py:238-272, randint_cuda_kernel.cu:23-102): out[C][4L] = floor(X q[c] / 2^128) + shift, X the 128-bit draw */
+int ckks_rng_randint(int64_t* out, int C, int L, const uint64_t* q, int64_t shift, const uint32_t* key_nonce,
+                     const uint64_t* ctr_base, uint32_t* epoch, uint64_t inc, void* stream);
+/* discrete_gaussian (csprng.py:274-305, discrete_gaussian_cuda_kernel.cu:27-108): out[C][4L]; lut: HOST table of the CDT
+ * search tree, lut_size low words then lut_size high words (discrete_gaussian_sampler.py:96-116), depth levels */
+int ckks_rng_gaussian(int64_t* out, int C, int L, const uint64_t* lut, int lut_size, int depth, const uint32_t* key_nonce,
+                      const uint64_t* ctr_base, uint32_t* epoch, uint64_t inc, void* stream);
+/* randround (csprng.py:307-323, randround_cuda_kernel.cu:8-37): out[i] = sign(coef[i]) (floor|coef[i]| + [u_i < frac 2^32]),
+ * u_i the i-th 32-bit word of blocks 0..ceil(n/16)-1 of one channel (ctr_base has one entry) */
+int ckks_rng_randround(const double* coef, int64_t* out, int n, const uint32_t* key_nonce, const uint64_t* ctr_base,
+                       uint32_t* epoch, uint64_t inc, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -8,7 +8,7 @@ from pathlib import Path
 
 HERE = Path(__file__).resolve().parent
 SOURCES = ["ckks_b200.cu"]
-HEADERS = ["mont.cuh", "ntt_kernels.cuh", "ntt_fast.cuh", "../../include/ckks_b200.h"]
+HEADERS = ["mont.cuh", "ntt_kernels.cuh", "ntt_fast.cuh", "csprng.cuh", "../../include/ckks_b200.h"]
 LIB = HERE / "libckks_b200.so"
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-shared", "-split-compile", "0"]

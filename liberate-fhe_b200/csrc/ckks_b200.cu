@@ -7,6 +7,7 @@
 #include "mont.cuh"
 #include "ntt_kernels.cuh"
 #include "ntt_fast.cuh"
+#include "csprng.cuh"
 
 using namespace ckks;
 
@@ -1069,7 +1070,8 @@ int ckks_exec_keyswitch_stage(const ckks_level_t* lv, const int64_t* const* digi
                               int64_t* out1, int64_t out_stride, int64_t* ws, const int64_t* d2hat, void* stream) {
     CHECK_PTRS(lv, digit_ptrs, k0_ptrs, k1_ptrs, out0, out1, ws);
     // own-partition skip: only with the default one-tile-per-CTA kernels, the partition table and d2hat from the tensor stage
-    const int32_t* own_row0 = (g_own_skip && d2hat && lv->part_row0 && !g_persist && g_warp != 2 && !g_colpp) ? lv->part_row0 : nullptr;
+    // (the tensor stage with the product fused into its inverse transform does not produce d2hat: the two options exclude each other)
+    const int32_t* own_row0 = (g_own_skip && !g_fuse_tensor && d2hat && lv->part_row0 && !g_persist && g_warp != 2 && !g_colpp) ? lv->part_row0 : nullptr;
     const int L = lv->L, K = lv->K, E = L + K, P = lv->nparts, N = 1 << lv->logN;
     int64_t* ext = ws;                                  // [P*E][N]
     int64_t* acc = ext + (long long)P * E * N;          // [2E][N]
@@ -1166,6 +1168,59 @@ int ckks_automorphism(const int64_t* in, int64_t is, int64_t* out, int64_t os, i
     if (canon && !_2q) return CKKS_E_BADARG;
     k_automorphism<<<dim3((N + EW_THREADS - 1) / EW_THREADS, C), EW_THREADS, 0, S(stream)>>>(
         in, is, out, os, N, (unsigned)(g & (2 * (int64_t)N - 1)), canon, _2q);
+    return launch_status();
+}
+
+// ---- sampler (csprng.cuh): ChaCha20 counter mode, one block = four samples ----------------------------------------
+static RngArgs rng_args(const uint32_t* key_nonce, const uint64_t* ctr_base, uint32_t* epoch, uint64_t inc, int L) {
+    RngArgs A{};
+    for (int i = 0; i < 10; ++i) A.key.w[i] = key_nonce[i];
+    A.ctr_base = ctr_base;
+    A.epoch = epoch;
+    A.inc = inc;
+    A.L = L;
+    return A;
+}
+static dim3 rng_grid(int C, int L) { return dim3((L + 127) / 128, C); }
+
+int ckks_rng_bytes(int64_t* out, int C, int L, const uint32_t* key_nonce, const uint64_t* ctr_base, uint32_t* epoch,
+                   uint64_t inc, void* stream) {
+    CHECK_PTRS(out, key_nonce, ctr_base, epoch);
+    if (C <= 0 || L <= 0) return CKKS_E_BADARG;
+    if (reinterpret_cast<uintptr_t>(out) & 31) return CKKS_E_ALIGN;
+    k_rng_bytes<<<rng_grid(C, L), 128, 0, S(stream)>>>(out, rng_args(key_nonce, ctr_base, epoch, inc, L));
+    return launch_status();
+}
+
+int ckks_rng_randint(int64_t* out, int C, int L, const uint64_t* q, int64_t shift, const uint32_t* key_nonce,
+                     const uint64_t* ctr_base, uint32_t* epoch, uint64_t inc, void* stream) {
+    CHECK_PTRS(out, q, key_nonce, ctr_base, epoch);
+    if (C <= 0 || L <= 0) return CKKS_E_BADARG;
+    if (reinterpret_cast<uintptr_t>(out) & 31) return CKKS_E_ALIGN;
+    k_rng_randint<<<rng_grid(C, L), 128, 0, S(stream)>>>(out, q, shift, rng_args(key_nonce, ctr_base, epoch, inc, L));
+    return launch_status();
+}
+
+int ckks_rng_gaussian(int64_t* out, int C, int L, const uint64_t* lut, int lut_size, int depth, const uint32_t* key_nonce,
+                      const uint64_t* ctr_base, uint32_t* epoch, uint64_t inc, void* stream) {
+    CHECK_PTRS(out, lut, key_nonce, ctr_base, epoch);
+    if (C <= 0 || L <= 0 || lut_size <= 0 || 2 * lut_size > 128 || depth <= 0 || depth > 6) return CKKS_E_BADARG;
+    if (reinterpret_cast<uintptr_t>(out) & 31) return CKKS_E_ALIGN;
+    GaussLut T{};
+    for (int i = 0; i < 2 * lut_size; ++i) T.v[i] = lut[i];   // HOST table: [low words | high words]
+    T.size = lut_size;
+    T.depth = depth;
+    k_rng_gaussian<<<rng_grid(C, L), 128, 0, S(stream)>>>(out, T, rng_args(key_nonce, ctr_base, epoch, inc, L));
+    return launch_status();
+}
+
+int ckks_rng_randround(const double* coef, int64_t* out, int n, const uint32_t* key_nonce, const uint64_t* ctr_base,
+                       uint32_t* epoch, uint64_t inc, void* stream) {
+    CHECK_PTRS(coef, out, key_nonce, ctr_base, epoch);
+    if (n <= 0) return CKKS_E_BADARG;
+    if (reinterpret_cast<uintptr_t>(out) & 31) return CKKS_E_ALIGN;
+    const int L = (n + 15) / 16;
+    k_rng_randround<<<rng_grid(1, L), 128, 0, S(stream)>>>(coef, out, n, rng_args(key_nonce, ctr_base, epoch, inc, L));
     return launch_status();
 }
 

@@ -55,6 +55,10 @@ SIGNATURES = {
     "ckks_exec_digits": [_vp, _i64p, _i64, _i64p, _i64, _vp],
     "ckks_exec_keyswitch_stage": [_vp, _vp, _i64, _vp, _vp, _i64, _i64p, _i64p, _i64, _i64p, _i64p, _i64, _i64p, _i64p, _vp],
     "ckks_exec_keyswitch_ws_elems": [_int, _int, _int, _int],
+    "ckks_rng_bytes": [_i64p, _int, _int, _vp, _vp, _vp, ctypes.c_uint64, _vp],
+    "ckks_rng_randint": [_i64p, _int, _int, _vp, _i64, _vp, _vp, _vp, ctypes.c_uint64, _vp],
+    "ckks_rng_gaussian": [_i64p, _int, _int, _vp, _int, _int, _vp, _vp, _vp, ctypes.c_uint64, _vp],
+    "ckks_rng_randround": [_vp, _i64p, _int, _vp, _vp, _vp, ctypes.c_uint64, _vp],
 }
 RESTYPES = {"ckks_exec_keyswitch_ws_elems": ctypes.c_int64, "ckks_launch_count": ctypes.c_int64}
 

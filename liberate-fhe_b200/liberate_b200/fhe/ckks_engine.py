@@ -76,8 +76,18 @@ class ckks_engine:
         self.num_levels = self.ntt.num_levels - 1
         self.num_slots = self.ctx.N // 2
         if rng is None:
+            seed = nonce = None
+            if distributed:
+                # one process per GPU: every rank must run the SAME ChaCha20 key and nonce, or the repeated channels
+                # (secret key, shared randomness of the public key) would differ between the ranks
+                box = [None]
+                if self.comm.rank == 0:
+                    from ..csprng import _words
+                    box = [(_words(None, 8, "seed"), _words(None, 2, "nonce"))]
+                self.comm.dist.broadcast_object_list(box, src=0, group=self.comm.group)
+                seed, nonce = box[0]
             rng = Csprng(self.ctx.N, [len(d) for d in self.ntt.p.d], max(self.ntt.num_special_primes, 2),
-                         devices=self.ntt.devices, local_ids=self.local_ids)
+                         devices=self.ntt.devices, local_ids=self.local_ids, seed=seed, nonce=nonce)
         self.rng = rng
         self.int_scale = 2 ** self.ctx.scale_bits
         self.scale = np.float64(self.int_scale)
