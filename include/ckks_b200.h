@@ -77,6 +77,9 @@ int ckks_mont_add(const int64_t* a, int64_t a_stride, const int64_t* b, int64_t 
                   int64_t c_stride, int C, int N, const int64_t* _2q, void* stream);
 int ckks_mont_sub(const int64_t* a, int64_t a_stride, const int64_t* b, int64_t b_stride, int64_t* c,
                   int64_t c_stride, int C, int N, const int64_t* _2q, void* stream);
+/* cc_add / cc_sub (engine.py:1268-1330): mont_add | mont_sub followed by reduce_2q, one pass instead of two (c may alias a or b) */
+int ckks_addsub_reduce(const int64_t* a, int64_t a_stride, const int64_t* b, int64_t b_stride, int64_t* c,
+                       int64_t c_stride, int C, int N, const int64_t* _2q, int sub, void* stream);
 /* tile_unsigned (ntt.cpp:409-419, kern.cu:997-1014): dst[i][:] = a[:] + q_i */
 int ckks_tile_unsigned(const int64_t* a, int64_t* dst, int64_t dst_stride, int C, int N, const int64_t* _2q,
                        void* stream);

@@ -86,7 +86,7 @@ __global__ void k_unary(int64_t* __restrict__ a, long long as, int N, const int6
     st2(a + i * as + j, x);
 }
 
-template <bool SUB>
+template <bool SUB, bool RED = false>
 __global__ void k_addsub(const int64_t* __restrict__ a, long long as, const int64_t* __restrict__ b, long long bs,
                          int64_t* __restrict__ c, long long cs, int N, const int64_t* __restrict__ _2q) {
     const int i = blockIdx.y;
@@ -97,6 +97,10 @@ __global__ void k_addsub(const int64_t* __restrict__ a, long long as, const int6
     longlong2 r;
     r.x = SUB ? lazy_sub(x.x, y.x, q2) : lazy_add(x.x, y.x, q2);
     r.y = SUB ? lazy_sub(x.y, y.y, q2) : lazy_add(x.y, y.y, q2);
+    if (RED) {   // + reduce_2q (kern.cu:664-680) in the same pass
+        r.x = reduce_q(r.x, q2 >> 1);
+        r.y = reduce_q(r.y, q2 >> 1);
+    }
     st2(c + i * cs + j, r);
 }
 
@@ -762,6 +766,16 @@ int ckks_mont_add(const int64_t* a, int64_t as, const int64_t* b, int64_t bs, in
     k_addsub<false><<<ew_grid(N, C), EW_THREADS, 0, S(stream)>>>(a, as, b, bs, c, cs, N, _2q);
     return launch_status();
 }
+int ckks_addsub_reduce(const int64_t* a, int64_t as, const int64_t* b, int64_t bs, int64_t* c, int64_t cs, int C, int N,
+                       const int64_t* _2q, int sub, void* stream) {
+    CHECK_PTRS(a, b, c, _2q);
+    if (C <= 0 || N <= 0 || (N & 1)) return CKKS_E_BADARG;
+    if (!row_ok(a, as) || !row_ok(b, bs) || !row_ok(c, cs)) return CKKS_E_ALIGN;
+    if (sub) k_addsub<true, true><<<ew_grid(N, C), EW_THREADS, 0, S(stream)>>>(a, as, b, bs, c, cs, N, _2q);
+    else k_addsub<false, true><<<ew_grid(N, C), EW_THREADS, 0, S(stream)>>>(a, as, b, bs, c, cs, N, _2q);
+    return launch_status();
+}
+
 int ckks_mont_sub(const int64_t* a, int64_t as, const int64_t* b, int64_t bs, int64_t* c, int64_t cs, int C, int N,
                   const int64_t* _2q, void* stream) {
     CHECK_PTRS(a, b, c, _2q);

@@ -35,6 +35,7 @@ SIGNATURES = {
     "ckks_make_unsigned": [_i64p, _i64, _int, _int, _i64p, _vp],
     "ckks_mont_add": [_i64p, _i64, _i64p, _i64, _i64p, _i64, _int, _int, _i64p, _vp],
     "ckks_mont_sub": [_i64p, _i64, _i64p, _i64, _i64p, _i64, _int, _int, _i64p, _vp],
+    "ckks_addsub_reduce": [_i64p, _i64, _i64p, _i64, _i64p, _i64, _int, _int, _i64p, _int, _vp],
     "ckks_tile_unsigned": [_i64p, _i64p, _i64, _int, _int, _i64p, _vp],
     "ckks_compact_twiddles": [_i64p, _i64p, _int, _int, _int, _vp],
     "ckks_fast_tables": [_i64p, _i64p, _vp, _vp, _int, _int, _vp],

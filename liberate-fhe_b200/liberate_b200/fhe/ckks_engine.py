@@ -888,22 +888,25 @@ class ckks_engine:
         level = a.level
         data = []
         for pa, pb in zip(a.data, b.data):
-            c = op(pa, pb, level)
-            self.ntt.reduce_2q(c, level)
+            if self.fast:      # one kernel per polynomial: add/sub and the reduce_2q that follows it
+                c = self.ntt.addsub_reduce(pa, pb, op == "sub", level)
+            else:
+                c = (self.ntt.mont_sub if op == "sub" else self.ntt.mont_add)(pa, pb, level)
+                self.ntt.reduce_2q(c, level)
             data.append(c)
         return self._ct(data, level, origin, ntt_state=want, montgomery_state=want)
 
     def cc_add_double(self, a, b):
-        return self._cc_linear(a, b, self.ntt.mont_add, "ct")
+        return self._cc_linear(a, b, "add", "ct")
 
     def cc_add_triplet(self, a, b):
-        return self._cc_linear(a, b, self.ntt.mont_add, "ctt")
+        return self._cc_linear(a, b, "add", "ctt")
 
     def cc_sub_double(self, a, b):
-        return self._cc_linear(a, b, self.ntt.mont_sub, "ct")
+        return self._cc_linear(a, b, "sub", "ct")
 
     def cc_sub_triplet(self, a, b):
-        return self._cc_linear(a, b, self.ntt.mont_sub, "ctt")
+        return self._cc_linear(a, b, "sub", "ctt")
 
     def cc_add(self, a: data_struct, b: data_struct) -> data_struct:
         if a.origin == types.origins["ct"] and b.origin == types.origins["ct"]:

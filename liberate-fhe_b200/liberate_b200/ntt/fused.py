@@ -24,6 +24,16 @@ def rescale(x, r0, scale, round_at, mp, canon=False):
     return out
 
 
+def addsub_reduce(a, b, _2q, sub=False):
+    """mont_add / mont_sub + reduce_2q in one pass (cc_add / cc_sub, engine.py:1268-1330) -> new [C,N]"""
+    sa, sb = _rows(a, "addsub_reduce"), _rows(b, "addsub_reduce")
+    out = torch.empty((a.size(0), a.size(1)), dtype=torch.int64, device=a.device)
+    with _Launch(a):
+        check(lib.ckks_addsub_reduce(_ptr(a), sa, _ptr(b), sb, _ptr(out), out.size(1), a.size(0), a.size(1), _ptr(_vec(_2q)),
+                                     1 if sub else 0, _stream(a)), "addsub_reduce")
+    return out
+
+
 def tensor_product(x0, x1, y0, y1, mp):
     """engine.py:1095-1101 -> (d0, d1, d2)"""
     s = _rows(x0, "tensor_product")

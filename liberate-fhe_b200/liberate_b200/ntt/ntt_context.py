@@ -314,5 +314,11 @@ class ntt_context:
     def mont_sub(self, a, b, lvl=0, mult_type=-1, part=0):
         return self._expand(a, ntt_cuda.mont_sub(self._live(a), self._live(b), self._sel(self._2q, lvl, mult_type, part)))
 
+    def addsub_reduce(self, a, b, sub, lvl=0, mult_type=-1, part=0):
+        """mont_add / mont_sub followed by reduce_2q as ONE kernel per device (same integers as the two-call sequence)"""
+        q2 = self._sel(self._2q, lvl, mult_type, part)
+        outs = [fused.addsub_reduce(x, y, q, sub) for x, y, q in zip(self._live(a), self._live(b), q2)]
+        return self._expand(a, outs)
+
     def tile_unsigned(self, a, lvl=0, mult_type=-1, part=0):
         return self._expand(a, ntt_cuda.tile_unsigned(self._live(a), self._sel(self._2q, lvl, mult_type, part)))
