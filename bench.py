@@ -5,7 +5,8 @@
 
 A "step" is one engine.mult(ct_a, ct_b, evk) = rescale x2 + 4 NTT + tensor product + 3 iNTT + hybrid key switch
 (ModUp -> beta*E NTTs -> evk inner product -> 2 iNTT -> ModDown) on level-0 gold ciphertexts.
-  value : mults/s with ciphertexts and keys resident in HBM (CUDA events, max over ranks)
+  value : mults/s with ciphertexts and keys resident in HBM (CUDA events, max over ranks); the step is the engine
+          call replayed as a CUDA graph (engine.capture; --graph off launches it eagerly: same kernels, +4 %)
   e2e   : mults/s through the same engine call with the two input ciphertexts in pinned HOST memory and the
           result read back to host inside the timed region (keys stay resident: they are long-lived operands)
   roofline : the batched forward NTT of the key switch ([E', N] limbs per call), timed alone with CUDA events;
@@ -13,7 +14,7 @@ A "step" is one engine.mult(ct_a, ct_b, evk) = rescale x2 + 4 NTT + tensor produ
   cpu_baseline / --impl reference : the oracle port (oracle/engine_oracle.OracleEngine, C + OpenMP) doing the same
           mult on the host cores -- the reference has no CPU implementation of its own.
 N > 1 shards the RNS limbs of ONE multiplication over the ranks (the reference's own partitioning) with one
-all_gather (ModUp digits) and two broadcasts (rescale limbs) per step: total work is fixed -> "strong" scaling.
+all_gather (ModUp digits) and one packed broadcast (rescale limbs) per step: total work is fixed -> "strong" scaling.
 Working set (2 ciphertexts + evk ~ 507 MB at gold) exceeds the 126 MB L2, so no explicit L2 flush is needed.
 """
 import argparse
