@@ -37,6 +37,28 @@ def build(verbose=False):
     return so
 
 
+CSPRNG_EXTS = {"chacha20_cuda": ["chacha20.cpp", "chacha20_cuda_kernel.cu"],
+               "randint_cuda": ["randint.cpp", "randint_cuda_kernel.cu"],
+               "discrete_gaussian_cuda": ["discrete_gaussian.cpp", "discrete_gaussian_cuda_kernel.cu"],
+               "randround_cuda": ["randround.cpp", "randround_cuda_kernel.cu"]}
+
+
+def build_one(name, verbose=False):
+    """one extension of the reference, from its sources in place, into oracle/_ref/"""
+    if name == "ntt_cuda_ref":
+        return build(verbose)
+    os.environ.setdefault("TORCH_CUDA_ARCH_LIST", "10.0")
+    os.environ.setdefault("MAX_JOBS", "2")
+    from torch.utils.cpp_extension import load
+    cs = REF.parent / "csprng"
+    bdir = OUT / f"build_{name}"
+    bdir.mkdir(parents=True, exist_ok=True)
+    if not (bdir / f"{name}.so").exists():
+        load(name=name, sources=[str(cs / s) for s in CSPRNG_EXTS[name]], extra_cuda_cflags=["-O3"],
+             build_directory=str(bdir), is_python_module=False, verbose=verbose)
+    return bdir / f"{name}.so"
+
+
 def build_engine(verbose=False):
     """"installs" the whole reference package for the GPU-side comparison rows (bench.py --impl reference_gpu,
     tests/test_gpu_vs_reference_engine.py): the four csprng extensions are compiled UNMODIFIED from
@@ -52,21 +74,15 @@ def build_engine(verbose=False):
     pkg = site / "liberate"
     if (pkg / ".complete").exists():
         return site
-    build(verbose)
-    os.environ.setdefault("TORCH_CUDA_ARCH_LIST", "10.0")
-    os.environ.setdefault("MAX_JOBS", "4")
-    from torch.utils.cpp_extension import load
-    cs = src_pkg / "csprng"
-    exts = {"chacha20_cuda": ["chacha20.cpp", "chacha20_cuda_kernel.cu"],
-            "randint_cuda": ["randint.cpp", "randint_cuda_kernel.cu"],
-            "discrete_gaussian_cuda": ["discrete_gaussian.cpp", "discrete_gaussian_cuda_kernel.cu"],
-            "randround_cuda": ["randround.cpp", "randround_cuda_kernel.cu"]}
-    for name, srcs in exts.items():
-        bdir = OUT / f"build_{name}"
-        bdir.mkdir(exist_ok=True)
-        if not (bdir / f"{name}.so").exists():
-            load(name=name, sources=[str(cs / s) for s in srcs], extra_cuda_cflags=["-O3"],
-                 build_directory=str(bdir), is_python_module=False, verbose=verbose)
+    # the five extensions are independent: compile them side by side, one child process each (about 4 minutes
+    # instead of 11 on 8 cores)
+    import subprocess
+    OUT.mkdir(exist_ok=True)
+    jobs = [subprocess.Popen([sys.executable, __file__, "--one", name]) for name in ["ntt_cuda_ref"] + list(CSPRNG_EXTS)]
+    failed = [j.args[-1] for j in jobs if j.wait() != 0]
+    if failed:
+        raise RuntimeError(f"reference extensions failed to build: {failed}")
+    exts = CSPRNG_EXTS
     if pkg.exists():
         shutil.rmtree(pkg)
     shutil.copytree(src_pkg, pkg, ignore=shutil.ignore_patterns("*.cu", "*.cpp", "*.h", "__pycache__", "tests"))
@@ -85,6 +101,9 @@ def build_engine(verbose=False):
 
 
 if __name__ == "__main__":
-    print(build(verbose="-v" in sys.argv))
-    if "--engine" in sys.argv:
+    if "--one" in sys.argv:
+        print(build_one(sys.argv[sys.argv.index("--one") + 1], verbose="-v" in sys.argv))
+    elif "--engine" in sys.argv:
         print(build_engine(verbose="-v" in sys.argv))
+    else:
+        print(build(verbose="-v" in sys.argv))
