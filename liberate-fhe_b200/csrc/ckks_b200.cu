@@ -489,11 +489,11 @@ static int launch_fast_col(bool fwd, const FastArgs& F, dim3 grid, cudaStream_t 
         return launch_status();
     }
     if (fwd) {
-        cudaFuncSetAttribute(fast_fwd_colpass<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, FAST_SMEM_BYTES);
-        fast_fwd_colpass<0><<<tile_grid(grid), NTT_THREADS, FAST_SMEM_BYTES, st>>>(F);
+        cudaFuncSetAttribute(fast_fwd_colpass<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, COL_SMEM_BYTES);
+        fast_fwd_colpass<0><<<tile_grid(grid), NTT_THREADS, COL_SMEM_BYTES, st>>>(F);
     } else {
-        cudaFuncSetAttribute(fast_inv_colpass<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, FAST_SMEM_BYTES);
-        fast_inv_colpass<0><<<tile_grid(grid), NTT_THREADS, FAST_SMEM_BYTES, st>>>(F);
+        cudaFuncSetAttribute(fast_inv_colpass<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, COL_SMEM_BYTES);
+        fast_inv_colpass<0><<<tile_grid(grid), NTT_THREADS, COL_SMEM_BYTES, st>>>(F);
     }
     return launch_status();
 }
@@ -1044,8 +1044,8 @@ int ckks_exec_tensor_stage(const ckks_level_t* lv, const int64_t* a0, const int6
         FastArgs F{x, N, reinterpret_cast<const ulonglong2*>(lv->twf_u64), lv->twf_f64, lv->q, lv->sR,
                    (const uint64_t*)lv->sR_sh, L, lv->logN, 0, 0, 0, 0, 0, 0, g_swap, 0, 0, 0};
         const dim3 grid(N / TILE, 4 * L);
-        cudaFuncSetAttribute(fast_fwd_colpass_rescale<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, FAST_SMEM_BYTES);
-        fast_fwd_colpass_rescale<0><<<tile_grid(grid), NTT_THREADS, FAST_SMEM_BYTES, S(stream)>>>(F, R);
+        cudaFuncSetAttribute(fast_fwd_colpass_rescale<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, COL_SMEM_BYTES);
+        fast_fwd_colpass_rescale<0><<<tile_grid(grid), NTT_THREADS, COL_SMEM_BYTES, S(stream)>>>(F, R);
         RC(launch_status());
         F.scal = nullptr;
         F.prefetch = g_prefetch;

@@ -456,6 +456,12 @@ __device__ __forceinline__ ulonglong2 scalar_tw<ArithU64>(const FastArgs& F, int
 #endif
 constexpr int FAST_TW_SLOTS = 4096;
 constexpr int FAST_SMEM_BYTES = SMEM_BYTES + FAST_TW_SLOTS * 8 + 16;
+// column passes stage only 256 twiddles: 39 KB per CTA and a 64-register cap give 4 CTAs/SM (col pass 94 -> 89 us per 380 limbs)
+#ifndef FAST_COL_CTAS
+#define FAST_COL_CTAS 4
+#endif
+constexpr int COL_TW_SLOTS = 256;
+constexpr int COL_SMEM_BYTES = SMEM_BYTES + COL_TW_SLOTS * 8 + 16;
 
 template <class TW>
 struct TwSharedBlock {   // block pass: stage j (global stage 8+j) holds 2^(j+unit_log) twiddles, stages back to back
@@ -573,7 +579,7 @@ __device__ __forceinline__ void fast_fwd_col_body(const FastArgs& F, const Resca
     int64_t* __restrict__ row0 = F.a + drow * F.a_stride + (long long)grid_chunk(F) * 16;
     const TW* __restrict__ W = tw_row<A>(F, limb);
     TW* tws = reinterpret_cast<TW*>(sm + SMEM_SLOTS);
-    uint64_t* bar = reinterpret_cast<uint64_t*>(sm + SMEM_SLOTS + FAST_TW_SLOTS);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(sm + SMEM_SLOTS + COL_TW_SLOTS);
     if constexpr (STAGED) stage_col_twiddles(reinterpret_cast<const double*>(W), reinterpret_cast<double*>(tws), bar);
     if constexpr (!RESC) {
         unsigned ca = 0;
@@ -616,7 +622,7 @@ __device__ __forceinline__ void fast_fwd_col_body(const FastArgs& F, const Resca
 }
 
 template <int DUMMY>
-__global__ void __launch_bounds__(NTT_THREADS, FAST_CTAS_PER_SM) fast_fwd_colpass(const FastArgs F) {
+__global__ void __launch_bounds__(NTT_THREADS, FAST_COL_CTAS) fast_fwd_colpass(const FastArgs F) {
     extern __shared__ __align__(16) int64_t sm[];
     if (fast_skip_own(F)) return;
     const RowId rid = fast_row(F);
@@ -630,7 +636,7 @@ __global__ void __launch_bounds__(NTT_THREADS, FAST_CTAS_PER_SM) fast_fwd_colpas
 
 // the tensor stage's column pass: rescale fused into the load (rows = 4 polynomials x L limbs, period L, F.scal = R mod q)
 template <int DUMMY>
-__global__ void __launch_bounds__(NTT_THREADS, FAST_CTAS_PER_SM) fast_fwd_colpass_rescale(const FastArgs F, const RescaleIn R) {
+__global__ void __launch_bounds__(NTT_THREADS, FAST_COL_CTAS) fast_fwd_colpass_rescale(const FastArgs F, const RescaleIn R) {
     extern __shared__ __align__(16) int64_t sm[];
     const RowId rid = fast_row(F);
     const int limb = rid.limb;
@@ -1861,7 +1867,7 @@ __device__ __forceinline__ void fast_inv_col_body(const FastArgs& F, int64_t* sm
     int64_t* __restrict__ row0 = F.a + drow * F.a_stride + (long long)grid_chunk(F) * 16;
     const TW* __restrict__ W = tw_row<A>(F, limb);
     TW* tws = reinterpret_cast<TW*>(sm + SMEM_SLOTS);
-    uint64_t* bar = reinterpret_cast<uint64_t*>(sm + SMEM_SLOTS + FAST_TW_SLOTS);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(sm + SMEM_SLOTS + COL_TW_SLOTS);
     if constexpr (STAGED) stage_col_twiddles(reinterpret_cast<const double*>(W), reinterpret_cast<double*>(tws), bar);
     {
         unsigned ca = 0;
@@ -1897,7 +1903,7 @@ __device__ __forceinline__ void fast_inv_col_body(const FastArgs& F, int64_t* sm
 }
 
 template <int DUMMY>
-__global__ void __launch_bounds__(NTT_THREADS, FAST_CTAS_PER_SM) fast_inv_colpass(const FastArgs F) {
+__global__ void __launch_bounds__(NTT_THREADS, FAST_COL_CTAS) fast_inv_colpass(const FastArgs F) {
     extern __shared__ __align__(16) int64_t sm[];
     const RowId rid = fast_row(F);
     const int limb = rid.limb;
