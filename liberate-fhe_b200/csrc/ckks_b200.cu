@@ -445,6 +445,9 @@ static int launch_inv_block(const NttArgs& A, dim3 grid, cudaStream_t st) {
 
 int g_persist = 0;
 int g_prefetch = PREFETCH_ROWS_AHEAD;   // ckks_set_option(2, rows_ahead); 0 disables the L2 prefetch   // 1: persistent TMA-pipelined block pass (ckks_set_option(1, v))
+int g_hyb = 3;    // ckks_set_option(15, mask): hybrid-twiddle block passes (4 CTAs/SM) -- bit 0 forward, bit 1 inverse,
+                  // bit 2 also inside the row-slab pipeline of ckks_ntt_fast / ckks_intt_fast
+bool g_in_row_slabs = false;
 int g_skip = 0;   // ckks_set_option(5, mask): measurement only -- bit 0 skips the column pass, bit 1 the block pass
 int g_warp = 1;   // ckks_set_option(3, v): 0 classic, 1 = warp-independent block passes with 256-bit global accesses (default), 2 = persistent
 inline bool aligned32(const void* p, long long stride) { return (((uintptr_t)p) & 31) == 0 && (stride & 3) == 0; }
@@ -517,6 +520,13 @@ static int launch_fast_fwd_block(const FastArgs& F, dim3 grid, cudaStream_t st) 
         fast_fwd_blockpass_pp<B><<<pp_ctas(tiles), NTT_THREADS, PP_SMEM_BYTES, st>>>(F, tiles, G);
         return launch_status();
     }
+    if constexpr (B >= 7) {
+        if (((g_warp == 1 && (g_hyb & 1) && !(g_in_row_slabs && !(g_hyb & 4))) || g_warp == 3) && aligned32(F.a, F.a_stride)) {
+            cudaFuncSetAttribute(fast_fwd_blockpass_h<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, HYB_SMEM_BYTES);
+            fast_fwd_blockpass_h<B><<<tile_grid(grid), NTT_THREADS, HYB_SMEM_BYTES, st>>>(F);
+            return launch_status();
+        }
+    }
     if (g_warp && aligned32(F.a, F.a_stride)) {
         cudaFuncSetAttribute(fast_fwd_blockpass_w<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, FAST_SMEM_BYTES);
         fast_fwd_blockpass_w<B><<<tile_grid(grid), NTT_THREADS, FAST_SMEM_BYTES, st>>>(F);
@@ -534,6 +544,13 @@ static int launch_fast_inv_block(const FastArgs& F, dim3 grid, cudaStream_t st) 
         cudaFuncSetAttribute(fast_inv_blockpass_pp<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, PP_SMEM_BYTES);
         fast_inv_blockpass_pp<B><<<pp_ctas(tiles), NTT_THREADS, PP_SMEM_BYTES, st>>>(F, tiles, G);
         return launch_status();
+    }
+    if constexpr (B >= 7) {
+        if (((g_warp == 1 && (g_hyb & 2) && !(g_in_row_slabs && !(g_hyb & 4))) || g_warp == 3) && aligned32(F.a, F.a_stride)) {
+            cudaFuncSetAttribute(fast_inv_blockpass_h<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, HYB_SMEM_BYTES);
+            fast_inv_blockpass_h<B><<<tile_grid(grid), NTT_THREADS, HYB_SMEM_BYTES, st>>>(F);
+            return launch_status();
+        }
     }
     if (g_warp && aligned32(F.a, F.a_stride)) {
         cudaFuncSetAttribute(fast_inv_blockpass_w<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, FAST_SMEM_BYTES);
@@ -664,7 +681,9 @@ static int intt_fast_impl(int64_t* a, int64_t as, int rows, int period, int logN
             Fs.row0 = r0 % period;
             const dim3 g((1 << logN) / TILE, r1 - r0);
             cudaStream_t ss = pipes->s[k % npipes];
+            g_in_row_slabs = true;
             rc = launch_fast_inv_block_any(Fs, g, ss, logN);
+            g_in_row_slabs = false;
             if (rc) return rc;
             rc = launch_fast_col(false, Fs, g, ss);
             if (rc) return rc;
@@ -698,6 +717,7 @@ int ckks_get_option(int key) {
     if (key == 12) return g_fuse_rescale;
     if (key == 13) return g_fuse_tensor;
     if (key == 14) return g_own_skip;
+    if (key == 15) return g_hyb;
     return CKKS_E_BADARG;
 }
 
@@ -716,6 +736,7 @@ int ckks_set_option(int key, int value) {
     if (key == 12) { g_fuse_rescale = value; return 0; }
     if (key == 13) { g_fuse_tensor = value; return 0; }
     if (key == 14) { g_own_skip = value; return 0; }
+    if (key == 15) { g_hyb = value; return 0; }
     return CKKS_E_BADARG;
 }
 
@@ -896,7 +917,9 @@ int ckks_ntt_fast(int64_t* a, int64_t as, int rows, int period, int logN, const 
             rc = launch_fast_col(true, Fs, g, ss);
             if (rc) return rc;
             Fs.scal = nullptr;
+            g_in_row_slabs = true;
             rc = launch_fast_fwd_block_any(Fs, g, ss, logN);
+            g_in_row_slabs = false;
             if (rc) return rc;
         }
         return pipes_join(pipes, st, npipes);
@@ -1049,7 +1072,7 @@ int ckks_exec_tensor_stage(const ckks_level_t* lv, const int64_t* a0, const int6
         RC(launch_status());
         F.scal = nullptr;
         F.prefetch = g_prefetch;
-        fused_tensor = g_fuse_tensor && lv->sExitT && lv->sExitT_sh && g_warp == 1;
+        fused_tensor = g_fuse_tensor && lv->sExitT && lv->sExitT_sh && (g_warp == 1 || g_warp == 3);
         F.out_raw = fused_tensor ? 1 : 0;   // scale-prime rows stay raw doubles for the fused tensor product
         RC(launch_fast_fwd_block_any(F, grid, S(stream), lv->logN));
     } else {

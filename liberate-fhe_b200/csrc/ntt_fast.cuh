@@ -461,6 +461,10 @@ constexpr int FAST_SMEM_BYTES = SMEM_BYTES + FAST_TW_SLOTS * 8 + 16;
 #define FAST_COL_CTAS 4
 #endif
 constexpr int COL_TW_SLOTS = 256;
+// "hybrid" block passes (B >= 7): only the twiddles that threads share (the first four stages of the pass) are staged;
+// the later stages' twiddles are used by exactly one thread each and are read from L2 directly -- 41 KB per CTA, 4 CTAs/SM
+constexpr int HYB_TW_SLOTS = 512;
+constexpr int HYB_SMEM_BYTES = SMEM_BYTES + HYB_TW_SLOTS * 8 + 16;
 constexpr int COL_SMEM_BYTES = SMEM_BYTES + COL_TW_SLOTS * 8 + 16;
 
 template <class TW>
@@ -493,6 +497,22 @@ __device__ __forceinline__ void stage_block_twiddles(const double* __restrict__ 
         const int unit_log = 12 - B;
         mbar_expect_tx(bar, (unsigned)(((1u << 12) - (1u << unit_log)) * 8u));
         for (int j = 0; j < B; ++j) {
+            const unsigned cnt = 1u << (j + unit_log);
+            tma_bulk_g2s(tws + (((1u << j) - 1u) << unit_log), W + (1u << (8 + j)) + (size_t)chunk * cnt, cnt * 8u, bar);
+        }
+    }
+}
+// the first `nst` stages only (the shared ones; the unshared twiddles of the later stages then come straight from L2)
+__device__ __forceinline__ void stage_block_twiddles_first(const double* __restrict__ W, double* tws, uint64_t* bar, int B,
+                                                           unsigned chunk, int nst) {
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int unit_log = 12 - B;
+        mbar_expect_tx(bar, (unsigned)((((1u << nst) - 1u) << unit_log) * 8u));
+        for (int j = 0; j < nst; ++j) {
             const unsigned cnt = 1u << (j + unit_log);
             tma_bulk_g2s(tws + (((1u << j) - 1u) << unit_log), W + (1u << (8 + j)) + (size_t)chunk * cnt, cnt * 8u, bar);
         }
@@ -975,19 +995,23 @@ __device__ __forceinline__ void fast_fwd_block_body(const FastArgs& F, int64_t* 
 // exchange buffer and needs __syncwarp() only -- no CTA barrier anywhere, so the 8 warps of a CTA drift apart and keep
 // the FP64 pipe fed while others wait on loads.  After the last round a thread holds 16 contiguous coefficients,
 // which leave as four 256-bit stores (no staging pass through shared memory).
-template <class A, int B, bool STAGED>
+template <class A, int B, bool STAGED, bool HYB = false>
 __device__ __forceinline__ void fast_fwd_block_body_w(const FastArgs& F, int64_t* sm, int limb, long long drow) {
     using T = typename A::T;
     using TW = typename A::TW;
     const int tau = threadIdx.x;
     const unsigned chunk = grid_chunk(F);
     constexpr int logN = B + 8;
+    constexpr bool S2 = STAGED && !HYB;   // rounds after the first take their twiddles from shared memory
     const typename A::C c = make_const<A>((uint64_t)F.q[limb]);
     int64_t* __restrict__ g = F.a + drow * F.a_stride + (long long)chunk * TILE;
     const TW* __restrict__ W = tw_row<A>(F, limb);
     TW* tws = reinterpret_cast<TW*>(sm + SMEM_SLOTS);
-    uint64_t* bar = reinterpret_cast<uint64_t*>(sm + SMEM_SLOTS + FAST_TW_SLOTS);
-    if constexpr (STAGED) stage_block_twiddles(reinterpret_cast<const double*>(W), reinterpret_cast<double*>(tws), bar, B, chunk);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(sm + SMEM_SLOTS + (HYB ? HYB_TW_SLOTS : FAST_TW_SLOTS));
+    if constexpr (STAGED && HYB)
+        stage_block_twiddles_first(reinterpret_cast<const double*>(W), reinterpret_cast<double*>(tws), bar, B, chunk, 4);
+    else if constexpr (STAGED)
+        stage_block_twiddles(reinterpret_cast<const double*>(W), reinterpret_cast<double*>(tws), bar, B, chunk);
     if (tau == 32) {
         unsigned ca = 0;
         const long long ra = F.prefetch ? fast_row_ahead(F, F.prefetch, ca) : -1;
@@ -1011,7 +1035,7 @@ __device__ __forceinline__ void fast_fwd_block_body_w(const FastArgs& F, int64_t
         smx_store(sm, e, tau, P1);
         __syncwarp();
         smx_load(sm, e, tau, P2);
-        if constexpr (STAGED)
+        if constexpr (S2)
             fast_fwd_round<A, 0>(e, TwSharedBlock<TW>{tws, 12 - B, 4, (unsigned)(tau >> P2)}, c);
         else
             fast_fwd_round<A, 0>(e, TwGlobal<TW>{W, logN - 4 - P2, (chunk << (8 - P2)) | (unsigned)(tau >> P2)}, c);
@@ -1020,7 +1044,7 @@ __device__ __forceinline__ void fast_fwd_block_body_w(const FastArgs& F, int64_t
             smx_store(sm, e, tau, P2);
             __syncwarp();
             smx_load(sm, e, tau, 0);
-            if constexpr (STAGED)
+            if constexpr (S2)
                 fast_fwd_round<A, 3>(e, TwSharedBlock<TW>{tws, 12 - B, B - 4, (unsigned)tau}, c);
             else
                 fast_fwd_round<A, 3>(e, TwGlobal<TW>{W, logN - 4, (chunk << 8) | (unsigned)tau}, c);
@@ -1029,7 +1053,7 @@ __device__ __forceinline__ void fast_fwd_block_body_w(const FastArgs& F, int64_t
         smx_store(sm, e, tau, P1);
         __syncwarp();
         smx_load(sm, e, tau, 0);
-        if constexpr (STAGED)
+        if constexpr (S2)
             fast_fwd_round<A, 8 - B>(e, TwSharedBlock<TW>{tws, 12 - B, B - 4, (unsigned)tau}, c);
         else
             fast_fwd_round<A, 8 - B>(e, TwGlobal<TW>{W, logN - 4, (chunk << 8) | (unsigned)tau}, c);
@@ -1054,6 +1078,18 @@ __global__ void __launch_bounds__(NTT_THREADS, FAST_CTAS_PER_SM) fast_fwd_blockp
         fast_fwd_block_body_w<ArithF64, B, true>(F, sm, limb, rid.data_row);
     else
         fast_fwd_block_body_w<ArithU64, B, false>(F, sm, limb, rid.data_row);
+}
+
+template <int B>
+__global__ void __launch_bounds__(NTT_THREADS, 4) fast_fwd_blockpass_h(const FastArgs F) {
+    extern __shared__ __align__(16) int64_t sm[];
+    if (fast_skip_own(F)) return;
+    const RowId rid = fast_row(F);
+    const int limb = rid.limb;
+    if (fast_use_f64(F, rid))
+        fast_fwd_block_body_w<ArithF64, B, true, true>(F, sm, limb, rid.data_row);
+    else
+        fast_fwd_block_body_w<ArithU64, B, false, true>(F, sm, limb, rid.data_row);
 }
 
 template <int B>
@@ -1616,7 +1652,7 @@ __device__ __forceinline__ void tensor_load<ArithU64>(const FastArgs& F, const T
 // ---- inverse pass B', WARP-INDEPENDENT form (see fast_fwd_block_body_w) ------------------------------------------------
 // A thread starts from its 16 contiguous coefficients (four 256-bit loads), exchanges stay inside the warp; for
 // B == 9 the last level (distance 256) is taken as the top stage of field [8:5], which keeps it warp-private too.
-template <class A, int B, bool STAGED, bool TENS>
+template <class A, int B, bool STAGED, bool TENS, bool HYB = false>
 __device__ __forceinline__ void fast_inv_block_body_w(const FastArgs& F, const TensorIn& Tn, int64_t* sm, int limb, long long drow) {
     using T = typename A::T;
     using TW = typename A::TW;
@@ -1627,8 +1663,12 @@ __device__ __forceinline__ void fast_inv_block_body_w(const FastArgs& F, const T
     int64_t* __restrict__ g = F.a + drow * F.a_stride + (long long)chunk * TILE;
     const TW* __restrict__ W = tw_row<A>(F, limb);
     TW* tws = reinterpret_cast<TW*>(sm + SMEM_SLOTS);
-    uint64_t* bar = reinterpret_cast<uint64_t*>(sm + SMEM_SLOTS + FAST_TW_SLOTS);
-    if constexpr (STAGED) stage_block_twiddles(reinterpret_cast<const double*>(W), reinterpret_cast<double*>(tws), bar, B, chunk);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(sm + SMEM_SLOTS + (HYB ? HYB_TW_SLOTS : FAST_TW_SLOTS));
+    constexpr bool S1 = STAGED && !HYB;   // the first round's twiddles (one thread each) come from shared memory
+    if constexpr (STAGED && HYB)
+        stage_block_twiddles_first(reinterpret_cast<const double*>(W), reinterpret_cast<double*>(tws), bar, B, chunk, B - 4);
+    else if constexpr (STAGED)
+        stage_block_twiddles(reinterpret_cast<const double*>(W), reinterpret_cast<double*>(tws), bar, B, chunk);
     if (tau == 32) {
         unsigned ca = 0;
         const long long ra = F.prefetch ? fast_row_ahead(F, F.prefetch, ca) : -1;
@@ -1645,11 +1685,12 @@ __device__ __forceinline__ void fast_inv_block_body_w(const FastArgs& F, const T
 #pragma unroll
         for (int k = 0; k < 16; ++k) e[k] = A::load_in(r[k], F.in_raw);
     }
-    if constexpr (STAGED) {
+    if constexpr (S1) {
         mbar_wait(bar, 0);
         fast_inv_round<A, 4>(e, TwSharedBlock<TW>{tws, 12 - B, B - 4, (unsigned)tau}, c);
     } else {
         fast_inv_round<A, 4>(e, TwGlobal<TW>{W, logN - 4, (chunk << 8) | (unsigned)tau}, c);
+        if constexpr (STAGED) mbar_wait(bar, 0);   // hybrid: the staged (shared) stages are needed from the next round on
     }
     if constexpr (B == 4) {
         int64_t r[16];
@@ -1704,6 +1745,18 @@ __global__ void __launch_bounds__(NTT_THREADS, FAST_CTAS_PER_SM) fast_inv_blockp
         fast_inv_block_body_w<ArithF64, B, true, false>(F, none, sm, limb, rid.data_row);
     else
         fast_inv_block_body_w<ArithU64, B, false, false>(F, none, sm, limb, rid.data_row);
+}
+
+template <int B>
+__global__ void __launch_bounds__(NTT_THREADS, 4) fast_inv_blockpass_h(const FastArgs F) {
+    extern __shared__ __align__(16) int64_t sm[];
+    const RowId rid = fast_row(F);
+    const int limb = rid.limb;
+    const TensorIn none{};
+    if (fast_use_f64(F, rid))
+        fast_inv_block_body_w<ArithF64, B, true, false, true>(F, none, sm, limb, rid.data_row);
+    else
+        fast_inv_block_body_w<ArithU64, B, false, false, true>(F, none, sm, limb, rid.data_row);
 }
 
 // the tensor stage's inverse block pass: tensor product fused into the load (rows = 3 x L, period L)

@@ -222,7 +222,8 @@ def test_fused_keyswitch_pieces_bit_exact(logN, alpha, K):
 
 # kernel variants of the fast transforms selected by ckks_set_option (key, value); every one must give the same bits
 FAST_VARIANTS = {"default": [], "classic": [(3, 0), (4, 0)], "warp": [(3, 1), (4, 0)], "pp": [(3, 2), (4, 1)],
-                 "pp-3ctas": [(3, 2), (4, 1), (7, 3)], "swapped-grid": [(8, 1)], "warp+swapped": [(3, 1), (8, 1)]}   # 3 persistent CTAs in total: each walks many tiles and limbs
+                 "pp-3ctas": [(3, 2), (4, 1), (7, 3)], "swapped-grid": [(8, 1)], "warp+swapped": [(3, 1), (8, 1)],
+                 "hybrid-twiddles": [(3, 3)], "no-hybrid": [(15, 0)], "hybrid-everywhere": [(15, 7)]}   # 3 persistent CTAs in total: each walks many tiles and limbs
 
 
 @pytest.mark.parametrize("logN", [12, 13, 14, 15, 16, 17])
