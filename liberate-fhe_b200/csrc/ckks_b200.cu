@@ -445,6 +445,7 @@ static int launch_inv_block(const NttArgs& A, dim3 grid, cudaStream_t st) {
 
 int g_persist = 0;
 int g_prefetch = PREFETCH_ROWS_AHEAD;   // ckks_set_option(2, rows_ahead); 0 disables the L2 prefetch   // 1: persistent TMA-pipelined block pass (ckks_set_option(1, v))
+int g_split_tail = 1;   // ckks_set_option(16, v): inverse transform + ModDown of the two output polynomials on two streams
 int g_hyb = 3;    // ckks_set_option(15, mask): hybrid-twiddle block passes (4 CTAs/SM) -- bit 0 forward, bit 1 inverse,
                   // bit 2 also inside the row-slab pipeline of ckks_ntt_fast / ckks_intt_fast
 bool g_in_row_slabs = false;
@@ -718,6 +719,7 @@ int ckks_get_option(int key) {
     if (key == 13) return g_fuse_tensor;
     if (key == 14) return g_own_skip;
     if (key == 15) return g_hyb;
+    if (key == 16) return g_split_tail;
     return CKKS_E_BADARG;
 }
 
@@ -737,6 +739,7 @@ int ckks_set_option(int key, int value) {
     if (key == 13) { g_fuse_tensor = value; return 0; }
     if (key == 14) { g_own_skip = value; return 0; }
     if (key == 15) { g_hyb = value; return 0; }
+    if (key == 16) { g_split_tail = value; return 0; }
     return CKKS_E_BADARG;
 }
 
@@ -1170,32 +1173,41 @@ int ckks_exec_keyswitch_stage(const ckks_level_t* lv, const int64_t* const* digi
         RC(ckks_ksk_inner(ext, N, P, k0_ptrs, k1_ptrs, ksk_stride, acc, acc + (long long)E * N, N, E, N, lv->_2q, lv->ql,
                           lv->qh, lv->kl, lv->kh, stream));
     }
-    RC(intt_fast_impl(acc, N, 2 * E, E, lv->logN, lv->twi_u64, lv->twi_f64, lv->q, lv->sExit, (const uint64_t*)lv->sExit_sh, 0, 0,
-                      stream, (lv->Hm && lv->Rinv) ? 1 : 0));
+    // The two output polynomials are independent from here on: inverse transform + ModDown of each half run on their
+    // own internal stream, so the small latency-bound ModDown kernels of one half overlap the transform of the other.
     int64_t* outs[2] = {out0, out1};
     const int64_t* adds[2] = {add0, add1};
     const int Ls = lv->Pinv ? lv->L_small : 0;   // leading ordinary rows handled by the FP64 kernel
+    const int in_raw = (lv->Hm && lv->Rinv) ? 1 : 0;
+    SidePipes* tail = (g_pipes > 1 && g_split_tail) ? side_pipes() : nullptr;
+    if (tail) RC(pipes_fork(tail, S(stream), 2));
     for (int h = 0; h < 2; ++h) {
+        cudaStream_t st = tail ? tail->s[h] : S(stream);
         int64_t* dh = acc + (long long)h * E * N;
-        k_moddown_special<<<col_grid(N), EW_THREADS, 0, S(stream)>>>(dh, N, L, K, N, lv->PiR, eff, m);
+        int64_t* effh = eff + (long long)h * K * N;
+        if (tail || h == 0)   // (one stream: both halves in one batched transform, as before)
+            RC(intt_fast_impl(dh, N, tail ? E : 2 * E, E, lv->logN, lv->twi_u64, lv->twi_f64, lv->q, lv->sExit,
+                              (const uint64_t*)lv->sExit_sh, 0, 0, st, in_raw));
+        k_moddown_special<<<col_grid(N), EW_THREADS, 0, st>>>(dh, N, L, K, N, lv->PiR, effh, m);
         RC(launch_status());
         if (Ls > 0) {
-            ModDownArgs M{dh, eff, adds[h], add_stride, outs[h], out_stride, lv->Pinv, lv->C31, lv->q, L, K, E, N};
-            k_moddown_fast<<<dim3((N / 2 + 255) / 256, Ls), 256, 0, S(stream)>>>(M);
+            ModDownArgs M{dh, effh, adds[h], add_stride, outs[h], out_stride, lv->Pinv, lv->C31, lv->q, L, K, E, N};
+            k_moddown_fast<<<dim3((N / 2 + 255) / 256, Ls), 256, 0, st>>>(M);
             RC(launch_status());
         }
         if (Ls < L) {
-            k_moddown_ordinary<<<ew_grid(N, L - Ls), EW_THREADS, 0, S(stream)>>>(dh, N, L, K, N, lv->Rs, lv->PiR, eff, adds[h],
-                                                                                add_stride, outs[h], out_stride, Ls, m);
+            k_moddown_ordinary<<<ew_grid(N, L - Ls), EW_THREADS, 0, st>>>(dh, N, L, K, N, lv->Rs, lv->PiR, effh, adds[h],
+                                                                        add_stride, outs[h], out_stride, Ls, m);
             RC(launch_status());
         }
     }
+    if (tail) RC(pipes_join(tail, S(stream), 2));
     return 0;
 }
 
 int64_t ckks_exec_keyswitch_ws_elems(int L, int K, int nparts, int N) {
     const long long E = L + K;
-    return ((long long)nparts * E + 2 * E + K) * N;
+    return ((long long)nparts * E + 2 * E + 2 * K) * N;   // extended block, two accumulators, ModDown scratch of both halves
 }
 
 int ckks_automorphism(const int64_t* in, int64_t is, int64_t* out, int64_t os, int C, int N, int64_t g, int canon,

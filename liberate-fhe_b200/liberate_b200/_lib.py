@@ -105,7 +105,7 @@ class _Counted:
 
 
 lib = _Counted(_load())
-OPTION_KEYS = (1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15)
+OPTION_KEYS = (1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16)
 _OPTION_DEFAULTS = {k: lib.ckks_get_option(k) for k in OPTION_KEYS}
 
 
