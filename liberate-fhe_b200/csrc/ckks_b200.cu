@@ -1118,8 +1118,10 @@ int ckks_exec_keyswitch_stage(const ckks_level_t* lv, const int64_t* const* digi
     int64_t* eff = acc + 2ll * E * N;                   // [K][N]
     const MontPack m{lv->_2q, lv->ql, lv->qh, lv->kl, lv->kh};
     if (lv->Hm && lv->Rinv) {
-        // Slab pipeline over target limbs [t0, t1): extend -> column pass -> block pass -> inner product, slab sized so
-        // that the extended block stays L2-resident between the four kernels (only the evaluation key streams from HBM).
+        // Slab pipeline over target limbs [t0, t1): extend -> column pass -> block pass -> inner product per slab, slabs
+        // alternating between two internal streams so that the tail of one kernel overlaps the next slab's kernels.
+        // Measured (profiles/r01_lab_notes.txt): L2-sized slabs (32-64 MB) lose more to small grids than they gain from
+        // L2 residency of the extended block; two 100 MB slabs on two streams are the best setting at gold.
         ExtArgs X{};
         X.digit_ptrs = digit_ptrs;
         X.d_stride = digit_stride;
