@@ -180,3 +180,47 @@ def model_intt(a, P, exit_mode):
         L = Limb(P, i)
         inv_blockpass(a[i], logN, P.ipsi[i], L)
         inv_colpass(a[i], logN, P.ipsi[i], L, P.Ninv[i], exit_mode, P, i)
+
+
+# ---- warp-independent block passes (ntt_fast.cuh: fast_*_block_body_w) ------------------------------------------------
+def block_round_fields(B, inverse):
+    """low bits p of the radix-16 fields the warp-independent block passes visit, in order"""
+    if not inverse:
+        if B >= 8:
+            return [B - 4, B - 8] + ([0] if B == 9 else [])
+        return [B - 4] + ([0] if B > 4 else [])
+    if B == 4:
+        return [0]
+    return [0, 4] + ([5] if B == 9 else [])        # B == 9: the last level is the TOP stage of field [8:5]
+
+
+def warp_of_elements(p):
+    """[256,16] warp-region index (512 contiguous coefficients) of every element thread tau touches in field p"""
+    return field_idx(p) // 512
+
+
+def inv_blockpass_w(row, logN, W, L):
+    """mirrors fast_inv_block_body_w: as inv_blockpass, but for B == 9 the last level (distance 256) is taken as the top
+    stage (pairs k, k+8) of field [8:5] with ONE twiddle per 512-point sub-block, which keeps the exchange inside a warp"""
+    B = logN - 8
+    tau = np.arange(T)
+    for chunk in range((1 << logN) // TILE):
+        g = row[chunk * TILE:(chunk + 1) * TILE]
+        sm = g.copy()
+        z = field_idx(0)
+        e = sm[z].copy()
+        inv_round(e, W, logN - 4, ((chunk << 8) | tau).astype(np.int64), L)
+        sm[z] = e
+        if B > 4:
+            z = field_idx(4)
+            e = sm[z].copy()
+            inv_round(e, W, logN - 8, ((chunk << 4) | (tau >> 4)).astype(np.int64), L, nst=4 if B >= 8 else B - 4)
+            sm[z] = e
+            if B == 9:
+                z = field_idx(5)
+                e = sm[z].copy()
+                w = W[(1 << (logN - 9)) + ((chunk << 3) | (tau >> 5))]
+                for k in range(8):
+                    e[..., k], e[..., k + 8] = gs(e[..., k].copy(), e[..., k + 8].copy(), w, L)
+                sm[z] = e
+        g[:] = sm

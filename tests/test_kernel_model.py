@@ -29,3 +29,32 @@ def test_two_pass_mapping_matches_oracle(logN):
         O.C.intt(r, P.ipsi, P.Ninv, P._2q, *P.mont, exit_mode=mode)
         K.model_intt(mm, P, mode)
         assert (mm == r).all()
+
+
+@pytest.mark.parametrize("B", [4, 5, 6, 7, 8, 9])
+@pytest.mark.parametrize("inverse", [False, True])
+def test_warp_independent_block_passes_stay_inside_a_warp(B, inverse):
+    """the invariant behind __syncwarp() in fast_*_block_body_w: in every round a thread only touches coefficients of
+    the 512-coefficient slice its own warp owns (thread tau -> warp tau // 32)"""
+    own = (np.arange(K.T) // 32)[:, None]
+    for p in K.block_round_fields(B, inverse):
+        assert (K.warp_of_elements(p) == own).all(), (B, inverse, p)
+
+
+def test_inverse_last_level_as_top_stage_of_field_8_5_matches_oracle():
+    """logN = 17: the warp-private form of the last inverse level (ntt_fast.cuh, B == 9) equals the oracle"""
+    logN = 17
+    q = primes_for(logN, 1, 0)
+    P = O.Params(q, logN)
+    rng = np.random.default_rng(5)
+    a = np.stack([rng.integers(0, 2 * qi, 1 << logN, dtype=np.int64) for qi in q])
+    ref = a.copy()
+    O.C.ntt(ref, P.psi, P._2q, *P.mont)
+    want = ref.copy()
+    O.C.intt(want, P.ipsi, P.Ninv, P._2q, *P.mont, exit_mode=0)
+    got = ref.copy()
+    for i in range(got.shape[0]):
+        L = K.Limb(P, i)
+        K.inv_blockpass_w(got[i], logN, P.ipsi[i], L)
+        K.inv_colpass(got[i], logN, P.ipsi[i], L, P.Ninv[i], 0, P, i)
+    assert (got == want).all()
