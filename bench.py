@@ -452,8 +452,8 @@ def run_ours(args):
     dsc = plan.desc
 
     def ntt_call():
-        check(lib.ckks_ntt_fast(buf.data_ptr(), N, rows, E, logN, dsc.twf_u64, dsc.twf_f64, dsc.q, None, None, 0, st),
-              "ntt_fast")
+        check(lib.ckks_ntt_fast(buf.data_ptr(), N, rows, E, logN, dsc.twf_u64, dsc.twf_f64, dsc.twpf_u64, dsc.twpf_f64,
+                                dsc.q, dsc.qinv, None, None, 0, st), "ntt_fast")
 
     if args.profile_roofline:        # ncu --profile-from-start off: exactly two launches of the measured kernel pair
         ntt_call()

@@ -29,14 +29,15 @@ extern "C" {
 #define CKKS_E_LOGN (-2)       /* logN outside [12, 17] */
 #define CKKS_E_ALIGN (-3)      /* pointer or stride not 16-byte aligned */
 
-int ckks_abi_version(void);
-/* tuning knobs: key 1 = persistent TMA-pipelined forward block pass (default 0: measured slower than the one-tile-per-CTA kernel) */
-int ckks_set_option(int key, int value);   /* key 2 = L2 prefetch distance in rows (default 28, 0 = off) */
-/* key 3 = block passes: 0 one tile per CTA, 1 warp-independent + 256-bit accesses, 2 persistent software-pipelined;
- * key 4 = 1: persistent software-pipelined column passes; key 5 = measurement only, skip column (1) / block (2) pass;
- * key 6 = persistent CTAs per SM (1..4); key 7 = cap on the persistent grid (0 = none)  -- keys 3/4 need 32-byte aligned rows;
- * key 8 = (row, chunk) grid order; key 9 = MB of extended rows per key-switch slab; key 10 = internal side streams (1..4);
- * key 11 = MB per row slab of a big batched transform; key 12 / 13 = rescale / tensor product fused into the tensor stage */
+int ckks_abi_version(void);                 /* 3; the Python loader refuses any other value */
+/* tuning knobs (defaults are the measured best):
+ *   2 = L2 prefetch distance in rows (28, 0 = off);  9 = MB of extended rows per key-switch slab (100);
+ *   10 = internal side streams (2; 1..4);  11 = MB per row slab of a big batched transform (24);
+ *   12 = rescale fused into the tensor stage's column pass (1);  16 = the two ModDown tails on two streams (1);
+ *   17 = block passes read the last-group twiddles from the packed tables (1);
+ *   18 = the executor keeps NTT-domain data in warp-interleaved order (1; needs permuted key copies, ckks_perm_rows).
+ * Unknown keys return CKKS_E_BADARG.  The library is single-threaded per device (one host thread per device issues calls). */
+int ckks_set_option(int key, int value);
 int ckks_get_option(int key);               /* current value of a knob (negative: unknown key) */
 int64_t ckks_launch_count(void);            /* kernels launched by the library since it was loaded */
 
@@ -95,12 +96,22 @@ int ckks_compact_twiddles(const int64_t* painted, int64_t* compact, int C, int l
  * Inputs: forward [0, 2q) (any |x| < 2^51 for primes < 2^42); inverse [0, 2q).  scal/scal_sh: per-limb plain
  * multiplier s and floor(s 2^64/q) (forward: optional, applied on load; inverse: required, e.g. N^-1 R^-1). */
 int ckks_fast_tables(const int64_t* plain, const int64_t* q, void* tw_u64, double* tw_f64, int C, int N, void* stream);
+/* PACKED copies of the last four stages of the fast tables (either table may be NULL): one thread of a block pass owns
+ * 15 twiddles there; per 512-coefficient warp tile they are stored lane-interleaved so that the loads of a warp are
+ * contiguous 256/512-byte runs (ntt_fast.cuh: TwPacked).  Same sizes as the plain tables: [C][N] x 16 B and [C][N] x 8 B. */
+int ckks_fast_pack(const void* tw_u64, const double* tw_f64, void* twp_u64, double* twp_f64, int C, int logN, void* stream);
+/* twp_u64 / twp_f64: the packed tables or NULL; qinv: [period] doubles 1/q or NULL (then computed per CTA) */
 int ckks_ntt_fast(int64_t* a, int64_t a_stride, int rows, int period, int logN, const void* tw_u64,
-                  const double* tw_f64, const int64_t* q, const int64_t* scal, const uint64_t* scal_sh,
-                  int force_int, void* stream);
+                  const double* tw_f64, const void* twp_u64, const double* twp_f64, const int64_t* q, const double* qinv,
+                  const int64_t* scal, const uint64_t* scal_sh, int force_int, void* stream);
 int ckks_intt_fast(int64_t* a, int64_t a_stride, int rows, int period, int logN, const void* tw_u64,
-                   const double* tw_f64, const int64_t* q, const int64_t* scal, const uint64_t* scal_sh,
-                   int centred, int force_int, void* stream);
+                   const double* tw_f64, const void* twp_u64, const double* twp_f64, const int64_t* q, const double* qinv,
+                   const int64_t* scal, const uint64_t* scal_sh, int centred, int force_int, void* stream);
+/* NTT-domain rows between natural order and the executor's warp-interleaved order (inverse != 0: back to natural):
+ * inside every 512-coefficient tile, coefficient 16 t + k <-> position ((k >> 1) * 32 + t) * 2 + (k & 1).  Out of place.
+ * Used once per evaluation / rotation key (the engine caches the permuted copy). */
+int ckks_perm_rows(const int64_t* in, int64_t in_stride, int64_t* out, int64_t out_stride, int rows, int N, int inverse,
+                   void* stream);
 
 /* ---- level 2: fused hot-path operators (additions; engine.py line numbers = src/liberate/fhe/ckks_engine.py) */
 
@@ -186,36 +197,33 @@ typedef struct {
     const double* Rinv;                                       /* [E] R^-1 mod q_t (FP64 inner product), or NULL  */
     const double* Pinv;                                       /* [K][E] P_i^-1 mod q_t (FP64 ModDown), or NULL   */
     int32_t L_small, amax;                                    /* leading ordinary rows with q < 2^42; max alpha  */
-    /* optional (NULL = separate tensor-product kernel): exit scalars of the inverse transform that has the tensor
-     * product fused into its load: N^-1 R^-2 for rows with q < 2^42 (FP64 product), N^-1 R^-1 for the others */
-    const int64_t *sExitT, *sExitT_sh;
-    /* optional (NULL = transform every row): [nparts] first row, among this device's live rows, of the limbs each
-     * partition is made of, or -1 when the partition lives on another device.  With d2hat (below) the key switch does
-     * not extend / transform those rows: NTT(extension of a partition to its own limbs) is the tensor product's d2. */
-    const int32_t* part_row0;
+    const void* twpf_u64; const double* twpf_f64;             /* packed forward tables (ckks_fast_pack) or NULL  */
+    const void* twpi_u64; const double* twpi_f64;             /* packed inverse tables or NULL                   */
+    const double* qinv;                                       /* [E] 1/q_t as doubles, or NULL                   */
 } ckks_level_t;
 
 /* rescale x4 -> batched enter+NTT -> tensor product -> batched iNTT+exit -> Garner digits of d2
  * (cc_mult + the first half of relinearize, engine.py:1072-1129, 654-705).  a0..b1: the rows that survive the rescale
  * ([L][N], in_stride); r0*: the dropped limb of each polynomial ([N], on this device).  x: workspace [4][L][N];
- * d: out [3][L][N] plain canonical d0,d1,d2; digits: out [L][N] (rows of the local partitions);
- * d2hat: optional out [L][N], the NTT-domain d2 (lazy Montgomery form) for ckks_exec_keyswitch_stage. */
+ * d: out [3][L][N] plain canonical d0,d1,d2; digits: out [L][N] (rows of the local partitions). */
 int ckks_exec_tensor_stage(const ckks_level_t* lv, const int64_t* a0, const int64_t* a1, const int64_t* b0,
                            const int64_t* b1, int64_t in_stride, const int64_t* r0a0, const int64_t* r0a1,
                            const int64_t* r0b0, const int64_t* r0b1, int64_t* x, int64_t* d, int64_t* digits,
-                           int64_t* d2hat, void* stream);
-/* Garner digits of the local partitions of a [L][N] polynomial (pre_extend for every partition, one launch) */
+                           void* stream);
+/* Garner digits of the local partitions of a [L][N] polynomial (pre_extend for every partition, one launch).
+ * CKKS_E_BADARG when a partition has more than 8 limbs (lv->amax). */
 int ckks_exec_digits(const ckks_level_t* lv, const int64_t* a, int64_t a_stride, int64_t* digits, int64_t d_stride,
                      void* stream);
 /* extend (all partitions) -> batched NTT -> evk inner product -> batched iNTT+exit -> ModDown (+add, reduce)
  * (create_switcher engine.py:812-904 + the relinearize / switch_key tails).  digit_ptrs: device [nparts] pointers to
  * each partition's [alpha][N] digit block (rows digit_stride apart) -- local or received from a peer;
- * ws: ckks_exec_keyswitch_ws_elems(...) int64 elements.  d2hat: NULL, or the tensor stage's NTT-domain polynomial whose
- * digits these are (relinearize only): rows a partition owns are then taken from it instead of being re-transformed. */
+ * k0_ptrs / k1_ptrs: device [nparts] row-0 pointers of the key halves; keys_permuted != 0: they point to copies made
+ * with ckks_perm_rows (the stage then keeps its NTT-domain data in the same order);
+ * ws: ckks_exec_keyswitch_ws_elems(...) int64 elements. */
 int ckks_exec_keyswitch_stage(const ckks_level_t* lv, const int64_t* const* digit_ptrs, int64_t digit_stride,
                               const int64_t* const* k0_ptrs, const int64_t* const* k1_ptrs, int64_t ksk_stride,
-                              const int64_t* add0, const int64_t* add1, int64_t add_stride, int64_t* out0,
-                              int64_t* out1, int64_t out_stride, int64_t* ws, const int64_t* d2hat, void* stream);
+                              int keys_permuted, const int64_t* add0, const int64_t* add1, int64_t add_stride,
+                              int64_t* out0, int64_t* out1, int64_t out_stride, int64_t* ws, void* stream);
 int64_t ckks_exec_keyswitch_ws_elems(int L, int K, int nparts, int N);
 
 /* ---- sampler: ChaCha20 counter mode (replaces src/liberate/csprng/: chacha20 / randint / discrete_gaussian / randround

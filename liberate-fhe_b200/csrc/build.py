@@ -21,13 +21,19 @@ def stale():
     return any((HERE / f).stat().st_mtime > t for f in SOURCES + HEADERS)
 
 
-def build(force=False, verbose=False):
-    if not force and not stale():
+def build(force=False, verbose=False, lab=False):
+    """lab=True: libckks_b200_lab.so with -DCKKS_LAB (measurement knob 5 = skip one pass of a transform; never the product
+    library -- load it with CKKS_B200_LIB=... from scripts/ntt_lab.py)"""
+    out = HERE / "libckks_b200_lab.so" if lab else LIB
+    if not force and not lab and not stale():
         return LIB
-    cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", str(LIB)] + [str(HERE / s) for s in SOURCES]
+    tmp = out.with_suffix(f".tmp{__import__('os').getpid()}.so")     # atomic replace: other ranks may be loading the old file
+    cmd = (["nvcc"] + NVCC_FLAGS + (["-DCKKS_LAB"] if lab else []) + (["-Xptxas", "-v"] if verbose else []) +
+           ["-o", str(tmp)] + [str(HERE / s) for s in SOURCES])
     subprocess.check_call(cmd)
-    return LIB
+    tmp.replace(out)
+    return out
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, lab="--lab" in sys.argv))

@@ -11,7 +11,7 @@
 
 using namespace ckks;
 
-#define CKKS_ABI_VERSION 2
+#define CKKS_ABI_VERSION 3
 
 namespace {
 
@@ -158,8 +158,7 @@ __global__ void k_rescale(const int64_t* __restrict__ in, long long is, const in
 
 __global__ void k_tensor(const int64_t* __restrict__ x0, const int64_t* __restrict__ x1, const int64_t* __restrict__ y0,
                          const int64_t* __restrict__ y1, long long is, int64_t* __restrict__ d0,
-                         int64_t* __restrict__ d1, int64_t* __restrict__ d2, long long os, int N, MontPack m,
-                         int64_t* __restrict__ d2hat) {
+                         int64_t* __restrict__ d1, int64_t* __restrict__ d2, long long os, int N, MontPack m) {
     const int i = blockIdx.y;
     const int j = 2 * (blockIdx.x * EW_THREADS + threadIdx.x);
     if (j >= N) return;
@@ -177,7 +176,6 @@ __global__ void k_tensor(const int64_t* __restrict__ x0, const int64_t* __restri
     st2(d0 + oo, r0);
     st2(d1 + oo, r1);
     st2(d2 + oo, r2);
-    if (d2hat) st2(d2hat + (long long)i * N + j, r2);   // NTT-domain d2 kept for the key switch (own-partition rows)
 }
 
 constexpr int MAX_ALPHA = 8;
@@ -443,176 +441,66 @@ static int launch_inv_block(const NttArgs& A, dim3 grid, cudaStream_t st) {
     return launch_status();
 }
 
-int g_persist = 0;
-int g_prefetch = PREFETCH_ROWS_AHEAD;   // ckks_set_option(2, rows_ahead); 0 disables the L2 prefetch   // 1: persistent TMA-pipelined block pass (ckks_set_option(1, v))
-int g_split_tail = 1;   // ckks_set_option(16, v): inverse transform + ModDown of the two output polynomials on two streams
-int g_hyb = 3;    // ckks_set_option(15, mask): hybrid-twiddle block passes (4 CTAs/SM) -- bit 0 forward, bit 1 inverse,
-                  // bit 2 also inside the row-slab pipeline of ckks_ntt_fast / ckks_intt_fast
-bool g_in_row_slabs = false;
-int g_skip = 0;   // ckks_set_option(5, mask): measurement only -- bit 0 skips the column pass, bit 1 the block pass
-int g_warp = 1;   // ckks_set_option(3, v): 0 classic, 1 = warp-independent block passes with 256-bit global accesses (default), 2 = persistent
+// ---- tuning knobs (ckks_set_option) -------------------------------------------------------------------------------
+int g_prefetch = PREFETCH_ROWS_AHEAD;   // 2: L2 prefetch distance in rows (0 = off)
+int g_slab_mb = 100;      // 9: MB of extended rows per key-switch slab (L2 residency vs grid size)
+int g_pipes = 2;          // 10: internal side streams used by the slab pipelines (1 = everything on the caller's stream)
+int g_ntt_slab_mb = 24;   // 11: MB of rows per slab of a big batched transform
+int g_fuse_rescale = 1;   // 12: rescale fused into the tensor stage's column pass
+int g_split_tail = 1;     // 16: inverse transform + ModDown of the two output polynomials on two streams
+int g_packed = 1;         // 17: block passes read the last-group twiddles from the packed tables (when the caller passes them)
+int g_perm = 1;           // 18: the executor keeps NTT-domain data in warp-interleaved order (needs permuted key copies)
+#ifdef CKKS_LAB
+int g_skip = 0;           // 5 (lab builds only): measurement -- bit 0 skips the column pass, bit 1 the block pass
+int g_lab_perm = 0;       // 20 (lab builds only): ckks_ntt_fast / ckks_intt_fast keep the NTT domain warp-interleaved
+#else
+constexpr int g_skip = 0;
+constexpr int g_lab_perm = 0;
+#endif
 inline bool aligned32(const void* p, long long stride) { return (((uintptr_t)p) & 31) == 0 && (stride & 3) == 0; }
-int sm_count() {
-    static int n = 0;
-    if (!n) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    }
-    return n;
-}
 
-// persistent software-pipelined ("pp") kernels: rows must tile into G rows per limb and be 32-byte aligned
-int g_swap = 0;    // ckks_set_option(8, v): 1 = (row, chunk) grid order for the one-tile-per-CTA kernels
-inline dim3 tile_grid(dim3 grid) { return g_swap ? dim3(grid.y, grid.x) : grid; }
-int g_slab_mb = 100; // ckks_set_option(9, v): MB of extended rows per key-switch slab (L2 residency vs grid size)
-int g_colpp = 0;   // ckks_set_option(4, v): 1 = persistent software-pipelined column passes
-int g_pp_ctas = 2; // ckks_set_option(6, v): persistent CTAs per SM
-int g_pp_cap = 0;  // ckks_set_option(7, v): cap on the persistent grid (0 = none; tests use it to make every CTA walk many tiles)
-inline bool pp_ok(const FastArgs& F, dim3 grid) {
-    if (!aligned32(F.a, F.a_stride)) return false;
-    return F.slab_rows ? (grid.y % F.slab_rows == 0) : (grid.y % F.period == 0);
-}
-inline int pp_group(const FastArgs& F, dim3 grid) { return F.slab_rows ? grid.y / F.slab_rows : grid.y / F.period; }
-inline int pp_ctas(long long tiles) {
-    long long slots = (long long)sm_count() * g_pp_ctas;
-    if (g_pp_cap > 0 && g_pp_cap < slots) slots = g_pp_cap;
-    return (int)(tiles < slots ? tiles : slots);
-}
 static int launch_fast_col(bool fwd, const FastArgs& F, dim3 grid, cudaStream_t st) {
-    if (g_colpp && pp_ok(F, grid)) {
-        const int G = pp_group(F, grid);
-        const long long tiles = (long long)grid.x * grid.y;
-        if (fwd) {
-            cudaFuncSetAttribute(fast_colpass_pp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PPC_SMEM_BYTES);
-            fast_colpass_pp<true><<<pp_ctas(tiles), NTT_THREADS, PPC_SMEM_BYTES, st>>>(F, tiles, G);
-        } else {
-            cudaFuncSetAttribute(fast_colpass_pp<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PPC_SMEM_BYTES);
-            fast_colpass_pp<false><<<pp_ctas(tiles), NTT_THREADS, PPC_SMEM_BYTES, st>>>(F, tiles, G);
-        }
-        return launch_status();
-    }
     if (fwd) {
         cudaFuncSetAttribute(fast_fwd_colpass<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, COL_SMEM_BYTES);
-        fast_fwd_colpass<0><<<tile_grid(grid), NTT_THREADS, COL_SMEM_BYTES, st>>>(F);
+        fast_fwd_colpass<0><<<grid, NTT_THREADS, COL_SMEM_BYTES, st>>>(F);
     } else {
         cudaFuncSetAttribute(fast_inv_colpass<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, COL_SMEM_BYTES);
-        fast_inv_colpass<0><<<tile_grid(grid), NTT_THREADS, COL_SMEM_BYTES, st>>>(F);
+        fast_inv_colpass<0><<<grid, NTT_THREADS, COL_SMEM_BYTES, st>>>(F);
     }
-    return launch_status();
-}
-
-template <int B>
-static int launch_fast_fwd_block(const FastArgs& F, dim3 grid, cudaStream_t st) {
-    if (g_persist) {
-        // rows of one launch that share a limb: plain batches rows/period, slab views rows/slab_rows
-        const int rows = grid.y;
-        const int G = F.slab_rows ? rows / F.slab_rows : rows / F.period;
-        const long long tiles = (long long)rows * grid.x;
-        const int ctas = (int)((tiles < (long long)sm_count()) ? tiles : (long long)sm_count());
-        cudaFuncSetAttribute(fast_fwd_blockpass_persist<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, PERSIST_SMEM_BYTES);
-        fast_fwd_blockpass_persist<B><<<ctas, NTT_THREADS, PERSIST_SMEM_BYTES, st>>>(F, tiles, G > 0 ? G : 1);
-        return launch_status();
-    }
-    if (g_warp == 2 && pp_ok(F, grid)) {
-        const int G = pp_group(F, grid);
-        const long long tiles = (long long)grid.x * grid.y;
-        cudaFuncSetAttribute(fast_fwd_blockpass_pp<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, PP_SMEM_BYTES);
-        fast_fwd_blockpass_pp<B><<<pp_ctas(tiles), NTT_THREADS, PP_SMEM_BYTES, st>>>(F, tiles, G);
-        return launch_status();
-    }
-    if constexpr (B >= 7) {
-        if (((g_warp == 1 && (g_hyb & 1) && !(g_in_row_slabs && !(g_hyb & 4))) || g_warp == 3) && aligned32(F.a, F.a_stride)) {
-            cudaFuncSetAttribute(fast_fwd_blockpass_h<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, HYB_SMEM_BYTES);
-            fast_fwd_blockpass_h<B><<<tile_grid(grid), NTT_THREADS, HYB_SMEM_BYTES, st>>>(F);
-            return launch_status();
-        }
-    }
-    if (g_warp && aligned32(F.a, F.a_stride)) {
-        cudaFuncSetAttribute(fast_fwd_blockpass_w<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, FAST_SMEM_BYTES);
-        fast_fwd_blockpass_w<B><<<tile_grid(grid), NTT_THREADS, FAST_SMEM_BYTES, st>>>(F);
-        return launch_status();
-    }
-    cudaFuncSetAttribute(fast_fwd_blockpass<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, FAST_SMEM_BYTES);
-    fast_fwd_blockpass<B><<<tile_grid(grid), NTT_THREADS, FAST_SMEM_BYTES, st>>>(F);
     return launch_status();
 }
 template <int B>
-static int launch_fast_inv_block(const FastArgs& F, dim3 grid, cudaStream_t st) {
-    if (g_warp == 2 && pp_ok(F, grid)) {
-        const int G = pp_group(F, grid);
-        const long long tiles = (long long)grid.x * grid.y;
-        cudaFuncSetAttribute(fast_inv_blockpass_pp<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, PP_SMEM_BYTES);
-        fast_inv_blockpass_pp<B><<<pp_ctas(tiles), NTT_THREADS, PP_SMEM_BYTES, st>>>(F, tiles, G);
-        return launch_status();
+static int launch_fast_block(bool fwd, const FastArgs& F, dim3 grid, cudaStream_t st) {
+    if (!aligned32(F.a, F.a_stride)) return CKKS_E_ALIGN;   // 256-bit accesses: rows must be 32-byte aligned
+    if (fwd) {
+        cudaFuncSetAttribute(fast_fwd_blockpass<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, BLK_SMEM_BYTES);
+        fast_fwd_blockpass<B><<<grid, NTT_THREADS, BLK_SMEM_BYTES, st>>>(F);
+    } else {
+        cudaFuncSetAttribute(fast_inv_blockpass<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, BLK_SMEM_BYTES);
+        fast_inv_blockpass<B><<<grid, NTT_THREADS, BLK_SMEM_BYTES, st>>>(F);
     }
-    if constexpr (B >= 7) {
-        if (((g_warp == 1 && (g_hyb & 2) && !(g_in_row_slabs && !(g_hyb & 4))) || g_warp == 3) && aligned32(F.a, F.a_stride)) {
-            cudaFuncSetAttribute(fast_inv_blockpass_h<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, HYB_SMEM_BYTES);
-            fast_inv_blockpass_h<B><<<tile_grid(grid), NTT_THREADS, HYB_SMEM_BYTES, st>>>(F);
-            return launch_status();
-        }
-    }
-    if (g_warp && aligned32(F.a, F.a_stride)) {
-        cudaFuncSetAttribute(fast_inv_blockpass_w<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, FAST_SMEM_BYTES);
-        fast_inv_blockpass_w<B><<<tile_grid(grid), NTT_THREADS, FAST_SMEM_BYTES, st>>>(F);
-        return launch_status();
-    }
-    cudaFuncSetAttribute(fast_inv_blockpass<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, FAST_SMEM_BYTES);
-    fast_inv_blockpass<B><<<tile_grid(grid), NTT_THREADS, FAST_SMEM_BYTES, st>>>(F);
     return launch_status();
 }
-static int launch_fast_fwd_block_any(const FastArgs& F, dim3 grid, cudaStream_t st, int logN) {
-    switch (logN - 8) {
-        case 4: return launch_fast_fwd_block<4>(F, grid, st);
-        case 5: return launch_fast_fwd_block<5>(F, grid, st);
-        case 6: return launch_fast_fwd_block<6>(F, grid, st);
-        case 7: return launch_fast_fwd_block<7>(F, grid, st);
-        case 8: return launch_fast_fwd_block<8>(F, grid, st);
-        case 9: return launch_fast_fwd_block<9>(F, grid, st);
+static int launch_fast_block_any(bool fwd, FastArgs F, dim3 grid, cudaStream_t st) {
+    if (!g_packed) { F.twp_u64 = nullptr; F.twp_f64 = nullptr; }
+    switch (F.logN - 8) {
+        case 4: return launch_fast_block<4>(fwd, F, grid, st);
+        case 5: return launch_fast_block<5>(fwd, F, grid, st);
+        case 6: return launch_fast_block<6>(fwd, F, grid, st);
+        case 7: return launch_fast_block<7>(fwd, F, grid, st);
+        case 8: return launch_fast_block<8>(fwd, F, grid, st);
+        case 9: return launch_fast_block<9>(fwd, F, grid, st);
     }
     return CKKS_E_LOGN;
 }
-static int launch_fast_inv_block_any(const FastArgs& F, dim3 grid, cudaStream_t st, int logN) {
-    switch (logN - 8) {
-        case 4: return launch_fast_inv_block<4>(F, grid, st);
-        case 5: return launch_fast_inv_block<5>(F, grid, st);
-        case 6: return launch_fast_inv_block<6>(F, grid, st);
-        case 7: return launch_fast_inv_block<7>(F, grid, st);
-        case 8: return launch_fast_inv_block<8>(F, grid, st);
-        case 9: return launch_fast_inv_block<9>(F, grid, st);
-    }
-    return CKKS_E_LOGN;
-}
-template <int B>
-static int launch_inv_block_tensor_b(const FastArgs& F, const TensorIn& Tn, dim3 grid, cudaStream_t st) {
-    cudaFuncSetAttribute(fast_inv_blockpass_tensor<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, FAST_SMEM_BYTES);
-    fast_inv_blockpass_tensor<B><<<tile_grid(grid), NTT_THREADS, FAST_SMEM_BYTES, st>>>(F, Tn);
-    return launch_status();
-}
-static int launch_inv_block_tensor(const FastArgs& F, const TensorIn& Tn, dim3 grid, cudaStream_t st, int logN) {
-    switch (logN - 8) {
-        case 4: return launch_inv_block_tensor_b<4>(F, Tn, grid, st);
-        case 5: return launch_inv_block_tensor_b<5>(F, Tn, grid, st);
-        case 6: return launch_inv_block_tensor_b<6>(F, Tn, grid, st);
-        case 7: return launch_inv_block_tensor_b<7>(F, Tn, grid, st);
-        case 8: return launch_inv_block_tensor_b<8>(F, Tn, grid, st);
-        case 9: return launch_inv_block_tensor_b<9>(F, Tn, grid, st);
-    }
-    return CKKS_E_LOGN;
-}
-int g_own_skip = 0;       // ckks_set_option(14, v): key switch takes every partition's own limbs from the tensor product's NTT-domain d2
-                          // (9 % fewer rows to extend / transform, but measured 732 vs 726 us per gold mult: off)
-int g_fuse_tensor = 0;    // ckks_set_option(13, v): tensor product fused into the tensor stage's inverse block pass (measured: 10 us SLOWER)
-int g_fuse_rescale = 1;   // ckks_set_option(12, v): rescale fused into the tensor stage's column pass
-int g_ntt_slab_mb = 24;   // ckks_set_option(11, v): MB of rows per slab of a big batched transform
 
 // ---- side streams: independent slabs of one call run on up to MAX_PIPES internal streams so that the tail of one
 // kernel overlaps the head of the next slab's kernels (small grids leave SMs idle at wave boundaries otherwise).
 // fork(): the side streams wait for everything already queued on the caller's stream; join(): the caller's stream
-// waits for the side streams.  Streams and events are created once per device and reused.
+// waits for the side streams.  Streams and events are created once per device and reused: the library is
+// SINGLE-THREADED PER DEVICE (one host thread issues the calls for a device; torch's model and the reference's).
+// PipeScope joins on every exit path, so an error return between fork and join cannot leave a capture open.
 constexpr int MAX_PIPES = 4;
-int g_pipes = 2;   // ckks_set_option(10, v): side streams used by the slab pipelines (1 = everything on the caller's stream)
 struct SidePipes {
     bool ready = false;
     cudaStream_t s[MAX_PIPES];
@@ -633,20 +521,80 @@ SidePipes* side_pipes() {
     }
     return &p;
 }
-int pipes_fork(SidePipes* p, cudaStream_t main_st, int n) {
-    if (cudaEventRecord(p->fork_ev, main_st) != cudaSuccess) return (int)cudaGetLastError();
-    for (int i = 0; i < n; ++i)
-        if (cudaStreamWaitEvent(p->s[i], p->fork_ev, 0) != cudaSuccess) return (int)cudaGetLastError();
-    return 0;
-}
-int pipes_join(SidePipes* p, cudaStream_t main_st, int n) {
-    for (int i = 0; i < n; ++i) {
-        if (cudaEventRecord(p->join_ev[i], p->s[i]) != cudaSuccess) return (int)cudaGetLastError();
-        if (cudaStreamWaitEvent(main_st, p->join_ev[i], 0) != cudaSuccess) return (int)cudaGetLastError();
+struct PipeScope {
+    SidePipes* p = nullptr;
+    cudaStream_t main_st = nullptr;
+    int n = 0;
+    bool open = false;
+    int fork(SidePipes* pipes, cudaStream_t st, int count) {
+        p = pipes; main_st = st; n = count;
+        if (cudaEventRecord(p->fork_ev, main_st) != cudaSuccess) return (int)cudaGetLastError();
+        open = true;
+        for (int i = 0; i < n; ++i)
+            if (cudaStreamWaitEvent(p->s[i], p->fork_ev, 0) != cudaSuccess) return (int)cudaGetLastError();
+        return 0;
     }
-    return 0;
+    int join() {
+        if (!open) return 0;
+        open = false;
+        int rc = 0;
+        for (int i = 0; i < n; ++i) {
+            if (cudaEventRecord(p->join_ev[i], p->s[i]) != cudaSuccess) rc = (int)cudaGetLastError();
+            if (cudaStreamWaitEvent(main_st, p->join_ev[i], 0) != cudaSuccess) rc = (int)cudaGetLastError();
+        }
+        return rc;
+    }
+    ~PipeScope() { join(); }
+};
+
+// one batched fast transform; big batches run as row slabs on the internal streams: the first pass of slab s+1 overlaps
+// the second pass of slab s and, more importantly, the hand-off between the two passes of a slab stays in L2 instead of
+// going through HBM twice (DRAM traffic = the algorithmic 16 B per coefficient).
+static int fast_transform(bool fwd, const FastArgs& F0, int rows, cudaStream_t st) {
+    const int logN = F0.logN;
+    const long long as = F0.a_stride;
+    const long long bytes = (long long)rows * 8 << logN;
+    const int nslabs = (int)((bytes + ((long long)g_ntt_slab_mb << 20) - 1) / ((long long)g_ntt_slab_mb << 20));
+    SidePipes* pipes = (bytes > (96ll << 20) && g_pipes > 1 && !g_skip) ? side_pipes() : nullptr;
+    auto passes = [&](const FastArgs& F, dim3 grid, cudaStream_t s) -> int {
+        FastArgs Fb = F;
+        if (fwd) {
+            if (!(g_skip & 1)) { int rc = launch_fast_col(true, F, grid, s); if (rc) return rc; }
+            if (g_skip & 2) return 0;
+            Fb.scal = nullptr;
+            return launch_fast_block_any(true, Fb, grid, s);
+        }
+        if (!(g_skip & 2)) { int rc = launch_fast_block_any(false, Fb, grid, s); if (rc) return rc; }
+        if (g_skip & 1) return 0;
+        return launch_fast_col(false, F, grid, s);
+    };
+    if (pipes) {
+        const int npipes = g_pipes < nslabs ? g_pipes : nslabs;
+        const int per = (rows + nslabs - 1) / nslabs;
+        PipeScope scope;
+        int rc = scope.fork(pipes, st, npipes);
+        if (rc) return rc;
+        int k = 0;
+        for (int r0 = 0; r0 < rows; r0 += per, ++k) {
+            const int r1 = r0 + per < rows ? r0 + per : rows;
+            FastArgs Fs = F0;
+            Fs.a = F0.a + (long long)r0 * as;
+            Fs.row0 = (F0.row0 + r0) % F0.period;
+            rc = passes(Fs, dim3((1 << logN) / TILE, r1 - r0), pipes->s[k % npipes]);
+            if (rc) return rc;
+        }
+        return scope.join();
+    }
+    return passes(F0, dim3((1 << logN) / TILE, rows), st);
 }
+
 }  // namespace
+
+#define RC(x)              \
+    do {                   \
+        int _rc = (x);     \
+        if (_rc) return _rc; \
+    } while (0)
 
 #define CHECK_PTRS(...)                                  \
     do {                                                 \
@@ -655,46 +603,27 @@ int pipes_join(SidePipes* p, cudaStream_t main_st, int n) {
             if (!x) return CKKS_E_BADARG;                \
     } while (0)
 
-static int intt_fast_impl(int64_t* a, int64_t as, int rows, int period, int logN, const void* tw_u64, const double* tw_f64,
-                   const int64_t* q, const int64_t* scal, const uint64_t* scal_sh, int centred, int force_int,
-                   void* stream, int in_raw) {
-    CHECK_PTRS(a, tw_u64, q, scal, scal_sh);
+static FastArgs fast_args(int64_t* a, long long as, const void* tw_u64, const double* tw_f64, const void* twp_u64,
+                          const double* twp_f64, const int64_t* q, const double* qinv, const int64_t* scal,
+                          const uint64_t* scal_sh, int period, int logN) {
+    FastArgs F{};
+    F.a = a; F.a_stride = as;
+    F.tw_u64 = reinterpret_cast<const ulonglong2*>(tw_u64); F.tw_f64 = tw_f64;
+    F.twp_u64 = reinterpret_cast<const ulonglong2*>(twp_u64); F.twp_f64 = twp_f64;
+    F.q = q; F.qinv = qinv; F.scal = scal; F.scal_sh = scal_sh;
+    F.period = period; F.logN = logN;
+    F.prefetch = g_prefetch;
+    return F;
+}
+static int fast_check(const void* a, long long as, int rows, int period, int logN, const void* tw_u64, const double* tw_f64,
+                      const void* twp_u64, const double* twp_f64, int force_int) {
     if (rows <= 0 || period <= 0) return CKKS_E_BADARG;
     if (!force_int && !tw_f64) return CKKS_E_BADARG;
     if (logN < 12 || logN > 17) return CKKS_E_LOGN;
-    if (!row_ok(a, as) || !aligned16(tw_u64) || (tw_f64 && !aligned16(tw_f64))) return CKKS_E_ALIGN;
-    FastArgs F{a, as, reinterpret_cast<const ulonglong2*>(tw_u64), tw_f64, q, scal, scal_sh, period, logN, centred, force_int, 0, 0, 0, g_prefetch, g_swap, 0, in_raw, 0};
-    cudaStream_t st = S(stream);
-    const dim3 grid((1 << logN) / TILE, rows);
-    const long long bytes = (long long)rows * 8 << logN;
-    const int nslabs = (int)((bytes + ((long long)g_ntt_slab_mb << 20) - 1) / ((long long)g_ntt_slab_mb << 20));
-    SidePipes* pipes = (bytes > (96ll << 20) && g_pipes > 1 && !g_skip && !g_persist && g_warp != 2 && !g_colpp) ? side_pipes() : nullptr;
-    if (pipes) {   // row slabs on two internal streams, see ckks_ntt_fast
-        const int npipes = g_pipes < nslabs ? g_pipes : nslabs;
-        const int per = (rows + nslabs - 1) / nslabs;
-        int rc = pipes_fork(pipes, st, npipes);
-        if (rc) return rc;
-        int k = 0;
-        for (int r0 = 0; r0 < rows; r0 += per, ++k) {
-            const int r1 = r0 + per < rows ? r0 + per : rows;
-            FastArgs Fs = F;
-            Fs.a = a + (long long)r0 * as;
-            Fs.row0 = r0 % period;
-            const dim3 g((1 << logN) / TILE, r1 - r0);
-            cudaStream_t ss = pipes->s[k % npipes];
-            g_in_row_slabs = true;
-            rc = launch_fast_inv_block_any(Fs, g, ss, logN);
-            g_in_row_slabs = false;
-            if (rc) return rc;
-            rc = launch_fast_col(false, Fs, g, ss);
-            if (rc) return rc;
-        }
-        return pipes_join(pipes, st, npipes);
-    }
-    int rc = (g_skip & 2) ? 0 : launch_fast_inv_block_any(F, grid, st, logN);
-    if (rc) return rc;
-    if (g_skip & 1) return 0;
-    return launch_fast_col(false, F, grid, st);
+    if (!row_ok(a, as) || !aligned16(tw_u64) || (tw_f64 && !aligned16(tw_f64)) || (twp_u64 && !aligned16(twp_u64)) ||
+        (twp_f64 && !aligned16(twp_f64)))
+        return CKKS_E_ALIGN;
+    return 0;
 }
 
 extern "C" {
@@ -703,44 +632,34 @@ int ckks_abi_version(void) { return CKKS_ABI_VERSION; }
 
 int64_t ckks_launch_count(void) { return (int64_t)g_launches; }
 
-int ckks_get_option(int key) {
-    if (key == 1) return g_persist;
-    if (key == 2) return g_prefetch;
-    if (key == 3) return g_warp;
-    if (key == 4) return g_colpp;
-    if (key == 5) return g_skip;
-    if (key == 6) return g_pp_ctas;
-    if (key == 7) return g_pp_cap;
-    if (key == 8) return g_swap;
-    if (key == 9) return g_slab_mb;
-    if (key == 10) return g_pipes;
-    if (key == 11) return g_ntt_slab_mb;
-    if (key == 12) return g_fuse_rescale;
-    if (key == 13) return g_fuse_tensor;
-    if (key == 14) return g_own_skip;
-    if (key == 15) return g_hyb;
-    if (key == 16) return g_split_tail;
-    return CKKS_E_BADARG;
+static int* option_slot(int key) {
+    switch (key) {
+        case 2: return &g_prefetch;
+#ifdef CKKS_LAB
+        case 5: return &g_skip;
+        case 20: return &g_lab_perm;
+#endif
+        case 9: return &g_slab_mb;
+        case 10: return &g_pipes;
+        case 11: return &g_ntt_slab_mb;
+        case 12: return &g_fuse_rescale;
+        case 16: return &g_split_tail;
+        case 17: return &g_packed;
+        case 18: return &g_perm;
+    }
+    return nullptr;
 }
-
+int ckks_get_option(int key) {
+    const int* p = option_slot(key);
+    return p ? *p : CKKS_E_BADARG;
+}
 int ckks_set_option(int key, int value) {
-    if (key == 1) { g_persist = value; return 0; }
-    if (key == 2) { g_prefetch = value; return 0; }
-    if (key == 3) { g_warp = value; return 0; }
-    if (key == 4) { g_colpp = value; return 0; }
-    if (key == 5) { g_skip = value; return 0; }
-    if (key == 6) { if (value < 1 || value > 4) return CKKS_E_BADARG; g_pp_ctas = value; return 0; }
-    if (key == 7) { g_pp_cap = value; return 0; }
-    if (key == 8) { g_swap = value; return 0; }
-    if (key == 9) { if (value < 1) return CKKS_E_BADARG; g_slab_mb = value; return 0; }
-    if (key == 10) { if (value < 1 || value > MAX_PIPES) return CKKS_E_BADARG; g_pipes = value; return 0; }
-    if (key == 11) { if (value < 1) return CKKS_E_BADARG; g_ntt_slab_mb = value; return 0; }
-    if (key == 12) { g_fuse_rescale = value; return 0; }
-    if (key == 13) { g_fuse_tensor = value; return 0; }
-    if (key == 14) { g_own_skip = value; return 0; }
-    if (key == 15) { g_hyb = value; return 0; }
-    if (key == 16) { g_split_tail = value; return 0; }
-    return CKKS_E_BADARG;
+    int* p = option_slot(key);
+    if (!p) return CKKS_E_BADARG;
+    if ((key == 9 || key == 11) && value < 1) return CKKS_E_BADARG;
+    if (key == 10 && (value < 1 || value > MAX_PIPES)) return CKKS_E_BADARG;
+    *p = value;
+    return 0;
 }
 
 int ckks_mont_mult(const int64_t* a, int64_t as, const int64_t* b, int64_t bs, int64_t* c, int64_t cs, int C, int N,
@@ -888,58 +807,47 @@ int ckks_fast_tables(const int64_t* plain, const int64_t* q, void* tw_u64, doubl
     return launch_status();
 }
 
-int ckks_ntt_fast(int64_t* a, int64_t as, int rows, int period, int logN, const void* tw_u64, const double* tw_f64,
-                  const int64_t* q, const int64_t* scal, const uint64_t* scal_sh, int force_int, void* stream) {
-    CHECK_PTRS(a, tw_u64, q);
-    if (rows <= 0 || period <= 0 || (scal && !scal_sh)) return CKKS_E_BADARG;
-    if (!force_int && !tw_f64) return CKKS_E_BADARG;
+int ckks_fast_pack(const void* tw_u64, const double* tw_f64, void* twp_u64, double* twp_f64, int C, int logN, void* stream) {
+    if (C <= 0) return CKKS_E_BADARG;
     if (logN < 12 || logN > 17) return CKKS_E_LOGN;
-    if (!row_ok(a, as) || !aligned16(tw_u64) || (tw_f64 && !aligned16(tw_f64))) return CKKS_E_ALIGN;
-    FastArgs F{a, as, reinterpret_cast<const ulonglong2*>(tw_u64), tw_f64, q, scal, scal_sh, period, logN, 0, force_int, 0, 0, 0, g_prefetch, g_swap, 0, 0, 0};
-    cudaStream_t st = S(stream);
-    const dim3 grid((1 << logN) / TILE, rows);
-    // Big batches run as row slabs on two internal streams: the column pass of slab s+1 overlaps the block pass of
-    // slab s and, more importantly, the hand-off between the two passes of a slab stays in L2 instead of going through
-    // HBM twice (DRAM traffic = the algorithmic 16 B per coefficient).
-    const long long bytes = (long long)rows * 8 << logN;
-    const int nslabs = (int)((bytes + ((long long)g_ntt_slab_mb << 20) - 1) / ((long long)g_ntt_slab_mb << 20));
-    SidePipes* pipes = (bytes > (96ll << 20) && g_pipes > 1 && !g_skip && !g_persist && g_warp != 2 && !g_colpp) ? side_pipes() : nullptr;
-    if (pipes) {
-        const int npipes = g_pipes < nslabs ? g_pipes : nslabs;
-        const int per = (rows + nslabs - 1) / nslabs;
-        int rc = pipes_fork(pipes, st, npipes);
-        if (rc) return rc;
-        int k = 0;
-        for (int r0 = 0; r0 < rows; r0 += per, ++k) {
-            const int r1 = r0 + per < rows ? r0 + per : rows;
-            FastArgs Fs = F;
-            Fs.a = a + (long long)r0 * as;
-            Fs.row0 = r0 % period;
-            const dim3 g((1 << logN) / TILE, r1 - r0);
-            cudaStream_t ss = pipes->s[k % npipes];
-            rc = launch_fast_col(true, Fs, g, ss);
-            if (rc) return rc;
-            Fs.scal = nullptr;
-            g_in_row_slabs = true;
-            rc = launch_fast_fwd_block_any(Fs, g, ss, logN);
-            g_in_row_slabs = false;
-            if (rc) return rc;
-        }
-        return pipes_join(pipes, st, npipes);
-    }
-    if (!(g_skip & 1)) {
-        int rc = launch_fast_col(true, F, grid, st);
-        if (rc) return rc;
-    }
-    if (g_skip & 2) return 0;
-    F.scal = nullptr;
-    return launch_fast_fwd_block_any(F, grid, st, logN);
+    if ((twp_u64 && !tw_u64) || (twp_f64 && !tw_f64) || (!twp_u64 && !twp_f64)) return CKKS_E_BADARG;
+    if ((twp_u64 && !aligned16(twp_u64)) || (twp_f64 && !aligned16(twp_f64))) return CKKS_E_ALIGN;
+    const int threads = (1 << logN) >> 4;
+    fast_pack_kernel<<<dim3((threads + 255) / 256, C), 256, 0, S(stream)>>>(
+        reinterpret_cast<const ulonglong2*>(tw_u64), tw_f64, reinterpret_cast<ulonglong2*>(twp_u64), twp_f64, logN);
+    return launch_status();
+}
+
+int ckks_perm_rows(const int64_t* in, int64_t in_stride, int64_t* out, int64_t out_stride, int rows, int N, int inverse,
+                   void* stream) {
+    CHECK_PTRS(in, out);
+    if (rows <= 0 || N < PACK_TILE || (N & (N - 1)) || in == out) return CKKS_E_BADARG;
+    fast_perm_kernel<<<dim3((N + 255) / 256, rows), 256, 0, S(stream)>>>(in, in_stride, out, out_stride, N, inverse);
+    return launch_status();
+}
+
+int ckks_ntt_fast(int64_t* a, int64_t as, int rows, int period, int logN, const void* tw_u64, const double* tw_f64,
+                  const void* twp_u64, const double* twp_f64, const int64_t* q, const double* qinv, const int64_t* scal,
+                  const uint64_t* scal_sh, int force_int, void* stream) {
+    CHECK_PTRS(a, tw_u64, q);
+    if (scal && !scal_sh) return CKKS_E_BADARG;
+    RC(fast_check(a, as, rows, period, logN, tw_u64, tw_f64, twp_u64, twp_f64, force_int));
+    FastArgs F = fast_args(a, as, tw_u64, tw_f64, twp_u64, twp_f64, q, qinv, scal, scal_sh, period, logN);
+    F.force_int = force_int ? 1 : 0;
+    F.perm = g_lab_perm;
+    return fast_transform(true, F, rows, S(stream));
 }
 
 int ckks_intt_fast(int64_t* a, int64_t as, int rows, int period, int logN, const void* tw_u64, const double* tw_f64,
-                   const int64_t* q, const int64_t* scal, const uint64_t* scal_sh, int centred, int force_int,
-                   void* stream) {
-    return intt_fast_impl(a, as, rows, period, logN, tw_u64, tw_f64, q, scal, scal_sh, centred, force_int, stream, 0);
+                   const void* twp_u64, const double* twp_f64, const int64_t* q, const double* qinv, const int64_t* scal,
+                   const uint64_t* scal_sh, int centred, int force_int, void* stream) {
+    CHECK_PTRS(a, tw_u64, q, scal, scal_sh);
+    RC(fast_check(a, as, rows, period, logN, tw_u64, tw_f64, twp_u64, twp_f64, force_int));
+    FastArgs F = fast_args(a, as, tw_u64, tw_f64, twp_u64, twp_f64, q, qinv, scal, scal_sh, period, logN);
+    F.force_int = force_int ? 1 : 0;
+    F.centred = centred;
+    F.perm = g_lab_perm;
+    return fast_transform(false, F, rows, S(stream));
 }
 
 // ---- level 2 -----------------------------------------------------------------------------------------
@@ -963,7 +871,7 @@ int ckks_tensor_product(const int64_t* x0, const int64_t* x1, const int64_t* y0,
         !row_ok(d1, os) || !row_ok(d2, os))
         return CKKS_E_ALIGN;
     k_tensor<<<ew_grid(N, C), EW_THREADS, 0, S(stream)>>>(x0, x1, y0, y1, is, d0, d1, d2, os, N,
-                                                          MontPack{_2q, ql, qh, kl, kh}, nullptr);
+                                                          MontPack{_2q, ql, qh, kl, kh});
     return launch_status();
 }
 
@@ -1031,15 +939,10 @@ int ckks_moddown(int64_t* d, int64_t ds, int L, int K, int N, const int64_t* Rs,
 }
 
 // ---- level 3: the fused executor (one C call = a whole stage of the hot path) ------------------------------
-#define RC(x)              \
-    do {                   \
-        int _rc = (x);     \
-        if (_rc) return _rc; \
-    } while (0)
-
 int ckks_exec_digits(const ckks_level_t* lv, const int64_t* a, int64_t as, int64_t* digits, int64_t ds, void* stream) {
     CHECK_PTRS(lv, a, digits);
     if (lv->nlocal <= 0) return 0;
+    if (lv->amax > MAX_ALPHA) return CKKS_E_BADARG;   // k_garner_batched keeps at most MAX_ALPHA digits per partition
     const int N = 1 << lv->logN;
     k_garner_batched<<<dim3((N + EW_THREADS - 1) / EW_THREADS, lv->nlocal), EW_THREADS, 0, S(stream)>>>(
         a, as, digits, ds, N, lv->loc_row0, lv->loc_alpha, lv->loc_Y, lv->loc_Ltri,
@@ -1047,17 +950,26 @@ int ckks_exec_digits(const ckks_level_t* lv, const int64_t* a, int64_t as, int64
     return launch_status();
 }
 
+static FastArgs level_fast(const ckks_level_t* lv, int64_t* a, long long as, bool fwd, const int64_t* scal, const int64_t* scal_sh,
+                           int period) {
+    return fwd ? fast_args(a, as, lv->twf_u64, lv->twf_f64, lv->twpf_u64, lv->twpf_f64, lv->q, lv->qinv, scal,
+                           (const uint64_t*)scal_sh, period, lv->logN)
+               : fast_args(a, as, lv->twi_u64, lv->twi_f64, lv->twpi_u64, lv->twpi_f64, lv->q, lv->qinv, scal,
+                           (const uint64_t*)scal_sh, period, lv->logN);
+}
+
 int ckks_exec_tensor_stage(const ckks_level_t* lv, const int64_t* a0, const int64_t* a1, const int64_t* b0,
                            const int64_t* b1, int64_t in_stride, const int64_t* r0a0, const int64_t* r0a1,
                            const int64_t* r0b0, const int64_t* r0b1, int64_t* x, int64_t* d, int64_t* digits,
-                           int64_t* d2hat, void* stream) {
+                           void* stream) {
     CHECK_PTRS(lv, a0, a1, b0, b1, r0a0, r0a1, r0b0, r0b1, x, d, digits);
-    if (!g_own_skip) d2hat = nullptr;
     const int L = lv->L, N = 1 << lv->logN;
     const long long LN = (long long)L * N;
     const int64_t* in[4] = {a0, a1, b0, b1};
     const int64_t* r0[4] = {r0a0, r0a1, r0b0, r0b1};
-    bool fused_tensor = false;
+    cudaStream_t st = S(stream);
+    // NTT-domain order inside this stage: warp-interleaved (the tensor product is pointwise)
+    const int perm = g_perm ? 1 : 0;
     if (g_fuse_rescale && aligned16(in[0]) && aligned16(in[1]) && aligned16(in[2]) && aligned16(in[3])) {
         // rescale fused into the load of the batched column pass (no rescaled polynomial is ever written to HBM)
         RescaleIn R{};
@@ -1067,57 +979,48 @@ int ckks_exec_tensor_stage(const ckks_level_t* lv, const int64_t* a0, const int6
         R.round_at = lv->round_at;
         R._2q = lv->_2q; R.ql = lv->ql; R.qh = lv->qh; R.kl = lv->kl; R.kh = lv->kh;
         R.L = L;
-        FastArgs F{x, N, reinterpret_cast<const ulonglong2*>(lv->twf_u64), lv->twf_f64, lv->q, lv->sR,
-                   (const uint64_t*)lv->sR_sh, L, lv->logN, 0, 0, 0, 0, 0, 0, g_swap, 0, 0, 0};
+        FastArgs F = level_fast(lv, x, N, true, lv->sR, lv->sR_sh, L);
+        F.prefetch = 0;
         const dim3 grid(N / TILE, 4 * L);
         cudaFuncSetAttribute(fast_fwd_colpass_rescale<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, COL_SMEM_BYTES);
-        fast_fwd_colpass_rescale<0><<<tile_grid(grid), NTT_THREADS, COL_SMEM_BYTES, S(stream)>>>(F, R);
+        fast_fwd_colpass_rescale<0><<<grid, NTT_THREADS, COL_SMEM_BYTES, st>>>(F, R);
         RC(launch_status());
         F.scal = nullptr;
         F.prefetch = g_prefetch;
-        fused_tensor = g_fuse_tensor && lv->sExitT && lv->sExitT_sh && (g_warp == 1 || g_warp == 3);
-        F.out_raw = fused_tensor ? 1 : 0;   // scale-prime rows stay raw doubles for the fused tensor product
-        RC(launch_fast_fwd_block_any(F, grid, S(stream), lv->logN));
+        F.perm = perm;
+        RC(launch_fast_block_any(true, F, grid, st));
     } else {
         for (int c = 0; c < 4; ++c)
             RC(ckks_rescale(in[c], in_stride, r0[c], x + c * LN, N, L, N, lv->rescale_scale, lv->round_at, 1, lv->_2q, lv->ql,
                             lv->qh, lv->kl, lv->kh, stream));
-        RC(ckks_ntt_fast(x, N, 4 * L, L, lv->logN, lv->twf_u64, lv->twf_f64, lv->q, lv->sR, (const uint64_t*)lv->sR_sh, 0, stream));
+        FastArgs F = level_fast(lv, x, N, true, lv->sR, lv->sR_sh, L);
+        F.perm = perm;
+        RC(fast_transform(true, F, 4 * L, st));
     }
-    if (fused_tensor) {
-        // tensor product fused into the load of the batched inverse block pass (d0, d1, d2 never exist in the NTT domain in HBM)
-        TensorIn Tn{x, LN, lv->_2q, lv->ql, lv->qh, lv->kl, lv->kh, nullptr, L};   // (its d2hat form differs: not used for the own-row skip)
-        d2hat = nullptr;
-        FastArgs Fi{d, N, reinterpret_cast<const ulonglong2*>(lv->twi_u64), lv->twi_f64, lv->q, lv->sExitT,
-                    (const uint64_t*)lv->sExitT_sh, L, lv->logN, 0, 0, 0, 0, 0, 0, g_swap, 0, 0, 0};
-        const dim3 grid(N / TILE, 3 * L);
-        RC(launch_inv_block_tensor(Fi, Tn, grid, S(stream), lv->logN));
-        Fi.prefetch = g_prefetch;
-        RC(launch_fast_col(false, Fi, grid, S(stream)));
-    } else {
-        k_tensor<<<ew_grid(N, L), EW_THREADS, 0, S(stream)>>>(x, x + LN, x + 2 * LN, x + 3 * LN, N, d, d + LN, d + 2 * LN, N, N,
-                                                              MontPack{lv->_2q, lv->ql, lv->qh, lv->kl, lv->kh}, d2hat);
-        RC(launch_status());
-        RC(ckks_intt_fast(d, N, 3 * L, L, lv->logN, lv->twi_u64, lv->twi_f64, lv->q, lv->sExit, (const uint64_t*)lv->sExit_sh, 0, 0,
-                          stream));
-    }
+    k_tensor<<<ew_grid(N, L), EW_THREADS, 0, st>>>(x, x + LN, x + 2 * LN, x + 3 * LN, N, d, d + LN, d + 2 * LN, N, N,
+                                                   MontPack{lv->_2q, lv->ql, lv->qh, lv->kl, lv->kh});
+    RC(launch_status());
+    FastArgs Fi = level_fast(lv, d, N, false, lv->sExit, lv->sExit_sh, L);
+    Fi.perm = perm;
+    RC(fast_transform(false, Fi, 3 * L, st));
     return ckks_exec_digits(lv, d + 2 * LN, N, digits, N, stream);
 }
 
 int ckks_exec_keyswitch_stage(const ckks_level_t* lv, const int64_t* const* digit_ptrs, int64_t digit_stride,
                               const int64_t* const* k0_ptrs, const int64_t* const* k1_ptrs, int64_t ksk_stride,
-                              const int64_t* add0, const int64_t* add1, int64_t add_stride, int64_t* out0,
-                              int64_t* out1, int64_t out_stride, int64_t* ws, const int64_t* d2hat, void* stream) {
+                              int keys_permuted, const int64_t* add0, const int64_t* add1, int64_t add_stride,
+                              int64_t* out0, int64_t* out1, int64_t out_stride, int64_t* ws, void* stream) {
     CHECK_PTRS(lv, digit_ptrs, k0_ptrs, k1_ptrs, out0, out1, ws);
-    // own-partition skip: only with the default one-tile-per-CTA kernels, the partition table and d2hat from the tensor stage
-    // (the tensor stage with the product fused into its inverse transform does not produce d2hat: the two options exclude each other)
-    const int32_t* own_row0 = (g_own_skip && !g_fuse_tensor && d2hat && lv->part_row0 && !g_persist && g_warp != 2 && !g_colpp) ? lv->part_row0 : nullptr;
+    if (lv->amax > MAX_ALPHA) return CKKS_E_BADARG;   // the extension kernels keep at most MAX_ALPHA digits per partition
     const int L = lv->L, K = lv->K, E = L + K, P = lv->nparts, N = 1 << lv->logN;
     int64_t* ext = ws;                                  // [P*E][N]
     int64_t* acc = ext + (long long)P * E * N;          // [2E][N]
     int64_t* eff = acc + 2ll * E * N;                   // [K][N]
     const MontPack m{lv->_2q, lv->ql, lv->qh, lv->kl, lv->kh};
-    if (lv->Hm && lv->Rinv) {
+    const bool fp64 = lv->Hm && lv->Pinv;
+    // the evaluation key decides the order of the NTT domain in this stage: permuted copies <-> warp-interleaved data
+    const int perm = keys_permuted ? 1 : 0;
+    if (fp64) {
         // Slab pipeline over target limbs [t0, t1): extend -> column pass -> block pass -> inner product per slab, slabs
         // alternating between two internal streams so that the tail of one kernel overlaps the next slab's kernels.
         // Measured (profiles/r01_lab_notes.txt): L2-sized slabs (32-64 MB) lose more to small grids than they gain from
@@ -1137,41 +1040,49 @@ int ckks_exec_keyswitch_stage(const ckks_level_t* lv, const int64_t* const* digi
         X.E = E;
         X.N = N;
         X.raw = 1;   // scale-prime rows travel as raw doubles from the extension to the inverse transform
-        X.own_row0 = own_row0;
+        X.qinv = lv->qinv;
         const long long slab_budget = (long long)g_slab_mb << 20;   // bytes of extended rows per slab
         const long long all_bytes = (long long)P * E * N * 8;
         const int nslabs = (int)((all_bytes + slab_budget - 1) / slab_budget);
         const int slab = (E + nslabs - 1) / nslabs;
+        if (slab > EXT_MAX_E) return CKKS_E_BADARG;
         cudaStream_t main_st = S(stream);
         SidePipes* pipes = (nslabs > 1 && g_pipes > 1) ? side_pipes() : nullptr;
         const int npipes = pipes ? (g_pipes < nslabs ? g_pipes : nslabs) : 0;
-        if (pipes) RC(pipes_fork(pipes, main_st, npipes));
+        PipeScope scope;
+        if (pipes) RC(scope.fork(pipes, main_st, npipes));
         int slab_no = 0;
         for (int t0 = 0; t0 < E; t0 += slab, ++slab_no) {
             cudaStream_t st = pipes ? pipes->s[slab_no % npipes] : main_st;
             const int t1 = (t0 + slab < E) ? t0 + slab : E;
             const dim3 eg((N / 2 + 255) / 256, P);
-            if (t1 - t0 > EXT_MAX_E) return CKKS_E_BADARG;
             if (lv->amax <= 2) k_extend_fast<2><<<eg, 256, 0, st>>>(X, t0, t1);
             else if (lv->amax <= 4) k_extend_fast<4><<<eg, 256, 0, st>>>(X, t0, t1);
             else k_extend_fast<8><<<eg, 256, 0, st>>>(X, t0, t1);
             RC(launch_status());
-            FastArgs F{ext, N, reinterpret_cast<const ulonglong2*>(lv->twf_u64), lv->twf_f64, lv->q, nullptr, nullptr, E,
-                       lv->logN, 0, 0, t1 - t0, E, t0, g_prefetch, g_swap, 0, 1, 1, own_row0, lv->part_alpha};
+            FastArgs F = level_fast(lv, ext, N, true, nullptr, nullptr, E);
+            F.slab_rows = t1 - t0; F.group_rows = E; F.slab_t0 = t0;
+            F.in_raw = 1; F.out_raw = 1;
             const dim3 grid(N / TILE, P * (t1 - t0));
             RC(launch_fast_col(true, F, grid, st));
-            RC(launch_fast_fwd_block_any(F, grid, st, lv->logN));
-            InnerArgs I{ext, k0_ptrs, k1_ptrs, ksk_stride, acc, acc + (long long)E * N, lv->Rinv, lv->q, lv->_2q, lv->ql, lv->qh,
-                        lv->kl, lv->kh, P, E, N, t0, 1, own_row0, lv->part_alpha, d2hat};
+            F.perm = perm;
+            RC(launch_fast_block_any(true, F, grid, st));
+            InnerArgs I{};
+            I.ext = ext; I.k0 = k0_ptrs; I.k1 = k1_ptrs; I.k_stride = ksk_stride;
+            I.acc0 = acc; I.acc1 = acc + (long long)E * N;
+            I.q = lv->q; I._2q = lv->_2q; I.ql = lv->ql; I.qh = lv->qh; I.kl = lv->kl; I.kh = lv->kh;
+            I.P = P; I.E = E; I.N = N; I.t0 = t0; I.raw = 1; I.qinv = lv->qinv;
             k_ksk_inner_fast<<<dim3((N / 2 + 255) / 256, t1 - t0), 256, 0, st>>>(I);
             RC(launch_status());
         }
-        if (pipes) RC(pipes_join(pipes, main_st, npipes));
+        RC(scope.join());
     } else {
+        if (perm) return CKKS_E_BADARG;   // the integer fall-back works on natural-order keys only
         k_extend_batched<<<ew_grid(N, P * E), EW_THREADS, 0, S(stream)>>>(digit_ptrs, digit_stride, lv->part_alpha, ext, N, E,
                                                                           N, lv->Rs, lv->Lenter, m);
         RC(launch_status());
-        RC(ckks_ntt_fast(ext, N, P * E, E, lv->logN, lv->twf_u64, lv->twf_f64, lv->q, nullptr, nullptr, 0, stream));
+        FastArgs F = level_fast(lv, ext, N, true, nullptr, nullptr, E);
+        RC(fast_transform(true, F, P * E, S(stream)));
         RC(ckks_ksk_inner(ext, N, P, k0_ptrs, k1_ptrs, ksk_stride, acc, acc + (long long)E * N, N, E, N, lv->_2q, lv->ql,
                           lv->qh, lv->kl, lv->kh, stream));
     }
@@ -1179,21 +1090,24 @@ int ckks_exec_keyswitch_stage(const ckks_level_t* lv, const int64_t* const* digi
     // own internal stream, so the small latency-bound ModDown kernels of one half overlap the transform of the other.
     int64_t* outs[2] = {out0, out1};
     const int64_t* adds[2] = {add0, add1};
-    const int Ls = lv->Pinv ? lv->L_small : 0;   // leading ordinary rows handled by the FP64 kernel
-    const int in_raw = (lv->Hm && lv->Rinv) ? 1 : 0;
+    const int Ls = fp64 ? lv->L_small : 0;   // leading ordinary rows handled by the FP64 kernel
     SidePipes* tail = (g_pipes > 1 && g_split_tail) ? side_pipes() : nullptr;
-    if (tail) RC(pipes_fork(tail, S(stream), 2));
+    PipeScope tscope;
+    if (tail) RC(tscope.fork(tail, S(stream), 2));
     for (int h = 0; h < 2; ++h) {
         cudaStream_t st = tail ? tail->s[h] : S(stream);
         int64_t* dh = acc + (long long)h * E * N;
         int64_t* effh = eff + (long long)h * K * N;
-        if (tail || h == 0)   // (one stream: both halves in one batched transform, as before)
-            RC(intt_fast_impl(dh, N, tail ? E : 2 * E, E, lv->logN, lv->twi_u64, lv->twi_f64, lv->q, lv->sExit,
-                              (const uint64_t*)lv->sExit_sh, 0, 0, st, in_raw));
+        if (tail || h == 0) {   // (one stream: both halves in one batched transform)
+            FastArgs Fi = level_fast(lv, dh, N, false, lv->sExit, lv->sExit_sh, E);
+            Fi.in_raw = fp64 ? 1 : 0;
+            Fi.perm = perm;
+            RC(fast_transform(false, Fi, tail ? E : 2 * E, st));
+        }
         k_moddown_special<<<col_grid(N), EW_THREADS, 0, st>>>(dh, N, L, K, N, lv->PiR, effh, m);
         RC(launch_status());
         if (Ls > 0) {
-            ModDownArgs M{dh, effh, adds[h], add_stride, outs[h], out_stride, lv->Pinv, lv->C31, lv->q, L, K, E, N};
+            ModDownArgs M{dh, effh, adds[h], add_stride, outs[h], out_stride, lv->Pinv, lv->C31, lv->q, L, K, E, N, lv->qinv};
             k_moddown_fast<<<dim3((N / 2 + 255) / 256, Ls), 256, 0, st>>>(M);
             RC(launch_status());
         }
@@ -1203,7 +1117,7 @@ int ckks_exec_keyswitch_stage(const ckks_level_t* lv, const int64_t* const* digi
             RC(launch_status());
         }
     }
-    if (tail) RC(pipes_join(tail, S(stream), 2));
+    RC(tscope.join());
     return 0;
 }
 

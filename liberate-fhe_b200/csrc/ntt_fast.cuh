@@ -14,7 +14,9 @@
 //     w' = floor(w 2^64 / q): t = umulhi(v, w'), r = v*w - t*q in [0, 2q); one conditional correction per butterfly.
 //
 // Twiddles are PLAIN (non-Montgomery) powers of psi: the transform is linear, so Montgomery-form data stay in
-// Montgomery form.  Tables: shoup[C][N] = {w, w'} (16 B) and dbl[C][N] (8 B, small primes only).
+// Montgomery form.  Tables: shoup[C][N] = {w, w'} (16 B) and dbl[C][N] (8 B, small primes only), plus PACKED copies of
+// the last four stages (one thread's 15 twiddles stored lane-interleaved, see TwPacked) so that the block passes read
+// them with fully coalesced 128-bit loads.
 #pragma once
 #include "ntt_kernels.cuh"
 
@@ -156,6 +158,20 @@ struct ArithF64 {
             }
         }
     }
+    template <int I>   // stage I of the packed last group (see TwPacked)
+    static __device__ __forceinline__ void load_tw_packed(TW (&w)[8], const TW* __restrict__ wt, int lane) {
+        if constexpr (I == 0) {
+            w[0] = __ldg(wt + lane);
+        } else {
+            const double2* __restrict__ gr = reinterpret_cast<const double2*>(wt + 64) + (((1 << (I - 1)) - 1) * 32 + lane);
+#pragma unroll
+            for (int g = 0; g < (1 << (I - 1)); ++g) {
+                const double2 v = __ldg(gr + g * 32);
+                w[2 * g] = v.x;
+                w[2 * g + 1] = v.y;
+            }
+        }
+    }
 };
 
 // ------------------------------------------------------------------------------------------------------------
@@ -220,6 +236,12 @@ struct ArithU64 {
 #pragma unroll
         for (int g = 0; g < RUN; ++g) w[g] = SMEM ? p[g] : __ldg(p + g);
     }
+    template <int I>
+    static __device__ __forceinline__ void load_tw_packed(TW (&w)[8], const TW* __restrict__ wt, int lane) {
+        const TW* __restrict__ en = wt + ((1 << I) - 1) * 32 + lane;
+#pragma unroll
+        for (int g = 0; g < (1 << I); ++g) w[g] = __ldg(en + g * 32);
+    }
 };
 
 // ------------------------------------------------------------------------------------------------------------
@@ -283,14 +305,24 @@ struct TwGlobal {
     static constexpr bool SMEM = false;
     __device__ __forceinline__ const TW* run(int i) const { return W + ((1u << (s0 + i)) + (pre << i)); }
 };
+// The last four stages of a forward block pass (the first four levels of an inverse one) use 15 twiddles that belong to
+// exactly one thread (the thread that holds 16 contiguous coefficients).  In the plain table they are 1 + 2 + 4 + 8
+// values at four different places, 8 to 64 bytes per thread: a warp's 128-bit loads touch up to 16 lines each.  The
+// PACKED table stores them per warp tile (32 threads = 512 coefficients) lane-interleaved:
+//   doubles  [512 per warp tile]: s0[lane] (32) | pad (32) | granule g = 0..6: {w, w}[lane] -- g 0: stage 1, 1-2: stage 2, 3-6: stage 3
+//   {w, w'}  [512 per warp tile]: entry e = 0..14 (stage i, index j -> e = 2^i - 1 + j): [e][lane]
+// so every load of a warp is one contiguous 256- or 512-byte run.
+constexpr int PACK_TILE = 512;
 template <class TW>
-struct TwShared {
-    const TW* const* stage;   // stage[j] = shared-memory array of pass-local stage j
-    int j0;                   // pass-local stage of i == 0
-    unsigned pre;             // CTA-local index bits above the field
-    static constexpr bool SMEM = true;
-    __device__ __forceinline__ const TW* run(int i) const { return stage[j0 + i] + (pre << i); }
+struct TwPacked {
+    const TW* wt;   // this warp tile's packed twiddles
+    int lane;
+    static constexpr bool SMEM = false;
 };
+template <class SRC>
+struct is_packed { static constexpr bool value = false; };
+template <class TW>
+struct is_packed<TwPacked<TW>> { static constexpr bool value = true; };
 
 // ------------------------------------------------------------------------------------------------------------
 // rounds
@@ -298,7 +330,10 @@ struct TwShared {
 template <class A, int I, class SRC>
 __device__ __forceinline__ void fast_fwd_stage(typename A::T (&e)[16], const SRC& src, const typename A::C& c) {
     typename A::TW w[8];
-    A::template load_tw<(1 << I), SRC::SMEM>(w, src.run(I));
+    if constexpr (is_packed<SRC>::value)
+        A::template load_tw_packed<I>(w, src.wt, src.lane);
+    else
+        A::template load_tw<(1 << I), SRC::SMEM>(w, src.run(I));
     A::template ct_stage<I>(e, w, c);
 }
 template <class A, int FIRST, class SRC>
@@ -311,7 +346,10 @@ __device__ __forceinline__ void fast_fwd_round(typename A::T (&e)[16], const SRC
 template <class A, int I, class SRC>
 __device__ __forceinline__ void fast_inv_stage(typename A::T (&e)[16], const SRC& src, const typename A::C& c) {
     typename A::TW w[8];
-    A::template load_tw<(1 << (3 - I)), SRC::SMEM>(w, src.run(3 - I));
+    if constexpr (is_packed<SRC>::value)
+        A::template load_tw_packed<3 - I>(w, src.wt, src.lane);
+    else
+        A::template load_tw<(1 << (3 - I)), SRC::SMEM>(w, src.run(3 - I));
     A::template gs_stage<I>(e, w, c);
 }
 template <class A, int NST, class SRC>
@@ -351,61 +389,41 @@ struct FastArgs {
     int period;                 // constants / twiddles of row r are those of limb r % period
     int logN;
     int centred;                // inverse only: output in (-q/2, q/2] instead of [0, q)
-    int force_int;              // 1: integer path for every limb; m > 1: for every m-th row (INT + FP64 pipes side by side)
+    int force_int;              // 1: integer path for every limb
     // slab view of a [groups][group_rows] block: grid row r -> group r / slab_rows, member r % slab_rows;
     // data row = group * group_rows + slab_t0 + member, limb = slab_t0 + member.  slab_rows == 0: plain rows.
     int slab_rows, group_rows, slab_t0;
     int prefetch;               // rows ahead whose tile is pulled into L2 by every CTA (0 = off)
-    int swap_grid;              // one-tile-per-CTA kernels: blockIdx.x = row, blockIdx.y = chunk
     int row0;                   // plain rows: limb of grid row r is (row0 + r) % period (row slabs of one batch)
     int in_raw, out_raw;        // FP64 rows: the input / the forward output are raw doubles (fused key switch), not int64
-    // slab views of a key switch: partition g owns target limbs [own_row0[g], own_row0[g] + own_alpha[g]) (own_row0 < 0:
-    // none on this device).  Those rows are NOT transformed: their NTT is the tensor product's d2 itself.
-    const int32_t* own_row0;
-    const int32_t* own_alpha;
+    // PACKED last-group twiddles (TwPacked), or nullptr: the block passes then read the plain tables
+    const ulonglong2* twp_u64;  // [period][N]
+    const double* twp_f64;      // [period][N]
+    const double* qinv;         // [period] 1/q as doubles, or nullptr (computed per CTA: an FP64 division)
+    // NTT-domain data in WARP-INTERLEAVED order (fused path only; pointwise consumers do not care, the evaluation key is
+    // permuted once): inside every 512-coefficient warp tile, coefficient 16 t + k sits at ((k >> 1) * 32 + t) * 2 + (k & 1),
+    // so the block passes move a thread's 16 contiguous coefficients as eight lane-contiguous 128-bit accesses
+    // (512 contiguous bytes per warp instruction) instead of four 256-bit accesses 128 bytes apart (32 lines per instruction).
+    int perm;
 };
 
-// grid mapping of the one-tile-per-CTA kernels: (chunk, row) by default; swapped (row, chunk) when F.swap_grid is
-// set, so that consecutive CTAs belong to consecutive rows and the integer-path rows (60-bit limbs) are spread
-// finely among the FP64 rows -- the two kinds of tile load different pipes and overlap when they share an SM.
-__device__ __forceinline__ int grid_row(const FastArgs& F) { return F.swap_grid ? blockIdx.x : blockIdx.y; }
-__device__ __forceinline__ int grid_rows(const FastArgs& F) { return F.swap_grid ? gridDim.x : gridDim.y; }
-__device__ __forceinline__ unsigned grid_chunk(const FastArgs& F) { return F.swap_grid ? blockIdx.y : blockIdx.x; }
+__device__ __forceinline__ int grid_row(const FastArgs& F) { return blockIdx.y; }
+__device__ __forceinline__ unsigned grid_chunk(const FastArgs& F) { return blockIdx.x; }
 
 struct RowId {
     long long data_row;
     int limb;
 };
-__device__ __forceinline__ bool own_target(const int32_t* row0, const int32_t* alpha, int part, int t) {
-    if (!row0) return false;
-    const int r0 = row0[part];
-    return r0 >= 0 && t >= r0 && t < r0 + alpha[part];
-}
-__device__ __forceinline__ bool fast_skip_own(const FastArgs& F) {   // CTA-uniform
-    if (!F.own_row0 || F.slab_rows == 0) return false;
-    const int r = grid_row(F), g = r / F.slab_rows;
-    return own_target(F.own_row0, F.own_alpha, g, F.slab_t0 + (r - g * F.slab_rows));
-}
 // the tile that a CTA dispatched about `ahead` rows x (chunks per row) tiles later will load: data row (or -1) and chunk
 __device__ __forceinline__ long long fast_row_ahead(const FastArgs& F, int ahead, unsigned& chunk) {
-    int r;
-    if (F.swap_grid) {   // dispatch order: row fastest, then chunk
-        const long long lin = (long long)blockIdx.y * gridDim.x + blockIdx.x + (long long)ahead * gridDim.y;
-        const int c = (int)(lin / gridDim.x);
-        if (c >= (int)gridDim.y) return -1;
-        r = (int)(lin - (long long)c * gridDim.x);
-        chunk = (unsigned)c;
-    } else {
-        r = blockIdx.y + ahead;
-        if (r >= (int)gridDim.y) return -1;
-        chunk = blockIdx.x;
-    }
+    const int r = blockIdx.y + ahead;
+    if (r >= (int)gridDim.y) return -1;
+    chunk = blockIdx.x;
     if (F.slab_rows == 0) return r;
     const int g = r / F.slab_rows, m = r - g * F.slab_rows;
     return (long long)g * F.group_rows + F.slab_t0 + m;
 }
 
-__device__ __forceinline__ bool fast_use_f64(const FastArgs& F, const RowId& rid);
 __device__ __forceinline__ RowId fast_row(const FastArgs& F) {
     const int r = grid_row(F);
     if (F.slab_rows == 0) return RowId{r, (F.row0 + r) % F.period};
@@ -413,20 +431,19 @@ __device__ __forceinline__ RowId fast_row(const FastArgs& F) {
     return RowId{(long long)g * F.group_rows + F.slab_t0 + m, F.slab_t0 + m};
 }
 __device__ __forceinline__ bool fast_use_f64(const FastArgs& F, const RowId& rid) {
-    if ((uint64_t)F.q[rid.limb] >= SMALL_PRIME_LIMIT) return false;
-    if (F.force_int == 0) return true;
-    if (F.force_int == 1) return false;
-    return (rid.data_row % F.force_int) != (F.force_int - 1);
+    return (uint64_t)F.q[rid.limb] < SMALL_PRIME_LIMIT && F.force_int == 0;
 }
 
 template <class A>
-__device__ __forceinline__ typename A::C make_const(uint64_t q);
+__device__ __forceinline__ typename A::C make_const(const FastArgs& F, int limb);
 template <>
-__device__ __forceinline__ F64C make_const<ArithF64>(uint64_t q) {
-    return F64C{(double)q, 1.0 / (double)q};
+__device__ __forceinline__ F64C make_const<ArithF64>(const FastArgs& F, int limb) {
+    const double q = (double)(uint64_t)F.q[limb];
+    return F64C{q, F.qinv ? F.qinv[limb] : 1.0 / q};
 }
 template <>
-__device__ __forceinline__ U64C make_const<ArithU64>(uint64_t q) {
+__device__ __forceinline__ U64C make_const<ArithU64>(const FastArgs& F, int limb) {
+    const uint64_t q = (uint64_t)F.q[limb];
     return U64C{q, q << 1};
 }
 template <class A>
@@ -440,6 +457,16 @@ __device__ __forceinline__ const ulonglong2* tw_row<ArithU64>(const FastArgs& F,
     return F.tw_u64 + ((long long)limb << F.logN);
 }
 template <class A>
+__device__ __forceinline__ const typename A::TW* twp_row(const FastArgs& F, int limb);
+template <>
+__device__ __forceinline__ const double* twp_row<ArithF64>(const FastArgs& F, int limb) {
+    return F.twp_f64 ? F.twp_f64 + ((long long)limb << F.logN) : nullptr;
+}
+template <>
+__device__ __forceinline__ const ulonglong2* twp_row<ArithU64>(const FastArgs& F, int limb) {
+    return F.twp_u64 ? F.twp_u64 + ((long long)limb << F.logN) : nullptr;
+}
+template <class A>
 __device__ __forceinline__ typename A::TW scalar_tw(const FastArgs& F, int limb);
 template <>
 __device__ __forceinline__ double scalar_tw<ArithF64>(const FastArgs& F, int limb) {
@@ -450,33 +477,18 @@ __device__ __forceinline__ ulonglong2 scalar_tw<ArithU64>(const FastArgs& F, int
     return make_ulonglong2((uint64_t)F.scal[limb], F.scal_sh[limb]);
 }
 
-// shared memory of the fast kernels: [data tile | staged twiddles (F64 path) | mbarrier]
-#ifndef FAST_CTAS_PER_SM
-#define FAST_CTAS_PER_SM 3
-#endif
-constexpr int FAST_TW_SLOTS = 4096;
-constexpr int FAST_SMEM_BYTES = SMEM_BYTES + FAST_TW_SLOTS * 8 + 16;
-// column passes stage only 256 twiddles: 39 KB per CTA and a 64-register cap give 4 CTAs/SM (col pass 94 -> 89 us per 380 limbs)
+// column passes: [data tile | 256 staged twiddles (F64 path) | mbarrier] = 39 KB per CTA; with a 64-register cap 4 CTAs/SM
 #ifndef FAST_COL_CTAS
 #define FAST_COL_CTAS 4
 #endif
 constexpr int COL_TW_SLOTS = 256;
-// "hybrid" block passes (B >= 7): only the twiddles that threads share (the first four stages of the pass) are staged;
-// the later stages' twiddles are used by exactly one thread each and are read from L2 directly -- 41 KB per CTA, 4 CTAs/SM
-constexpr int HYB_TW_SLOTS = 512;
-constexpr int HYB_SMEM_BYTES = SMEM_BYTES + HYB_TW_SLOTS * 8 + 16;
 constexpr int COL_SMEM_BYTES = SMEM_BYTES + COL_TW_SLOTS * 8 + 16;
+// block passes: the (warp-private) exchange buffer only
+#ifndef FAST_BLK_CTAS
+#define FAST_BLK_CTAS 4
+#endif
+constexpr int BLK_SMEM_BYTES = SMEM_BYTES;
 
-template <class TW>
-struct TwSharedBlock {   // block pass: stage j (global stage 8+j) holds 2^(j+unit_log) twiddles, stages back to back
-    const TW* base;
-    int unit_log, j0;
-    unsigned pre;
-    static constexpr bool SMEM = true;
-    __device__ __forceinline__ const TW* run(int i) const {
-        return base + (((1u << (j0 + i)) - 1u) << unit_log) + (pre << i);
-    }
-};
 template <class TW>
 struct TwSharedCol {     // column pass: the first 256 table entries, indexed exactly like the global table
     const TW* base;
@@ -486,38 +498,7 @@ struct TwSharedCol {     // column pass: the first 256 table entries, indexed ex
     __device__ __forceinline__ const TW* run(int i) const { return base + (1u << (j0 + i)) + (pre << i); }
 };
 
-// one thread arms the barrier and issues the bulk copies; everybody waits right before the first use
-__device__ __forceinline__ void stage_block_twiddles(const double* __restrict__ W, double* tws, uint64_t* bar, int B,
-                                                     unsigned chunk) {
-    if (threadIdx.x == 0) {
-        mbar_init(bar, 1);
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const int unit_log = 12 - B;
-        mbar_expect_tx(bar, (unsigned)(((1u << 12) - (1u << unit_log)) * 8u));
-        for (int j = 0; j < B; ++j) {
-            const unsigned cnt = 1u << (j + unit_log);
-            tma_bulk_g2s(tws + (((1u << j) - 1u) << unit_log), W + (1u << (8 + j)) + (size_t)chunk * cnt, cnt * 8u, bar);
-        }
-    }
-}
-// the first `nst` stages only (the shared ones; the unshared twiddles of the later stages then come straight from L2)
-__device__ __forceinline__ void stage_block_twiddles_first(const double* __restrict__ W, double* tws, uint64_t* bar, int B,
-                                                           unsigned chunk, int nst) {
-    if (threadIdx.x == 0) {
-        mbar_init(bar, 1);
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const int unit_log = 12 - B;
-        mbar_expect_tx(bar, (unsigned)((((1u << nst) - 1u) << unit_log) * 8u));
-        for (int j = 0; j < nst; ++j) {
-            const unsigned cnt = 1u << (j + unit_log);
-            tma_bulk_g2s(tws + (((1u << j) - 1u) << unit_log), W + (1u << (8 + j)) + (size_t)chunk * cnt, cnt * 8u, bar);
-        }
-    }
-}
+// one thread arms the barrier and issues the bulk copy; everybody waits right before the first use
 __device__ __forceinline__ void stage_col_twiddles(const double* __restrict__ W, double* tws, uint64_t* bar) {
     if (threadIdx.x == 0) {
         mbar_init(bar, 1);
@@ -595,7 +576,7 @@ __device__ __forceinline__ void fast_fwd_col_body(const FastArgs& F, const Resca
     using TW = typename A::TW;
     const int tau = threadIdx.x;
     const int b = F.logN - 8;
-    const typename A::C c = make_const<A>((uint64_t)F.q[limb]);
+    const typename A::C c = make_const<A>(F, limb);
     int64_t* __restrict__ row0 = F.a + drow * F.a_stride + (long long)grid_chunk(F) * 16;
     const TW* __restrict__ W = tw_row<A>(F, limb);
     TW* tws = reinterpret_cast<TW*>(sm + SMEM_SLOTS);
@@ -644,7 +625,6 @@ __device__ __forceinline__ void fast_fwd_col_body(const FastArgs& F, const Resca
 template <int DUMMY>
 __global__ void __launch_bounds__(NTT_THREADS, FAST_COL_CTAS) fast_fwd_colpass(const FastArgs F) {
     extern __shared__ __align__(16) int64_t sm[];
-    if (fast_skip_own(F)) return;
     const RowId rid = fast_row(F);
     const int limb = rid.limb;
     const RescaleIn none{};
@@ -689,7 +669,7 @@ struct ExtArgs {
     int64_t* out;                       // [P*E][N], row p*E + t
     int E, N;
     int raw;                            // scale-prime targets are written as raw doubles (read back with in_raw)
-    const int32_t* own_row0;            // [P] or nullptr: first own target limb of each partition (skipped), < 0 = none
+    const double* qinv;                 // [E] 1/q_t, or nullptr
 };
 
 // per-target constants of the extension staged once per CTA (q, 1/q, 2^31 mod q, the Horner multipliers): a thread
@@ -704,7 +684,6 @@ template <int AMAX>
 __device__ __forceinline__ void ext_target(const ExtArgs& X, const ExtShared& S, int p, int t, int tl, int alpha, bool wide,
                                            const longlong2 (&s)[AMAX], const double (&dx)[AMAX], const double (&dy)[AMAX],
                                            const int64_t* __restrict__ le, int64_t* __restrict__ out) {
-    if (own_target(X.own_row0, X.alphas, p, t)) return;   // the key switch takes this row from the tensor product
     longlong2 r;
     if (S.q[tl] < (double)SMALL_PRIME_LIMIT) {
         const F64C c{S.q[tl], S.qinv[tl]};
@@ -760,7 +739,7 @@ __global__ void __launch_bounds__(256) k_extend_fast(const ExtArgs X, int t0, in
         for (int i = threadIdx.x; i < t1 - t0; i += blockDim.x) {
             const double q = (double)(uint64_t)X.q[t0 + i];
             S.q[i] = q;
-            S.qinv[i] = 1.0 / q;
+            S.qinv[i] = X.qinv ? X.qinv[t0 + i] : 1.0 / q;
             S.c31[i] = X.C31[t0 + i];
 #pragma unroll
             for (int k = 0; k < 7; ++k) S.hm[k][i] = (k < alpha - 1 && k < AMAX - 1) ? hm[(long long)k * X.E + t0 + i] : 0.0;
@@ -809,8 +788,7 @@ struct InnerArgs {
     const int64_t *q, *_2q, *ql, *qh, *kl, *kh;
     int P, E, N, t0;
     int raw;                            // scale-prime rows: ext holds raw doubles and acc is written as raw doubles
-    const int32_t *own_row0, *alphas;   // [P] own target rows of each partition (see FastArgs), or nullptr
-    const int64_t* d2hat;               // [L][N] NTT-domain d2 = NTT(X) R (lazy integers) used for the own rows
+    const double* qinv;                 // [E] 1/q_t, or nullptr
 };
 
 __global__ void __launch_bounds__(256) k_ksk_inner_fast(const InnerArgs X) {
@@ -820,22 +798,14 @@ __global__ void __launch_bounds__(256) k_ksk_inner_fast(const InnerArgs X) {
     const uint64_t q = (uint64_t)X.q[t];
     longlong2 r0, r1;
     if (q < SMALL_PRIME_LIMIT) {
-        const F64C c{(double)q, 1.0 / (double)q};
+        const F64C c{(double)q, X.qinv ? X.qinv[t] : 1.0 / (double)q};
         double a0x = 0.0, a0y = 0.0, a1x = 0.0, a1y = 0.0;
         for (int p = 0; p < X.P; ++p) {
-            const bool own = own_target(X.own_row0, X.alphas, p, t);
-            const longlong2 e = own ? *reinterpret_cast<const longlong2*>(X.d2hat + (long long)t * X.N + j)
-                                    : *reinterpret_cast<const longlong2*>(X.ext + ((long long)p * X.E + t) * X.N + j);
+            const longlong2 e = *reinterpret_cast<const longlong2*>(X.ext + ((long long)p * X.E + t) * X.N + j);
             const longlong2 u = *reinterpret_cast<const longlong2*>(X.k0[p] + (long long)t * X.k_stride + j);
             const longlong2 v = *reinterpret_cast<const longlong2*>(X.k1[p] + (long long)t * X.k_stride + j);
-            double ex, ey;
-            if (own) {   // d2hat carries the Montgomery factor; the extended rows of this kernel are plain
-                ex = f64_mulmod(i2d(e.x), X.Rinv[t], c);
-                ey = f64_mulmod(i2d(e.y), X.Rinv[t], c);
-            } else {
-                ex = X.raw ? __longlong_as_double(e.x) : i2d(e.x);
-                ey = X.raw ? __longlong_as_double(e.y) : i2d(e.y);
-            }
+            const double ex = X.raw ? __longlong_as_double(e.x) : i2d(e.x);
+            const double ey = X.raw ? __longlong_as_double(e.y) : i2d(e.y);
             a0x = __dadd_rn(a0x, f64_mulmod(ex, i2d(u.x), c));
             a0y = __dadd_rn(a0y, f64_mulmod(ey, i2d(u.y), c));
             a1x = __dadd_rn(a1x, f64_mulmod(ex, i2d(v.x), c));
@@ -856,9 +826,7 @@ __global__ void __launch_bounds__(256) k_ksk_inner_fast(const InnerArgs X) {
         r0 = make_longlong2(0, 0);
         r1 = make_longlong2(0, 0);
         for (int p = 0; p < X.P; ++p) {
-            const bool own = own_target(X.own_row0, X.alphas, p, t);
-            const longlong2 e = own ? *reinterpret_cast<const longlong2*>(X.d2hat + (long long)t * X.N + j)
-                                    : *reinterpret_cast<const longlong2*>(X.ext + ((long long)p * X.E + t) * X.N + j);
+            const longlong2 e = *reinterpret_cast<const longlong2*>(X.ext + ((long long)p * X.E + t) * X.N + j);
             const longlong2 u = *reinterpret_cast<const longlong2*>(X.k0[p] + (long long)t * X.k_stride + j);
             const longlong2 v = *reinterpret_cast<const longlong2*>(X.k1[p] + (long long)t * X.k_stride + j);
             r0.x = lazy_add(r0.x, mont_mul_ss(e.x, u.x, k.q4, k.k), q2);
@@ -886,6 +854,7 @@ struct ModDownArgs {
     const double* C31;                  // [E]
     const int64_t* q;
     int L, K, E, N;
+    const double* qinv;                 // [E] 1/q_t, or nullptr
 };
 
 __global__ void __launch_bounds__(256) k_moddown_fast(const ModDownArgs X) {
@@ -893,7 +862,7 @@ __global__ void __launch_bounds__(256) k_moddown_fast(const ModDownArgs X) {
     const long long j = 2ll * (blockIdx.x * 256 + threadIdx.x);
     if (j >= X.N) return;
     const uint64_t q = (uint64_t)X.q[t];
-    const F64C c{(double)q, 1.0 / (double)q};
+    const F64C c{(double)q, X.qinv ? X.qinv[t] : 1.0 / (double)q};
     const double c31 = X.C31[t];
     const longlong2 dv = *reinterpret_cast<const longlong2*>(X.d + (long long)t * X.N + j);
     double vx = i2d(dv.x), vy = i2d(dv.y);
@@ -917,20 +886,80 @@ __global__ void __launch_bounds__(256) k_moddown_fast(const ModDownArgs X) {
     *reinterpret_cast<longlong2*>(X.out + (long long)t * X.out_stride + j) = r;
 }
 
-// ---- forward pass B (block pass, stages 8..logN-1), canonical [0,q) out --------------------------------------
-template <class A, int B, bool STAGED>
+// ---- block passes (forward stages 8..logN-1 / inverse levels 0..B-1), WARP-INDEPENDENT ---------------------------------
+// The stages of a block pass only mix coefficients inside 2^B-point sub-blocks (B <= 9), i.e. inside the 512 contiguous
+// coefficients a warp owns (32 threads x 16).  Every exchange therefore stays inside the warp's private slice of the
+// exchange buffer and needs __syncwarp() only -- no CTA barrier anywhere, so the 8 warps of a CTA drift apart and keep
+// the FP64 pipe fed while others wait on loads.  Twiddles go straight from L2 to registers: the stages whose twiddles
+// several threads share are broadcast loads from the plain table, the last group (one thread per twiddle) comes from the
+// PACKED table as lane-contiguous 128-bit loads.  Nothing is staged through shared memory, no mbarrier, no prologue
+// barrier: round 1 profiling showed the L1 data pipe (75-83 % busy, 80 % of it global accesses that touch up to 32 lines
+// per warp instruction), not shared memory, to be what the FP64 pipe was waiting for.
+//
+// The thread that ends (forward) / starts (inverse) with coefficients 16 t .. 16 t + 15 of the tile moves them either as
+// four 256-bit accesses (natural order) or, with F.perm, as eight lane-contiguous 128-bit accesses (warp-interleaved order).
+template <class T>
+__device__ __forceinline__ void tile_store16(int64_t* __restrict__ g, const int64_t (&r)[16], int tau, int perm) {
+    if (perm) {
+        longlong2* __restrict__ o = reinterpret_cast<longlong2*>(g + (tau >> 5) * PACK_TILE) + (tau & 31);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j * 32] = make_longlong2(r[2 * j], r[2 * j + 1]);
+    } else {
+        int64_t* o = g + tau * 16;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) stg256(o, r, j);
+    }
+}
+__device__ __forceinline__ void tile_load16(const int64_t* __restrict__ g, int64_t (&r)[16], int tau, int perm) {
+    if (perm) {
+        const longlong2* __restrict__ in = reinterpret_cast<const longlong2*>(g + (tau >> 5) * PACK_TILE) + (tau & 31);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const longlong2 v = in[j * 32];
+            r[2 * j] = v.x;
+            r[2 * j + 1] = v.y;
+        }
+    } else {
+        const int64_t* in = g + tau * 16;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) ldg256(in, r, j);
+    }
+}
+
+// the round on field [3:0] (a thread's 16 contiguous coefficients): packed twiddles when the table is there
+template <class A, int FIRST>
+__device__ __forceinline__ void fast_fwd_last_round(typename A::T (&e)[16], const FastArgs& F, int limb, unsigned chunk,
+                                                    const typename A::C& c) {
+    using TW = typename A::TW;
+    const int tau = threadIdx.x;
+    const TW* __restrict__ WP = twp_row<A>(F, limb);
+    if (WP)
+        fast_fwd_round<A, FIRST>(e, TwPacked<TW>{WP + ((long long)(chunk * 8u + (unsigned)(tau >> 5))) * PACK_TILE, tau & 31}, c);
+    else
+        fast_fwd_round<A, FIRST>(e, TwGlobal<TW>{tw_row<A>(F, limb), F.logN - 4, (chunk << 8) | (unsigned)tau}, c);
+}
+template <class A>
+__device__ __forceinline__ void fast_inv_first_round(typename A::T (&e)[16], const FastArgs& F, int limb, unsigned chunk,
+                                                     const typename A::C& c) {
+    using TW = typename A::TW;
+    const int tau = threadIdx.x;
+    const TW* __restrict__ WP = twp_row<A>(F, limb);
+    if (WP)
+        fast_inv_round<A, 4>(e, TwPacked<TW>{WP + ((long long)(chunk * 8u + (unsigned)(tau >> 5))) * PACK_TILE, tau & 31}, c);
+    else
+        fast_inv_round<A, 4>(e, TwGlobal<TW>{tw_row<A>(F, limb), F.logN - 4, (chunk << 8) | (unsigned)tau}, c);
+}
+
+template <class A, int B>
 __device__ __forceinline__ void fast_fwd_block_body(const FastArgs& F, int64_t* sm, int limb, long long drow) {
     using T = typename A::T;
     using TW = typename A::TW;
     const int tau = threadIdx.x;
     const unsigned chunk = grid_chunk(F);
     constexpr int logN = B + 8;
-    const typename A::C c = make_const<A>((uint64_t)F.q[limb]);
+    const typename A::C c = make_const<A>(F, limb);
     int64_t* __restrict__ g = F.a + drow * F.a_stride + (long long)chunk * TILE;
     const TW* __restrict__ W = tw_row<A>(F, limb);
-    TW* tws = reinterpret_cast<TW*>(sm + SMEM_SLOTS);
-    uint64_t* bar = reinterpret_cast<uint64_t*>(sm + SMEM_SLOTS + FAST_TW_SLOTS);
-    if constexpr (STAGED) stage_block_twiddles(reinterpret_cast<const double*>(W), reinterpret_cast<double*>(tws), bar, B, chunk);
     if (tau == 32) {
         unsigned ca = 0;
         const long long ra = F.prefetch ? fast_row_ahead(F, F.prefetch, ca) : -1;
@@ -942,772 +971,82 @@ __device__ __forceinline__ void fast_fwd_block_body(const FastArgs& F, int64_t* 
         const int zb = zbase(tau, P1);
 #pragma unroll
         for (int k = 0; k < 16; ++k) e[k] = A::load_mid(g[zb | (k << P1)]);
-        if constexpr (STAGED) {
-            mbar_wait(bar, 0);
-            fast_fwd_round<A, 0>(e, TwSharedBlock<TW>{tws, 12 - B, 0, (unsigned)(tau >> P1)}, c);
-        } else {
-            fast_fwd_round<A, 0>(e, TwGlobal<TW>{W, logN - 4 - P1, (chunk << (8 - P1)) | (unsigned)(tau >> P1)}, c);
-        }
     }
-    if constexpr (B >= 8) {
-        constexpr int P2 = B - 8;
-        smx_store(sm, e, tau, P1);
-        __syncthreads();
-        smx_load(sm, e, tau, P2);
-        if constexpr (STAGED)
-            fast_fwd_round<A, 0>(e, TwSharedBlock<TW>{tws, 12 - B, 4, (unsigned)(tau >> P2)}, c);
-        else
-            fast_fwd_round<A, 0>(e, TwGlobal<TW>{W, logN - 4 - P2, (chunk << (8 - P2)) | (unsigned)(tau >> P2)}, c);
-        if constexpr (B == 9) {
-            __syncthreads();
-            smx_store(sm, e, tau, P2);
-            __syncthreads();
-            smx_load(sm, e, tau, 0);
-            if constexpr (STAGED)
-                fast_fwd_round<A, 3>(e, TwSharedBlock<TW>{tws, 12 - B, B - 4, (unsigned)tau}, c);
-            else
-                fast_fwd_round<A, 3>(e, TwGlobal<TW>{W, logN - 4, (chunk << 8) | (unsigned)tau}, c);
-        }
-        __syncthreads();
-    } else if constexpr (B > 4) {
-        smx_store(sm, e, tau, P1);
-        __syncthreads();
-        smx_load(sm, e, tau, 0);
-        if constexpr (STAGED)
-            fast_fwd_round<A, 8 - B>(e, TwSharedBlock<TW>{tws, 12 - B, B - 4, (unsigned)tau}, c);
-        else
-            fast_fwd_round<A, 8 - B>(e, TwGlobal<TW>{W, logN - 4, (chunk << 8) | (unsigned)tau}, c);
-        __syncthreads();
-    }
-    {   // canonical values back through shared memory for coalesced 128-bit stores
-        int64_t r[16];
-#pragma unroll
-        for (int k = 0; k < 16; ++k) r[k] = A::store_out(e[k], c, F.out_raw);
-        sm_store_field(sm, r, tau, 0);
-    }
-    __syncthreads();
-    sm_to_global(sm, g, tau);
-}
-
-// ---- forward pass B, WARP-INDEPENDENT form -------------------------------------------------------------------------
-// Stages 8..logN-1 only mix coefficients inside 2^B-point sub-blocks (B <= 9), i.e. inside the 512 contiguous
-// coefficients a warp owns (32 threads x 16).  Every exchange therefore stays inside the warp's private slice of the
-// exchange buffer and needs __syncwarp() only -- no CTA barrier anywhere, so the 8 warps of a CTA drift apart and keep
-// the FP64 pipe fed while others wait on loads.  After the last round a thread holds 16 contiguous coefficients,
-// which leave as four 256-bit stores (no staging pass through shared memory).
-template <class A, int B, bool STAGED, bool HYB = false>
-__device__ __forceinline__ void fast_fwd_block_body_w(const FastArgs& F, int64_t* sm, int limb, long long drow) {
-    using T = typename A::T;
-    using TW = typename A::TW;
-    const int tau = threadIdx.x;
-    const unsigned chunk = grid_chunk(F);
-    constexpr int logN = B + 8;
-    constexpr bool S2 = STAGED && !HYB;   // rounds after the first take their twiddles from shared memory
-    const typename A::C c = make_const<A>((uint64_t)F.q[limb]);
-    int64_t* __restrict__ g = F.a + drow * F.a_stride + (long long)chunk * TILE;
-    const TW* __restrict__ W = tw_row<A>(F, limb);
-    TW* tws = reinterpret_cast<TW*>(sm + SMEM_SLOTS);
-    uint64_t* bar = reinterpret_cast<uint64_t*>(sm + SMEM_SLOTS + (HYB ? HYB_TW_SLOTS : FAST_TW_SLOTS));
-    if constexpr (STAGED && HYB)
-        stage_block_twiddles_first(reinterpret_cast<const double*>(W), reinterpret_cast<double*>(tws), bar, B, chunk, 4);
-    else if constexpr (STAGED)
-        stage_block_twiddles(reinterpret_cast<const double*>(W), reinterpret_cast<double*>(tws), bar, B, chunk);
-    if (tau == 32) {
-        unsigned ca = 0;
-        const long long ra = F.prefetch ? fast_row_ahead(F, F.prefetch, ca) : -1;
-        if (ra >= 0) l2_prefetch_bulk(F.a + ra * F.a_stride + (long long)ca * TILE, TILE * 8u);
-    }
-    T e[16];
-    constexpr int P1 = B - 4;
-    {
-        const int zb = zbase(tau, P1);
-#pragma unroll
-        for (int k = 0; k < 16; ++k) e[k] = A::load_mid(g[zb | (k << P1)]);
-        if constexpr (STAGED) {
-            mbar_wait(bar, 0);
-            fast_fwd_round<A, 0>(e, TwSharedBlock<TW>{tws, 12 - B, 0, (unsigned)(tau >> P1)}, c);
-        } else {
-            fast_fwd_round<A, 0>(e, TwGlobal<TW>{W, logN - 4 - P1, (chunk << (8 - P1)) | (unsigned)(tau >> P1)}, c);
-        }
-    }
-    if constexpr (B >= 8) {
-        constexpr int P2 = B - 8;
-        smx_store(sm, e, tau, P1);
-        __syncwarp();
-        smx_load(sm, e, tau, P2);
-        if constexpr (S2)
-            fast_fwd_round<A, 0>(e, TwSharedBlock<TW>{tws, 12 - B, 4, (unsigned)(tau >> P2)}, c);
-        else
-            fast_fwd_round<A, 0>(e, TwGlobal<TW>{W, logN - 4 - P2, (chunk << (8 - P2)) | (unsigned)(tau >> P2)}, c);
-        if constexpr (B == 9) {
-            __syncwarp();
-            smx_store(sm, e, tau, P2);
-            __syncwarp();
-            smx_load(sm, e, tau, 0);
-            if constexpr (S2)
-                fast_fwd_round<A, 3>(e, TwSharedBlock<TW>{tws, 12 - B, B - 4, (unsigned)tau}, c);
-            else
-                fast_fwd_round<A, 3>(e, TwGlobal<TW>{W, logN - 4, (chunk << 8) | (unsigned)tau}, c);
-        }
-    } else if constexpr (B > 4) {
-        smx_store(sm, e, tau, P1);
-        __syncwarp();
-        smx_load(sm, e, tau, 0);
-        if constexpr (S2)
-            fast_fwd_round<A, 8 - B>(e, TwSharedBlock<TW>{tws, 12 - B, B - 4, (unsigned)tau}, c);
-        else
-            fast_fwd_round<A, 8 - B>(e, TwGlobal<TW>{W, logN - 4, (chunk << 8) | (unsigned)tau}, c);
-    }
-    {   // the thread's 16 contiguous canonical coefficients: four full-sector 256-bit stores
-        int64_t r[16];
-#pragma unroll
-        for (int k = 0; k < 16; ++k) r[k] = A::store_out(e[k], c, F.out_raw);
-        int64_t* o = g + tau * 16;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) stg256(o, r, j);
-    }
-}
-
-template <int B>
-__global__ void __launch_bounds__(NTT_THREADS, FAST_CTAS_PER_SM) fast_fwd_blockpass_w(const FastArgs F) {
-    extern __shared__ __align__(16) int64_t sm[];
-    if (fast_skip_own(F)) return;
-    const RowId rid = fast_row(F);
-    const int limb = rid.limb;
-    if (fast_use_f64(F, rid))
-        fast_fwd_block_body_w<ArithF64, B, true>(F, sm, limb, rid.data_row);
-    else
-        fast_fwd_block_body_w<ArithU64, B, false>(F, sm, limb, rid.data_row);
-}
-
-template <int B>
-__global__ void __launch_bounds__(NTT_THREADS, 4) fast_fwd_blockpass_h(const FastArgs F) {
-    extern __shared__ __align__(16) int64_t sm[];
-    if (fast_skip_own(F)) return;
-    const RowId rid = fast_row(F);
-    const int limb = rid.limb;
-    if (fast_use_f64(F, rid))
-        fast_fwd_block_body_w<ArithF64, B, true, true>(F, sm, limb, rid.data_row);
-    else
-        fast_fwd_block_body_w<ArithU64, B, false, true>(F, sm, limb, rid.data_row);
-}
-
-template <int B>
-__global__ void __launch_bounds__(NTT_THREADS, FAST_CTAS_PER_SM) fast_fwd_blockpass(const FastArgs F) {
-    extern __shared__ __align__(16) int64_t sm[];
-    if (fast_skip_own(F)) return;
-    const RowId rid = fast_row(F);
-    const int limb = rid.limb;
-    if (fast_use_f64(F, rid))
-        fast_fwd_block_body<ArithF64, B, true>(F, sm, limb, rid.data_row);
-    else
-        fast_fwd_block_body<ArithU64, B, false>(F, sm, limb, rid.data_row);
-}
-
-// ---- PERSISTENT forward block pass: TMA double-buffered tiles ----------------------------------------------------
-// One CTA walks a contiguous range of tiles.  While tile i is being transformed out of registers, the 32 KB of
-// tile i+1 are already in flight (one cp.async.bulk into the other buffer, completion on an mbarrier), so the
-// DRAM/L2 latency that the one-tile-per-CTA kernels expose at every CTA start is hidden behind compute.  Tiles are
-// ordered so that consecutive tiles share (limb, chunk): the staged twiddles are reused by all G rows of a batch
-// that belong to the same limb (the P partitions of a key switch, the 4 polynomials of a tensor stage, ...).
-struct TileId {
-    long long drow;
-    int limb, chunk, group;
-};
-__device__ __forceinline__ TileId decode_tile(const FastArgs& F, long long id, int G, int chunks) {
-    const int group = (int)(id / G), g = (int)(id - (long long)group * G);
-    const int m = group / chunks, chunk = group - m * chunks;
-    TileId t;
-    t.group = group;
-    t.chunk = chunk;
-    if (F.slab_rows == 0) {
-        t.limb = m;
-        t.drow = (long long)g * F.period + m;
+    if constexpr (B == 4) {
+        fast_fwd_last_round<A, 0>(e, F, limb, chunk, c);
     } else {
-        t.limb = F.slab_t0 + m;
-        t.drow = (long long)g * F.group_rows + F.slab_t0 + m;
-    }
-    return t;
-}
-__device__ __forceinline__ TileId decode_tile32(const FastArgs& F, int id, int G, int chunks) {   // 32-bit index maths
-    const int group = id / G, g = id - group * G;
-    const int m = group / chunks, chunk = group - m * chunks;
-    TileId t;
-    t.group = group;
-    t.chunk = chunk;
-    if (F.slab_rows == 0) {
-        t.limb = m;
-        t.drow = (long long)g * F.period + m;
-    } else {
-        t.limb = F.slab_t0 + m;
-        t.drow = (long long)g * F.group_rows + F.slab_t0 + m;
-    }
-    return t;
-}
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-// persistent kernel shared memory:
-// [exchange buffer (padded tile) | PERSIST_SLOTS raw tile slots | 2 twiddle stages | mbarriers]
-constexpr int PERSIST_SLOTS = 3;
-constexpr int PERSIST_SMEM_BYTES = SMEM_BYTES + PERSIST_SLOTS * TILE * 8 + 2 * FAST_TW_SLOTS * 8 + 64;
-
-template <class A, int B, bool STAGED>
-__device__ __forceinline__ void persist_fwd_block_compute(const FastArgs& F, typename A::T (&e)[16], int64_t* xb,
-                                                          const typename A::TW* tws, const TileId& tl,
-                                                          int64_t* __restrict__ gout) {
-    using TW = typename A::TW;
-    const int tau = threadIdx.x;
-    constexpr int logN = B + 8;
-    constexpr int P1 = B - 4;
-    const unsigned chunk = (unsigned)tl.chunk;
-    const typename A::C c = make_const<A>((uint64_t)F.q[tl.limb]);
-    const TW* __restrict__ W = tw_row<A>(F, tl.limb);
-    if constexpr (STAGED)
-        fast_fwd_round<A, 0>(e, TwSharedBlock<TW>{tws, 12 - B, 0, (unsigned)(tau >> P1)}, c);
-    else
         fast_fwd_round<A, 0>(e, TwGlobal<TW>{W, logN - 4 - P1, (chunk << (8 - P1)) | (unsigned)(tau >> P1)}, c);
-    if constexpr (B >= 8) {
-        constexpr int P2 = B - 8;
-        smx_store(xb, e, tau, P1);
-        __syncthreads();
-        smx_load(xb, e, tau, P2);
-        if constexpr (STAGED)
-            fast_fwd_round<A, 0>(e, TwSharedBlock<TW>{tws, 12 - B, 4, (unsigned)(tau >> P2)}, c);
-        else
-            fast_fwd_round<A, 0>(e, TwGlobal<TW>{W, logN - 4 - P2, (chunk << (8 - P2)) | (unsigned)(tau >> P2)}, c);
-        if constexpr (B == 9) {
-            __syncthreads();
-            smx_store(xb, e, tau, P2);
-            __syncthreads();
-            smx_load(xb, e, tau, 0);
-            if constexpr (STAGED)
-                fast_fwd_round<A, 3>(e, TwSharedBlock<TW>{tws, 12 - B, B - 4, (unsigned)tau}, c);
-            else
-                fast_fwd_round<A, 3>(e, TwGlobal<TW>{W, logN - 4, (chunk << 8) | (unsigned)tau}, c);
-        }
-        __syncthreads();
-    } else if constexpr (B > 4) {
-        smx_store(xb, e, tau, P1);
-        __syncthreads();
-        smx_load(xb, e, tau, 0);
-        if constexpr (STAGED)
-            fast_fwd_round<A, 8 - B>(e, TwSharedBlock<TW>{tws, 12 - B, B - 4, (unsigned)tau}, c);
-        else
-            fast_fwd_round<A, 8 - B>(e, TwGlobal<TW>{W, logN - 4, (chunk << 8) | (unsigned)tau}, c);
-        __syncthreads();
-    }
-    {
-        int64_t r[16];
-#pragma unroll
-        for (int k = 0; k < 16; ++k) r[k] = A::store_out(e[k], c, F.out_raw);
-        sm_store_field(xb, r, tau, 0);
-    }
-    __syncthreads();
-    sm_to_global(xb, gout, tau);
-}
-
-// One CTA per SM.  A ring of PERSIST_SLOTS raw tiles keeps the next tiles' loads (TMA bulk copies) in flight while
-// the current tile is transformed, and the twiddles of the NEXT (limb, chunk) group are staged into the second
-// twiddle buffer while the current group is processed: after the prologue no wait on L2/DRAM is exposed.
-template <int B>
-__global__ void __launch_bounds__(NTT_THREADS, 1) fast_fwd_blockpass_persist(const FastArgs F, long long total_tiles, int G) {
-    extern __shared__ __align__(16) int64_t sm[];
-    int64_t* xb = sm;
-    int64_t* ring = sm + SMEM_SLOTS;
-    double* tws = reinterpret_cast<double*>(ring + PERSIST_SLOTS * TILE);      // [2][FAST_TW_SLOTS]
-    uint64_t* bar_data = reinterpret_cast<uint64_t*>(tws + 2 * FAST_TW_SLOTS);  // [PERSIST_SLOTS]
-    uint64_t* bar_tw = bar_data + PERSIST_SLOTS;                               // [2]
-    const int tau = threadIdx.x;
-    constexpr int P1 = B - 4;
-    const int chunks = (1 << (B + 8)) / TILE;
-    const long long t_begin = total_tiles * blockIdx.x / gridDim.x;
-    const long long t_end = total_tiles * (blockIdx.x + 1) / gridDim.x;
-    if (t_begin >= t_end) return;
-    if (tau == 0) {
-        for (int i = 0; i < PERSIST_SLOTS; ++i) mbar_init(&bar_data[i], 1);
-        mbar_init(&bar_tw[0], 1);
-        mbar_init(&bar_tw[1], 1);
-    }
-    __syncthreads();
-    auto issue_data = [&](long long id, int slot) {   // thread 0 only
-        const TileId t = decode_tile(F, id, G, chunks);
-        const int64_t* src = F.a + t.drow * F.a_stride + (long long)t.chunk * TILE;
-        fence_async_smem();
-        mbar_expect_tx(&bar_data[slot], TILE * 8u);
-        tma_bulk_g2s(ring + slot * TILE, src, TILE * 8u, &bar_data[slot]);
-    };
-    auto group_staged = [&](int limb) { return (uint64_t)F.q[limb] < SMALL_PRIME_LIMIT && F.force_int != 1; };
-    auto issue_tw = [&](long long id, int tslot) {    // thread 0 only; id = first tile of the group
-        const TileId t = decode_tile(F, id, G, chunks);
-        if (!group_staged(t.limb)) return;
-        const double* W = F.tw_f64 + ((long long)t.limb << (B + 8));
-        const int unit_log = 12 - B;
-        double* dst = tws + tslot * FAST_TW_SLOTS;
-        fence_async_smem();
-        mbar_expect_tx(&bar_tw[tslot], (unsigned)(((1u << 12) - (1u << unit_log)) * 8u));
-        for (int j = 0; j < B; ++j) {
-            const unsigned cnt = 1u << (j + unit_log);
-            tma_bulk_g2s(dst + (((1u << j) - 1u) << unit_log), W + (1u << (8 + j)) + (size_t)t.chunk * cnt, cnt * 8u, &bar_tw[tslot]);
-        }
-    };
-    if (tau == 0) {
-        issue_tw(t_begin, 0);
-        for (int i = 0; i < PERSIST_SLOTS && t_begin + i < t_end; ++i) issue_data(t_begin + i, i);
-    }
-    long long cur_group = -1;
-    unsigned gcount = 0;            // groups seen by this CTA; group k stages into buffer k & 1
-    unsigned tw_w0 = 0, tw_w1 = 0;  // completed phases per twiddle buffer
-    unsigned it = 0;
-    for (int id = t_begin; id < t_end; ++id, ++it) {
-        const int slot = it % PERSIST_SLOTS;
-        const TileId tl = decode_tile(F, id, G, chunks);
-        const RowId rid{tl.drow, tl.limb};
-        const bool f64 = fast_use_f64(F, rid);
-        bool new_group = false;
-        if (tl.group != cur_group) {   // readers of buffer (gcount+1)&1 (two groups back) left at the loop-end barrier
-            cur_group = tl.group;
-            new_group = true;
-            const int next_first = (tl.group + 1) * G;
-            if (tau == 0 && next_first < t_end) issue_tw(next_first, (gcount + 1) & 1);
-            ++gcount;
-        }
-        const int tslot = (gcount - 1) & 1;
-        mbar_wait(&bar_data[slot], (it / PERSIST_SLOTS) & 1);
-        int64_t* gout = F.a + tl.drow * F.a_stride + (long long)tl.chunk * TILE;
-        const int64_t* raw = ring + slot * TILE;
-        const int zb = zbase(tau, P1);
-        if (new_group && group_staged(tl.limb)) {
-            mbar_wait(&bar_tw[tslot], (tslot ? tw_w1 : tw_w0) & 1);
-            if (tslot) ++tw_w1; else ++tw_w0;
-        }
-        if (f64) {
-            double e[16];
-#pragma unroll
-            for (int k = 0; k < 16; ++k) e[k] = ArithF64::load_mid(raw[zb | (k << P1)]);
-            __syncthreads();   // slot consumed
-            if (tau == 0 && id + PERSIST_SLOTS < t_end) issue_data(id + PERSIST_SLOTS, slot);
-            persist_fwd_block_compute<ArithF64, B, true>(F, e, xb, tws + tslot * FAST_TW_SLOTS, tl, gout);
+        smx_store(sm, e, tau, P1);
+        __syncwarp();
+        if constexpr (B >= 8) {
+            constexpr int P2 = B - 8;
+            smx_load(sm, e, tau, P2);
+            if constexpr (B == 8) {
+                fast_fwd_last_round<A, 0>(e, F, limb, chunk, c);
+            } else {
+                fast_fwd_round<A, 0>(e, TwGlobal<TW>{W, logN - 4 - P2, (chunk << (8 - P2)) | (unsigned)(tau >> P2)}, c);
+                __syncwarp();
+                smx_store(sm, e, tau, P2);
+                __syncwarp();
+                smx_load(sm, e, tau, 0);
+                fast_fwd_last_round<A, 3>(e, F, limb, chunk, c);
+            }
         } else {
-            uint64_t e[16];
-#pragma unroll
-            for (int k = 0; k < 16; ++k) e[k] = ArithU64::load_mid(raw[zb | (k << P1)]);
-            __syncthreads();
-            if (tau == 0 && id + PERSIST_SLOTS < t_end) issue_data(id + PERSIST_SLOTS, slot);
-            persist_fwd_block_compute<ArithU64, B, false>(F, e, xb, nullptr, tl, gout);
+            smx_load(sm, e, tau, 0);
+            fast_fwd_last_round<A, 8 - B>(e, F, limb, chunk, c);
         }
-        __syncthreads();   // exchange buffer free; on a group change the older twiddle buffer is free
-    }
-}
-
-// ---- PERSISTENT, SOFTWARE-PIPELINED forward block pass ("pp") ---------------------------------------------------------
-// The one-tile-per-CTA kernels run load -> compute -> store back to back in every CTA, and the CTAs of an SM fall
-// into step: the memory system is idle while they compute and the FP64 pipe is idle while they load (ncu: FP64 pipe
-// 42 % busy, no dominant stall).  Here a CTA walks a contiguous range of tiles and every thread PREFETCHES THE NEXT
-// TILE'S 16 COEFFICIENTS INTO REGISTERS before it transforms the current one, so the load latency of tile i+1 hides
-// behind the butterflies of tile i.  Warps are independent inside a tile (see fast_fwd_block_body_w): the only CTA
-// barrier is at a change of (limb, chunk) group, where the twiddle buffer of the group before last is handed back
-// to the TMA engine (twiddles are double-buffered and staged one group ahead).  Tiles are ordered so that the G
-// rows sharing a limb (the partitions of a key switch) are consecutive and reuse the staged twiddles.
-// Static split of the (limb-major) tile list over the persistent CTAs, by COST rather than by count: a tile of a
-// 60-bit limb (integer Shoup path) takes about PP_INT_WEIGHT times as long as an FP64 tile, and those limbs sit at
-// the end of the list -- an even split by count leaves the last CTAs with integer tiles only (measured: 35 % idle).
-constexpr int PP_INT_WEIGHT = 3;
-struct TileRange {
-    int begin, end;
-};
-__device__ __forceinline__ TileRange pp_tile_range(const FastArgs& F, int nlimbs, int tiles_per_limb) {
-    const int l0 = F.slab_rows ? F.slab_t0 : 0;
-    auto weight = [&](int l) { return ((uint64_t)F.q[l0 + l] < SMALL_PRIME_LIMIT && F.force_int != 1) ? 1 : PP_INT_WEIGHT; };
-    long long W = 0;
-    for (int l = 0; l < nlimbs; ++l) W += (long long)weight(l) * tiles_per_limb;
-    const long long lo = W * blockIdx.x / gridDim.x, hi = W * (blockIdx.x + 1) / gridDim.x;
-    auto to_tile = [&](long long x) {
-        long long acc = 0;
-        int tiles = 0;
-        for (int l = 0; l < nlimbs; ++l) {
-            const int w = weight(l);
-            const long long seg = (long long)w * tiles_per_limb;
-            if (x < acc + seg) return tiles + (int)((x - acc) / w);
-            acc += seg;
-            tiles += tiles_per_limb;
-        }
-        return tiles;
-    };
-    return TileRange{to_tile(lo), to_tile(hi)};
-}
-constexpr int PP_SMEM_BYTES = SMEM_BYTES + 2 * FAST_TW_SLOTS * 8 + 32;
-
-template <class A, int B, bool STAGED>
-__device__ __forceinline__ void pp_fwd_block_tile(const FastArgs& F, const int64_t (&raw)[16], int64_t* xb,
-                                                  const typename A::TW* tws, const TileId& tl, int64_t* __restrict__ g) {
-    using T = typename A::T;
-    using TW = typename A::TW;
-    const int tau = threadIdx.x;
-    constexpr int logN = B + 8;
-    constexpr int P1 = B - 4;
-    const unsigned chunk = (unsigned)tl.chunk;
-    const typename A::C c = make_const<A>((uint64_t)F.q[tl.limb]);
-    const TW* __restrict__ W = tw_row<A>(F, tl.limb);
-    T e[16];
-#pragma unroll
-    for (int k = 0; k < 16; ++k) e[k] = A::load_mid(raw[k]);
-    if constexpr (STAGED)
-        fast_fwd_round<A, 0>(e, TwSharedBlock<TW>{tws, 12 - B, 0, (unsigned)(tau >> P1)}, c);
-    else
-        fast_fwd_round<A, 0>(e, TwGlobal<TW>{W, logN - 4 - P1, (chunk << (8 - P1)) | (unsigned)(tau >> P1)}, c);
-    if constexpr (B >= 8) {
-        constexpr int P2 = B - 8;
-        __syncwarp();   // the warp's slice of the exchange buffer is free (previous tile fully read)
-        smx_store(xb, e, tau, P1);
-        __syncwarp();
-        smx_load(xb, e, tau, P2);
-        if constexpr (STAGED)
-            fast_fwd_round<A, 0>(e, TwSharedBlock<TW>{tws, 12 - B, 4, (unsigned)(tau >> P2)}, c);
-        else
-            fast_fwd_round<A, 0>(e, TwGlobal<TW>{W, logN - 4 - P2, (chunk << (8 - P2)) | (unsigned)(tau >> P2)}, c);
-        if constexpr (B == 9) {
-            __syncwarp();
-            smx_store(xb, e, tau, P2);
-            __syncwarp();
-            smx_load(xb, e, tau, 0);
-            if constexpr (STAGED)
-                fast_fwd_round<A, 3>(e, TwSharedBlock<TW>{tws, 12 - B, B - 4, (unsigned)tau}, c);
-            else
-                fast_fwd_round<A, 3>(e, TwGlobal<TW>{W, logN - 4, (chunk << 8) | (unsigned)tau}, c);
-        }
-    } else if constexpr (B > 4) {
-        __syncwarp();
-        smx_store(xb, e, tau, P1);
-        __syncwarp();
-        smx_load(xb, e, tau, 0);
-        if constexpr (STAGED)
-            fast_fwd_round<A, 8 - B>(e, TwSharedBlock<TW>{tws, 12 - B, B - 4, (unsigned)tau}, c);
-        else
-            fast_fwd_round<A, 8 - B>(e, TwGlobal<TW>{W, logN - 4, (chunk << 8) | (unsigned)tau}, c);
     }
     int64_t r[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) r[k] = A::store_out(e[k], c, F.out_raw);
-    int64_t* o = g + tau * 16;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) stg256(o, r, j);
-}
-
-// thread 0: stage the block-pass twiddles of (limb, chunk) into `dst` (FP64 rows only), completion on `bar`
-template <int B>
-__device__ __forceinline__ void pp_issue_block_twiddles(const FastArgs& F, int limb, int chunk, double* dst, uint64_t* bar) {
-    const double* W = F.tw_f64 + ((long long)limb << (B + 8));
-    constexpr int unit_log = 12 - B;
-    fence_async_smem();
-    mbar_expect_tx(bar, (unsigned)(((1u << 12) - (1u << unit_log)) * 8u));
-#pragma unroll
-    for (int j = 0; j < B; ++j) {
-        const unsigned cnt = 1u << (j + unit_log);
-        tma_bulk_g2s(dst + (((1u << j) - 1u) << unit_log), W + (1u << (8 + j)) + (size_t)chunk * cnt, cnt * 8u, bar);
-    }
+    tile_store16<T>(g, r, tau, F.perm);
 }
 
 template <int B>
-__global__ void __launch_bounds__(NTT_THREADS, 2) fast_fwd_blockpass_pp(const FastArgs F, long long total_tiles, int G) {
+__global__ void __launch_bounds__(NTT_THREADS, FAST_BLK_CTAS) fast_fwd_blockpass(const FastArgs F) {
     extern __shared__ __align__(16) int64_t sm[];
-    int64_t* xb = sm;
-    double* tws = reinterpret_cast<double*>(sm + SMEM_SLOTS);                   // [2][FAST_TW_SLOTS]
-    uint64_t* bar_tw = reinterpret_cast<uint64_t*>(tws + 2 * FAST_TW_SLOTS);    // [2]
-    const int tau = threadIdx.x;
-    constexpr int P1 = B - 4;
-    const int chunks = (1 << (B + 8)) / TILE;
-    const TileRange range = pp_tile_range(F, (int)(total_tiles / ((long long)chunks * G)), chunks * G);
-    const int t_begin = range.begin, t_end = range.end;
-    if (t_begin >= t_end) return;
-    auto staged = [&](int limb) { return (uint64_t)F.q[limb] < SMALL_PRIME_LIMIT && F.force_int != 1; };
-    if (tau == 0) {
-        mbar_init(&bar_tw[0], 1);
-        mbar_init(&bar_tw[1], 1);
-    }
-    __syncthreads();
-    const int zb = zbase(tau, P1);
-    int64_t nxt[16];
-    {
-        const TileId t0 = decode_tile32(F, t_begin, G, chunks);
-        if (tau == 0 && staged(t0.limb)) pp_issue_block_twiddles<B>(F, t0.limb, t0.chunk, tws, &bar_tw[0]);
-        const int64_t* __restrict__ src = F.a + t0.drow * F.a_stride + (long long)t0.chunk * TILE;
-#pragma unroll
-        for (int k = 0; k < 16; ++k) nxt[k] = src[zb | (k << P1)];
-    }
-    int cur_group = -1;
-    unsigned gcount = 0;                 // groups seen by this CTA; group k uses twiddle buffer k & 1
-    unsigned ph0 = 0, ph1 = 0;           // completed phases of the two twiddle barriers
-#pragma unroll 1
-    for (int id = t_begin; id < t_end; ++id) {
-        const TileId tl = decode_tile32(F, id, G, chunks);
-        int64_t cur[16];
-#pragma unroll
-        for (int k = 0; k < 16; ++k) cur[k] = nxt[k];
-        if (id + 1 < t_end) {            // prefetch the next tile while this one is transformed
-            const TileId tn = decode_tile32(F, id + 1, G, chunks);
-            const int64_t* __restrict__ src = F.a + tn.drow * F.a_stride + (long long)tn.chunk * TILE;
-#pragma unroll
-            for (int k = 0; k < 16; ++k) nxt[k] = src[zb | (k << P1)];
-        }
-        if (tl.group != cur_group) {
-            cur_group = tl.group;
-            __syncthreads();             // every warp is done with the group before: its twiddle buffer can be refilled
-            const int next_first = (tl.group + 1) * G;
-            if (tau == 0 && next_first < t_end) {
-                const TileId tg = decode_tile32(F, next_first, G, chunks);
-                if (staged(tg.limb)) pp_issue_block_twiddles<B>(F, tg.limb, tg.chunk, tws + ((gcount + 1) & 1) * FAST_TW_SLOTS, &bar_tw[(gcount + 1) & 1]);
-            }
-            if (staged(tl.limb)) {
-                const unsigned b = gcount & 1;
-                mbar_wait(&bar_tw[b], (b ? ph1 : ph0) & 1);
-                if (b) ++ph1; else ++ph0;
-            }
-            ++gcount;
-        }
-        const unsigned tb = (gcount - 1) & 1;
-        int64_t* gout = F.a + tl.drow * F.a_stride + (long long)tl.chunk * TILE;
-        const RowId rid{tl.drow, tl.limb};
-        if (fast_use_f64(F, rid))
-            pp_fwd_block_tile<ArithF64, B, true>(F, cur, xb, tws + tb * FAST_TW_SLOTS, tl, gout);
-        else
-            pp_fwd_block_tile<ArithU64, B, false>(F, cur, xb, nullptr, tl, gout);
-    }
+    const RowId rid = fast_row(F);
+    if (fast_use_f64(F, rid))
+        fast_fwd_block_body<ArithF64, B>(F, sm, rid.limb, rid.data_row);
+    else
+        fast_fwd_block_body<ArithU64, B>(F, sm, rid.limb, rid.data_row);
 }
 
-// ---- inverse pass B' (levels 0..B-1) ---------------------------------------------------------------------------
-template <class A, int B, bool STAGED>
+// inverse: for B == 9 the last level (distance 256) is taken as the top stage of field [8:5], which keeps it warp-private too
+template <class A, int B>
 __device__ __forceinline__ void fast_inv_block_body(const FastArgs& F, int64_t* sm, int limb, long long drow) {
     using T = typename A::T;
     using TW = typename A::TW;
     const int tau = threadIdx.x;
     const unsigned chunk = grid_chunk(F);
     constexpr int logN = B + 8;
-    const typename A::C c = make_const<A>((uint64_t)F.q[limb]);
+    const typename A::C c = make_const<A>(F, limb);
     int64_t* __restrict__ g = F.a + drow * F.a_stride + (long long)chunk * TILE;
     const TW* __restrict__ W = tw_row<A>(F, limb);
-    TW* tws = reinterpret_cast<TW*>(sm + SMEM_SLOTS);
-    uint64_t* bar = reinterpret_cast<uint64_t*>(sm + SMEM_SLOTS + FAST_TW_SLOTS);
-    if constexpr (STAGED) stage_block_twiddles(reinterpret_cast<const double*>(W), reinterpret_cast<double*>(tws), bar, B, chunk);
     if (tau == 32) {
         unsigned ca = 0;
         const long long ra = F.prefetch ? fast_row_ahead(F, F.prefetch, ca) : -1;
         if (ra >= 0) l2_prefetch_bulk(F.a + ra * F.a_stride + (long long)ca * TILE, TILE * 8u);
     }
     T e[16];
-    global_to_sm(sm, g, tau);
-    __syncthreads();
     {
         int64_t r[16];
-        sm_load_field(sm, r, tau, 0);
+        tile_load16(g, r, tau, F.perm);
 #pragma unroll
         for (int k = 0; k < 16; ++k) e[k] = A::load_in(r[k], F.in_raw);
     }
-    if constexpr (STAGED) {
-        mbar_wait(bar, 0);
-        fast_inv_round<A, 4>(e, TwSharedBlock<TW>{tws, 12 - B, B - 4, (unsigned)tau}, c);
-    } else {
-        fast_inv_round<A, 4>(e, TwGlobal<TW>{W, logN - 4, (chunk << 8) | (unsigned)tau}, c);
-    }
+    fast_inv_first_round<A>(e, F, limb, chunk, c);
     if constexpr (B == 4) {
         int64_t r[16];
 #pragma unroll
         for (int k = 0; k < 16; ++k) r[k] = A::store_mid(e[k], c);
-        __syncthreads();
-        sm_store_field(sm, r, tau, 0);
-        __syncthreads();
-        sm_to_global(sm, g, tau);
-    } else {
-        __syncthreads();
-        smx_store(sm, e, tau, 0);
-        __syncthreads();
-        smx_load(sm, e, tau, 4);
-        constexpr int NST = (B >= 8) ? 4 : B - 4;
-        if constexpr (STAGED)
-            fast_inv_round<A, NST>(e, TwSharedBlock<TW>{tws, 12 - B, B - 8, (unsigned)(tau >> 4)}, c);
-        else
-            fast_inv_round<A, NST>(e, TwGlobal<TW>{W, logN - 8, (chunk << 4) | (unsigned)(tau >> 4)}, c);
-        if constexpr (B == 9) {
-            __syncthreads();
-            smx_store(sm, e, tau, 4);
-            __syncthreads();
-            smx_load(sm, e, tau, 8);
-            if constexpr (STAGED)
-                fast_inv_round<A, 1>(e, TwSharedBlock<TW>{tws, 12 - B, B - 12, 0u}, c);
-            else
-                fast_inv_round<A, 1>(e, TwGlobal<TW>{W, logN - 12, chunk}, c);
-            const int zb = zbase(tau, 8);
-#pragma unroll
-            for (int k = 0; k < 16; ++k) g[zb | (k << 8)] = A::store_mid(e[k], c);
-        } else {
-            const int zb = zbase(tau, 4);
-#pragma unroll
-            for (int k = 0; k < 16; ++k) g[zb | (k << 4)] = A::store_mid(e[k], c);
-        }
-    }
-}
-
-// ---- tensor product of cc_mult (engine.py:1095-1101) fused into the load of the inverse block pass ---------------------
-// Row r of the [3L] batch is d_(r / L), limb r % L:  d0 = x0 y0,  d1 = x0 y1 + x1 y0,  d2 = x1 y1, where x[4][L][N] holds
-// the NTT-domain polynomials x0, x1, y0, y1 (Montgomery form: transforms of x R).  Scale-prime rows multiply in FP64
-// (x holds raw doubles there; the product carries R^2, removed by the exit scalar N^-1 R^-2), 60-bit rows use the
-// reference's Montgomery product (exit scalar N^-1 R^-1).  If d2hat != nullptr the NTT-domain d2 is also kept
-// (row-major [L][N]) for the key switch, which then skips the transform of every partition's own limbs.
-struct TensorIn {
-    const int64_t* x;          // [4][L][N]
-    long long poly_stride;     // L * N
-    const int64_t *_2q, *ql, *qh, *kl, *kh;
-    int64_t* d2hat;            // optional [L][N]
-    int L;
-};
-__device__ __forceinline__ void ldg256v(const int64_t* p, int64_t (&r)[4]) {
-    asm volatile("ld.global.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(r[0]), "=l"(r[1]), "=l"(r[2]), "=l"(r[3]) : "l"(p));
-}
-__device__ __forceinline__ void stg256v(int64_t* p, const int64_t (&r)[4]) {
-    asm volatile("st.global.v4.b64 [%0], {%1,%2,%3,%4};" ::"l"(p), "l"(r[0]), "l"(r[1]), "l"(r[2]), "l"(r[3]) : "memory");
-}
-template <class A>
-__device__ __forceinline__ void tensor_load(const FastArgs& F, const TensorIn& Tn, typename A::T (&e)[16], int limb,
-                                            long long drow, long long off, const typename A::C& c);
-template <>
-__device__ __forceinline__ void tensor_load<ArithF64>(const FastArgs& F, const TensorIn& Tn, double (&e)[16], int limb,
-                                                      long long drow, long long off, const F64C& c) {
-    const int g = (int)(drow / Tn.L);
-    const int64_t* base = Tn.x + (long long)limb * F.a_stride + off;
-    const int64_t* pa = base + ((g == 2) ? 1 : 0) * Tn.poly_stride;
-    const int64_t* pb = base + ((g == 0) ? 2 : 3) * Tn.poly_stride;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {      // four coefficients at a time keeps the live operand registers low
-        int64_t a[4], b[4];
-        ldg256v(pa + 4 * j, a);
-        ldg256v(pb + 4 * j, b);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) e[4 * j + i] = f64_mulmod(__longlong_as_double(a[i]), __longlong_as_double(b[i]), c);
-    }
-    if (g == 1) {
-        const int64_t* pc = base + 1 * Tn.poly_stride;
-        const int64_t* pd = base + 2 * Tn.poly_stride;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            int64_t a[4], b[4];
-            ldg256v(pc + 4 * j, a);
-            ldg256v(pd + 4 * j, b);
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-                e[4 * j + i] = __dadd_rn(e[4 * j + i], f64_mulmod(__longlong_as_double(a[i]), __longlong_as_double(b[i]), c));
-        }
-    }
-    if (g == 2 && Tn.d2hat) {
-        int64_t* o = Tn.d2hat + (long long)limb * F.a_stride + off;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            int64_t r[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) r[i] = (int64_t)__double_as_longlong(e[4 * j + i]);
-            stg256v(o + 4 * j, r);
-        }
-    }
-}
-template <>
-__device__ __forceinline__ void tensor_load<ArithU64>(const FastArgs& F, const TensorIn& Tn, uint64_t (&e)[16], int limb,
-                                                      long long drow, long long off, const U64C& c) {
-    const int g = (int)(drow / Tn.L);
-    const int64_t* base = Tn.x + (long long)limb * F.a_stride + off;
-    const int64_t* pa = base + ((g == 2) ? 1 : 0) * Tn.poly_stride;
-    const int64_t* pb = base + ((g == 0) ? 2 : 3) * Tn.poly_stride;
-    const LimbConst k = load_limb_const(Tn._2q, Tn.ql, Tn.qh, Tn.kl, Tn.kh, limb);
-    const int64_t q2 = (int64_t)k.q2;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        int64_t a[4], b[4];
-        ldg256v(pa + 4 * j, a);
-        ldg256v(pb + 4 * j, b);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) e[4 * j + i] = (uint64_t)mont_mul_ss(a[i], b[i], k.q4, k.k);   // lazy, in [0, 2q)
-    }
-    if (g == 1) {
-        const int64_t* pc = base + 1 * Tn.poly_stride;
-        const int64_t* pd = base + 2 * Tn.poly_stride;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            int64_t a[4], b[4];
-            ldg256v(pc + 4 * j, a);
-            ldg256v(pd + 4 * j, b);
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-                e[4 * j + i] = (uint64_t)lazy_add((int64_t)e[4 * j + i], mont_mul_ss(a[i], b[i], k.q4, k.k), q2);
-        }
-    }
-    if (g == 2 && Tn.d2hat) {
-        int64_t* o = Tn.d2hat + (long long)limb * F.a_stride + off;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            int64_t r[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) r[i] = (int64_t)e[4 * j + i];
-            stg256v(o + 4 * j, r);
-        }
-    }
-}
-
-// ---- inverse pass B', WARP-INDEPENDENT form (see fast_fwd_block_body_w) ------------------------------------------------
-// A thread starts from its 16 contiguous coefficients (four 256-bit loads), exchanges stay inside the warp; for
-// B == 9 the last level (distance 256) is taken as the top stage of field [8:5], which keeps it warp-private too.
-template <class A, int B, bool STAGED, bool TENS, bool HYB = false>
-__device__ __forceinline__ void fast_inv_block_body_w(const FastArgs& F, const TensorIn& Tn, int64_t* sm, int limb, long long drow) {
-    using T = typename A::T;
-    using TW = typename A::TW;
-    const int tau = threadIdx.x;
-    const unsigned chunk = grid_chunk(F);
-    constexpr int logN = B + 8;
-    const typename A::C c = make_const<A>((uint64_t)F.q[limb]);
-    int64_t* __restrict__ g = F.a + drow * F.a_stride + (long long)chunk * TILE;
-    const TW* __restrict__ W = tw_row<A>(F, limb);
-    TW* tws = reinterpret_cast<TW*>(sm + SMEM_SLOTS);
-    uint64_t* bar = reinterpret_cast<uint64_t*>(sm + SMEM_SLOTS + (HYB ? HYB_TW_SLOTS : FAST_TW_SLOTS));
-    constexpr bool S1 = STAGED && !HYB;   // the first round's twiddles (one thread each) come from shared memory
-    if constexpr (STAGED && HYB)
-        stage_block_twiddles_first(reinterpret_cast<const double*>(W), reinterpret_cast<double*>(tws), bar, B, chunk, B - 4);
-    else if constexpr (STAGED)
-        stage_block_twiddles(reinterpret_cast<const double*>(W), reinterpret_cast<double*>(tws), bar, B, chunk);
-    if (tau == 32) {
-        unsigned ca = 0;
-        const long long ra = F.prefetch ? fast_row_ahead(F, F.prefetch, ca) : -1;
-        if (ra >= 0) l2_prefetch_bulk(F.a + ra * F.a_stride + (long long)ca * TILE, TILE * 8u);
-    }
-    T e[16];
-    if constexpr (TENS) {
-        tensor_load<A>(F, Tn, e, limb, drow, (long long)chunk * TILE + tau * 16, c);
-    } else {
-        int64_t r[16];
-        const int64_t* in = g + tau * 16;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) ldg256(in, r, j);
-#pragma unroll
-        for (int k = 0; k < 16; ++k) e[k] = A::load_in(r[k], F.in_raw);
-    }
-    if constexpr (S1) {
-        mbar_wait(bar, 0);
-        fast_inv_round<A, 4>(e, TwSharedBlock<TW>{tws, 12 - B, B - 4, (unsigned)tau}, c);
-    } else {
-        fast_inv_round<A, 4>(e, TwGlobal<TW>{W, logN - 4, (chunk << 8) | (unsigned)tau}, c);
-        if constexpr (STAGED) mbar_wait(bar, 0);   // hybrid: the staged (shared) stages are needed from the next round on
-    }
-    if constexpr (B == 4) {
-        int64_t r[16];
-#pragma unroll
-        for (int k = 0; k < 16; ++k) r[k] = A::store_mid(e[k], c);
-        int64_t* o = g + tau * 16;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) stg256(o, r, j);
+        tile_store16<T>(g, r, tau, 0);
     } else {
         smx_store(sm, e, tau, 0);
         __syncwarp();
         smx_load(sm, e, tau, 4);
         constexpr int NST = (B >= 8) ? 4 : B - 4;
-        if constexpr (STAGED)
-            fast_inv_round<A, NST>(e, TwSharedBlock<TW>{tws, 12 - B, B - 8, (unsigned)(tau >> 4)}, c);
-        else
-            fast_inv_round<A, NST>(e, TwGlobal<TW>{W, logN - 8, (chunk << 4) | (unsigned)(tau >> 4)}, c);
+        fast_inv_round<A, NST>(e, TwGlobal<TW>{W, logN - 8, (chunk << 4) | (unsigned)(tau >> 4)}, c);
         if constexpr (B == 9) {
             __syncwarp();
             smx_store(sm, e, tau, 4);
@@ -1715,11 +1054,7 @@ __device__ __forceinline__ void fast_inv_block_body_w(const FastArgs& F, const T
             smx_load(sm, e, tau, 5);
             {   // level with distance 2^8 = top stage of field [8:5]: pairs (k, k+8), one twiddle per 512-point sub-block
                 TW w[8];
-                const unsigned sub = (unsigned)(tau >> 5);
-                if constexpr (STAGED)
-                    w[0] = tws[sub];
-                else
-                    w[0] = __ldg(W + (1u << (logN - 9)) + ((chunk << 3) | sub));
+                w[0] = __ldg(W + (1u << (logN - 9)) + ((chunk << 3) | (unsigned)(tau >> 5)));
                 A::template gs_stage<3>(e, w, c);
 #pragma unroll
                 for (int k = 0; k < 16; ++k) A::tame(e[k], c);
@@ -1736,178 +1071,15 @@ __device__ __forceinline__ void fast_inv_block_body_w(const FastArgs& F, const T
 }
 
 template <int B>
-__global__ void __launch_bounds__(NTT_THREADS, FAST_CTAS_PER_SM) fast_inv_blockpass_w(const FastArgs F) {
+__global__ void __launch_bounds__(NTT_THREADS, FAST_BLK_CTAS) fast_inv_blockpass(const FastArgs F) {
     extern __shared__ __align__(16) int64_t sm[];
     const RowId rid = fast_row(F);
-    const int limb = rid.limb;
-    const TensorIn none{};
     if (fast_use_f64(F, rid))
-        fast_inv_block_body_w<ArithF64, B, true, false>(F, none, sm, limb, rid.data_row);
+        fast_inv_block_body<ArithF64, B>(F, sm, rid.limb, rid.data_row);
     else
-        fast_inv_block_body_w<ArithU64, B, false, false>(F, none, sm, limb, rid.data_row);
+        fast_inv_block_body<ArithU64, B>(F, sm, rid.limb, rid.data_row);
 }
 
-template <int B>
-__global__ void __launch_bounds__(NTT_THREADS, 4) fast_inv_blockpass_h(const FastArgs F) {
-    extern __shared__ __align__(16) int64_t sm[];
-    const RowId rid = fast_row(F);
-    const int limb = rid.limb;
-    const TensorIn none{};
-    if (fast_use_f64(F, rid))
-        fast_inv_block_body_w<ArithF64, B, true, false, true>(F, none, sm, limb, rid.data_row);
-    else
-        fast_inv_block_body_w<ArithU64, B, false, false, true>(F, none, sm, limb, rid.data_row);
-}
-
-// the tensor stage's inverse block pass: tensor product fused into the load (rows = 3 x L, period L)
-template <int B>
-__global__ void __launch_bounds__(NTT_THREADS, FAST_CTAS_PER_SM) fast_inv_blockpass_tensor(const FastArgs F, const TensorIn Tn) {
-    extern __shared__ __align__(16) int64_t sm[];
-    const RowId rid = fast_row(F);
-    const int limb = rid.limb;
-    if (fast_use_f64(F, rid))
-        fast_inv_block_body_w<ArithF64, B, true, true>(F, Tn, sm, limb, rid.data_row);
-    else
-        fast_inv_block_body_w<ArithU64, B, false, true>(F, Tn, sm, limb, rid.data_row);
-}
-
-template <int B>
-__global__ void __launch_bounds__(NTT_THREADS, FAST_CTAS_PER_SM) fast_inv_blockpass(const FastArgs F) {
-    extern __shared__ __align__(16) int64_t sm[];
-    const RowId rid = fast_row(F);
-    const int limb = rid.limb;
-    if (fast_use_f64(F, rid))
-        fast_inv_block_body<ArithF64, B, true>(F, sm, limb, rid.data_row);
-    else
-        fast_inv_block_body<ArithU64, B, false>(F, sm, limb, rid.data_row);
-}
-
-// ---- PERSISTENT, SOFTWARE-PIPELINED inverse block pass (see fast_fwd_blockpass_pp) --------------------------------------
-template <class A, int B, bool STAGED>
-__device__ __forceinline__ void pp_inv_block_tile(const FastArgs& F, const int64_t (&raw)[16], int64_t* xb,
-                                                  const typename A::TW* tws, const TileId& tl, int64_t* __restrict__ g) {
-    using T = typename A::T;
-    using TW = typename A::TW;
-    const int tau = threadIdx.x;
-    constexpr int logN = B + 8;
-    const unsigned chunk = (unsigned)tl.chunk;
-    const typename A::C c = make_const<A>((uint64_t)F.q[tl.limb]);
-    const TW* __restrict__ W = tw_row<A>(F, tl.limb);
-    T e[16];
-#pragma unroll
-    for (int k = 0; k < 16; ++k) e[k] = A::load_in(raw[k], F.in_raw);
-    if constexpr (STAGED)
-        fast_inv_round<A, 4>(e, TwSharedBlock<TW>{tws, 12 - B, B - 4, (unsigned)tau}, c);
-    else
-        fast_inv_round<A, 4>(e, TwGlobal<TW>{W, logN - 4, (chunk << 8) | (unsigned)tau}, c);
-    if constexpr (B == 4) {
-        int64_t r[16];
-#pragma unroll
-        for (int k = 0; k < 16; ++k) r[k] = A::store_mid(e[k], c);
-        int64_t* o = g + tau * 16;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) stg256(o, r, j);
-    } else {
-        __syncwarp();   // the warp's slice of the exchange buffer is free (previous tile fully read)
-        smx_store(xb, e, tau, 0);
-        __syncwarp();
-        smx_load(xb, e, tau, 4);
-        constexpr int NST = (B >= 8) ? 4 : B - 4;
-        if constexpr (STAGED)
-            fast_inv_round<A, NST>(e, TwSharedBlock<TW>{tws, 12 - B, B - 8, (unsigned)(tau >> 4)}, c);
-        else
-            fast_inv_round<A, NST>(e, TwGlobal<TW>{W, logN - 8, (chunk << 4) | (unsigned)(tau >> 4)}, c);
-        if constexpr (B == 9) {
-            __syncwarp();
-            smx_store(xb, e, tau, 4);
-            __syncwarp();
-            smx_load(xb, e, tau, 5);
-            {
-                TW w[8];
-                const unsigned sub = (unsigned)(tau >> 5);
-                if constexpr (STAGED)
-                    w[0] = tws[sub];
-                else
-                    w[0] = __ldg(W + (1u << (logN - 9)) + ((chunk << 3) | sub));
-                A::template gs_stage<3>(e, w, c);
-#pragma unroll
-                for (int k = 0; k < 16; ++k) A::tame(e[k], c);
-            }
-            const int zb = zbase(tau, 5);
-#pragma unroll
-            for (int k = 0; k < 16; ++k) g[zb | (k << 5)] = A::store_mid(e[k], c);
-        } else {
-            const int zb = zbase(tau, 4);
-#pragma unroll
-            for (int k = 0; k < 16; ++k) g[zb | (k << 4)] = A::store_mid(e[k], c);
-        }
-    }
-}
-
-template <int B>
-__global__ void __launch_bounds__(NTT_THREADS, 2) fast_inv_blockpass_pp(const FastArgs F, long long total_tiles, int G) {
-    extern __shared__ __align__(16) int64_t sm[];
-    int64_t* xb = sm;
-    double* tws = reinterpret_cast<double*>(sm + SMEM_SLOTS);                   // [2][FAST_TW_SLOTS]
-    uint64_t* bar_tw = reinterpret_cast<uint64_t*>(tws + 2 * FAST_TW_SLOTS);    // [2]
-    const int tau = threadIdx.x;
-    const int chunks = (1 << (B + 8)) / TILE;
-    const TileRange range = pp_tile_range(F, (int)(total_tiles / ((long long)chunks * G)), chunks * G);
-    const int t_begin = range.begin, t_end = range.end;
-    if (t_begin >= t_end) return;
-    auto staged = [&](int limb) { return (uint64_t)F.q[limb] < SMALL_PRIME_LIMIT && F.force_int != 1; };
-    if (tau == 0) {
-        mbar_init(&bar_tw[0], 1);
-        mbar_init(&bar_tw[1], 1);
-    }
-    __syncthreads();
-    int64_t nxt[16];
-    {
-        const TileId t0 = decode_tile32(F, t_begin, G, chunks);
-        if (tau == 0 && staged(t0.limb)) pp_issue_block_twiddles<B>(F, t0.limb, t0.chunk, tws, &bar_tw[0]);
-        const int64_t* src = F.a + t0.drow * F.a_stride + (long long)t0.chunk * TILE + tau * 16;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) ldg256(src, nxt, j);
-    }
-    long long cur_group = -1;
-    unsigned gcount = 0;
-    unsigned ph0 = 0, ph1 = 0;
-#pragma unroll 1
-    for (int id = t_begin; id < t_end; ++id) {
-        const TileId tl = decode_tile32(F, id, G, chunks);
-        int64_t cur[16];
-#pragma unroll
-        for (int k = 0; k < 16; ++k) cur[k] = nxt[k];
-        if (id + 1 < t_end) {
-            const TileId tn = decode_tile32(F, id + 1, G, chunks);
-            const int64_t* src = F.a + tn.drow * F.a_stride + (long long)tn.chunk * TILE + tau * 16;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) ldg256(src, nxt, j);
-        }
-        if (tl.group != cur_group) {
-            cur_group = tl.group;
-            __syncthreads();
-            const int next_first = (tl.group + 1) * G;
-            if (tau == 0 && next_first < t_end) {
-                const TileId tg = decode_tile32(F, next_first, G, chunks);
-                if (staged(tg.limb)) pp_issue_block_twiddles<B>(F, tg.limb, tg.chunk, tws + ((gcount + 1) & 1) * FAST_TW_SLOTS, &bar_tw[(gcount + 1) & 1]);
-            }
-            if (staged(tl.limb)) {
-                const unsigned b = gcount & 1;
-                mbar_wait(&bar_tw[b], (b ? ph1 : ph0) & 1);
-                if (b) ++ph1; else ++ph0;
-            }
-            ++gcount;
-        }
-        const unsigned tb = (gcount - 1) & 1;
-        int64_t* gout = F.a + tl.drow * F.a_stride + (long long)tl.chunk * TILE;
-        const RowId rid{tl.drow, tl.limb};
-        if (fast_use_f64(F, rid))
-            pp_inv_block_tile<ArithF64, B, true>(F, cur, xb, tws + tb * FAST_TW_SLOTS, tl, gout);
-        else
-            pp_inv_block_tile<ArithU64, B, false>(F, cur, xb, nullptr, tl, gout);
-    }
-}
 
 // ---- inverse pass A' (levels b..logN-1), x scalar, canonical out ---------------------------------------------
 template <class A, bool STAGED>
@@ -1916,7 +1088,7 @@ __device__ __forceinline__ void fast_inv_col_body(const FastArgs& F, int64_t* sm
     using TW = typename A::TW;
     const int tau = threadIdx.x;
     const int b = F.logN - 8;
-    const typename A::C c = make_const<A>((uint64_t)F.q[limb]);
+    const typename A::C c = make_const<A>(F, limb);
     int64_t* __restrict__ row0 = F.a + drow * F.a_stride + (long long)grid_chunk(F) * 16;
     const TW* __restrict__ W = tw_row<A>(F, limb);
     TW* tws = reinterpret_cast<TW*>(sm + SMEM_SLOTS);
@@ -1966,177 +1138,6 @@ __global__ void __launch_bounds__(NTT_THREADS, FAST_COL_CTAS) fast_inv_colpass(c
         fast_inv_col_body<ArithU64, false>(F, sm, limb, rid.data_row);
 }
 
-// ---- PERSISTENT, SOFTWARE-PIPELINED column passes -------------------------------------------------------------------------
-// Same idea as fast_fwd_blockpass_pp for the strided passes: a CTA walks tiles (256 rows x 16 columns of one limb row),
-// prefetching the next tile's 16 coefficients per thread into registers while the current tile is transformed.  The
-// exchange between the two radix-16 rounds crosses warps here, so there is one CTA barrier per tile; the exchange
-// buffer is double-buffered so that no second barrier is needed.  Tile order: all column chunks of a row, then the
-// next of the G rows that share the limb, then the next limb: the 2 KB of column-pass twiddles are staged once per
-// limb (double-buffered, one limb ahead).
-constexpr int PPC_SMEM_BYTES = 2 * SMEM_BYTES + 2 * 256 * 8 + 32;
-
-struct ColTile {
-    long long drow;
-    int limb, ch, group;
-};
-__device__ __forceinline__ ColTile decode_col_tile(const FastArgs& F, int id, int G, int chunks) {
-    const int per_group = G * chunks;
-    const int group = id / per_group, rem = id - group * per_group;
-    const int g = rem / chunks;
-    ColTile t;
-    t.group = group;
-    t.ch = rem - g * chunks;
-    if (F.slab_rows == 0) {
-        t.limb = group;
-        t.drow = (long long)g * F.period + group;
-    } else {
-        t.limb = F.slab_t0 + group;
-        t.drow = (long long)g * F.group_rows + F.slab_t0 + group;
-    }
-    return t;
-}
-__device__ __forceinline__ void pp_issue_col_twiddles(const FastArgs& F, int limb, double* dst, uint64_t* bar) {
-    fence_async_smem();
-    mbar_expect_tx(bar, 256u * 8u);
-    tma_bulk_g2s(dst, F.tw_f64 + ((long long)limb << F.logN), 256u * 8u, bar);
-}
-
-template <class A, bool STAGED>
-__device__ __forceinline__ void pp_fwd_col_tile(const FastArgs& F, const int64_t (&raw)[16], int64_t* xb,
-                                                const typename A::TW* tws, const ColTile& tl) {
-    using T = typename A::T;
-    using TW = typename A::TW;
-    const int tau = threadIdx.x;
-    const int b = F.logN - 8;
-    const typename A::C c = make_const<A>((uint64_t)F.q[tl.limb]);
-    int64_t* __restrict__ row0 = F.a + tl.drow * F.a_stride + (long long)tl.ch * 16;
-    const TW* __restrict__ W = tw_row<A>(F, tl.limb);
-    T e[16];
-#pragma unroll
-    for (int k = 0; k < 16; ++k) e[k] = A::load_in(raw[k], F.in_raw);
-    if (F.scal) {
-        const TW s = scalar_tw<A>(F, tl.limb);
-#pragma unroll
-        for (int k = 0; k < 16; ++k) e[k] = A::mul(e[k], s, c);
-    }
-    if constexpr (STAGED)
-        fast_fwd_round<A, 0>(e, TwSharedCol<TW>{tws, 0, 0u}, c);
-    else
-        fast_fwd_round<A, 0>(e, TwGlobal<TW>{W, 0, 0u}, c);
-    smx_store(xb, e, tau, 8);
-    __syncthreads();
-    smx_load(xb, e, tau, 4);
-    const int hi = tau >> 4, col = tau & 15;
-    if constexpr (STAGED)
-        fast_fwd_round<A, 0>(e, TwSharedCol<TW>{tws, 4, (unsigned)hi}, c);
-    else
-        fast_fwd_round<A, 0>(e, TwGlobal<TW>{W, 4, (unsigned)hi}, c);
-#pragma unroll
-    for (int k = 0; k < 16; ++k) row0[((long long)(hi * 16 + k) << b) + col] = A::store_mid(e[k], c);
-}
-
-template <class A, bool STAGED>
-__device__ __forceinline__ void pp_inv_col_tile(const FastArgs& F, const int64_t (&raw)[16], int64_t* xb,
-                                                const typename A::TW* tws, const ColTile& tl) {
-    using T = typename A::T;
-    using TW = typename A::TW;
-    const int tau = threadIdx.x;
-    const int b = F.logN - 8;
-    const typename A::C c = make_const<A>((uint64_t)F.q[tl.limb]);
-    int64_t* __restrict__ row0 = F.a + tl.drow * F.a_stride + (long long)tl.ch * 16;
-    const TW* __restrict__ W = tw_row<A>(F, tl.limb);
-    T e[16];
-#pragma unroll
-    for (int k = 0; k < 16; ++k) e[k] = A::load_mid(raw[k]);
-    const int hi = tau >> 4;
-    if constexpr (STAGED)
-        fast_inv_round<A, 4>(e, TwSharedCol<TW>{tws, 4, (unsigned)hi}, c);
-    else
-        fast_inv_round<A, 4>(e, TwGlobal<TW>{W, 4, (unsigned)hi}, c);
-    smx_store(xb, e, tau, 4);
-    __syncthreads();
-    smx_load(xb, e, tau, 8);
-    if constexpr (STAGED)
-        fast_inv_round<A, 4>(e, TwSharedCol<TW>{tws, 0, 0u}, c);
-    else
-        fast_inv_round<A, 4>(e, TwGlobal<TW>{W, 0, 0u}, c);
-    const TW s = scalar_tw<A>(F, tl.limb);
-    const int r0 = tau >> 4, col = tau & 15;
-#pragma unroll
-    for (int k = 0; k < 16; ++k)
-        row0[((long long)(r0 + 16 * k) << b) + col] = A::store_canon(A::mul(e[k], s, c), c, F.centred != 0);
-}
-
-template <bool FWD>
-__global__ void __launch_bounds__(NTT_THREADS, 2) fast_colpass_pp(const FastArgs F, long long total_tiles, int G) {
-    extern __shared__ __align__(16) int64_t sm[];
-    double* tws = reinterpret_cast<double*>(sm + 2 * SMEM_SLOTS);               // [2][256]
-    uint64_t* bar_tw = reinterpret_cast<uint64_t*>(tws + 2 * 256);               // [2]
-    const int tau = threadIdx.x;
-    const int b = F.logN - 8;
-    const int chunks = (1 << F.logN) / TILE;
-    const TileRange range = pp_tile_range(F, (int)(total_tiles / ((long long)chunks * G)), chunks * G);
-    const int t_begin = range.begin, t_end = range.end;
-    if (t_begin >= t_end) return;
-    auto staged = [&](int limb) { return (uint64_t)F.q[limb] < SMALL_PRIME_LIMIT && F.force_int != 1; };
-    if (tau == 0) {
-        mbar_init(&bar_tw[0], 1);
-        mbar_init(&bar_tw[1], 1);
-    }
-    __syncthreads();
-    // element k of a thread: forward reads rows (tau>>4) + 16k, inverse rows 16 (tau>>4) + k, column tau & 15
-    const long long off0 = FWD ? ((long long)(tau >> 4) << b) + (tau & 15) : ((long long)((tau >> 4) * 16) << b) + (tau & 15);
-    const long long kstep = FWD ? (16ll << b) : (1ll << b);
-    int64_t nxt[16];
-    {
-        const ColTile t0 = decode_col_tile(F, t_begin, G, chunks);
-        if (tau == 0 && staged(t0.limb)) pp_issue_col_twiddles(F, t0.limb, tws, &bar_tw[0]);
-        const int64_t* __restrict__ src = F.a + t0.drow * F.a_stride + (long long)t0.ch * 16 + off0;
-#pragma unroll
-        for (int k = 0; k < 16; ++k) nxt[k] = src[k * kstep];
-    }
-    long long cur_group = -1;
-    unsigned gcount = 0, ph0 = 0, ph1 = 0, it = 0;
-#pragma unroll 1
-    for (int id = t_begin; id < t_end; ++id, ++it) {
-        const ColTile tl = decode_col_tile(F, id, G, chunks);
-        int64_t cur[16];
-#pragma unroll
-        for (int k = 0; k < 16; ++k) cur[k] = nxt[k];
-        if (id + 1 < t_end) {
-            const ColTile tn = decode_col_tile(F, id + 1, G, chunks);
-            const int64_t* __restrict__ src = F.a + tn.drow * F.a_stride + (long long)tn.ch * 16 + off0;
-#pragma unroll
-            for (int k = 0; k < 16; ++k) nxt[k] = src[k * kstep];
-        }
-        if (tl.group != cur_group) {
-            cur_group = tl.group;
-            __syncthreads();             // every warp is done with the limb before: its twiddle buffer can be refilled
-            const int next_first = (tl.group + 1) * G * chunks;
-            if (tau == 0 && next_first < t_end) {
-                const ColTile tg = decode_col_tile(F, next_first, G, chunks);
-                if (staged(tg.limb)) pp_issue_col_twiddles(F, tg.limb, tws + ((gcount + 1) & 1) * 256, &bar_tw[(gcount + 1) & 1]);
-            }
-            if (staged(tl.limb)) {
-                const unsigned bb = gcount & 1;
-                mbar_wait(&bar_tw[bb], (bb ? ph1 : ph0) & 1);
-                if (bb) ++ph1; else ++ph0;
-            }
-            ++gcount;
-        }
-        const double* tw = tws + ((gcount - 1) & 1) * 256;
-        int64_t* xb = sm + (it & 1) * SMEM_SLOTS;   // alternate exchange buffers: one barrier per tile is enough
-        const RowId rid{tl.drow, tl.limb};
-        if (fast_use_f64(F, rid)) {
-            if constexpr (FWD) pp_fwd_col_tile<ArithF64, true>(F, cur, xb, tw, tl);
-            else pp_inv_col_tile<ArithF64, true>(F, cur, xb, tw, tl);
-        } else {
-            if constexpr (FWD) pp_fwd_col_tile<ArithU64, false>(F, cur, xb, nullptr, tl);
-            else pp_inv_col_tile<ArithU64, false>(F, cur, xb, nullptr, tl);
-        }
-    }
-}
-
 // ---- table construction ----------------------------------------------------------------------------------------
 // plain canonical twiddles [C][N] -> {w, floor(w 2^64 / q)} and double(w)
 __global__ void fast_tables_kernel(const int64_t* __restrict__ plain, const int64_t* __restrict__ q,
@@ -2149,6 +1150,44 @@ __global__ void fast_tables_kernel(const int64_t* __restrict__ plain, const int6
     const uint64_t wp = (uint64_t)(num / (unsigned __int128)(uint64_t)q[i]);
     sh[(long long)i * N + j] = make_ulonglong2(w, wp);
     if (dbl) dbl[(long long)i * N + j] = (double)w;
+}
+
+// packed last-group tables (TwPacked) from the plain fast tables: thread T = coefficient index / 16
+__global__ void fast_pack_kernel(const ulonglong2* __restrict__ sh, const double* __restrict__ dbl, ulonglong2* __restrict__ psh,
+                                 double* __restrict__ pdbl, int logN) {
+    const int limb = blockIdx.y;
+    const int T = blockIdx.x * blockDim.x + threadIdx.x;
+    const int N = 1 << logN;
+    if (T >= (N >> 4)) return;
+    const long long row = (long long)limb << logN;
+    const long long wt = row + (long long)(T >> 5) * PACK_TILE;
+    const int lane = T & 31;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+#pragma unroll
+        for (int j = 0; j < (1 << i); ++j) {
+            const long long src = row + (1ll << (logN - 4 + i)) + ((long long)T << i) + j;
+            if (psh) psh[wt + ((1 << i) - 1 + j) * 32 + lane] = sh[src];
+            if (pdbl) {
+                if (i == 0) pdbl[wt + lane] = dbl[src];
+                else pdbl[wt + 64 + ((((1 << (i - 1)) - 1) + (j >> 1)) * 32 + lane) * 2 + (j & 1)] = dbl[src];
+            }
+        }
+    }
+    if (psh) psh[wt + 15 * 32 + lane] = make_ulonglong2(0, 0);
+    if (pdbl) pdbl[wt + 32 + lane] = 0.0;
+}
+
+// natural <-> warp-interleaved order of NTT-domain rows (FastArgs::perm); used once per evaluation key
+__global__ void fast_perm_kernel(const int64_t* __restrict__ in, long long in_stride, int64_t* __restrict__ out, long long out_stride,
+                                 int N, int inverse) {
+    const long long row = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;   // natural index
+    if (i >= N) return;
+    const int tile = i >> 9, t = (i >> 4) & 31, k = i & 15;
+    const int p = (tile << 9) + (((k >> 1) * 32 + t) << 1) + (k & 1);
+    if (inverse) out[row * out_stride + i] = in[row * in_stride + p];
+    else out[row * out_stride + p] = in[row * in_stride + i];
 }
 
 }  // namespace ckks

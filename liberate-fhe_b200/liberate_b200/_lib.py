@@ -39,8 +39,10 @@ SIGNATURES = {
     "ckks_tile_unsigned": [_i64p, _i64p, _i64, _int, _int, _i64p, _vp],
     "ckks_compact_twiddles": [_i64p, _i64p, _int, _int, _int, _vp],
     "ckks_fast_tables": [_i64p, _i64p, _vp, _vp, _int, _int, _vp],
-    "ckks_ntt_fast": [_i64p, _i64, _int, _int, _int, _vp, _vp, _i64p, _i64p, _i64p, _int, _vp],
-    "ckks_intt_fast": [_i64p, _i64, _int, _int, _int, _vp, _vp, _i64p, _i64p, _i64p, _int, _int, _vp],
+    "ckks_fast_pack": [_vp, _vp, _vp, _vp, _int, _int, _vp],
+    "ckks_perm_rows": [_i64p, _i64, _i64p, _i64, _int, _int, _int, _vp],
+    "ckks_ntt_fast": [_i64p, _i64, _int, _int, _int, _vp, _vp, _vp, _vp, _i64p, _vp, _i64p, _i64p, _int, _vp],
+    "ckks_intt_fast": [_i64p, _i64, _int, _int, _int, _vp, _vp, _vp, _vp, _i64p, _vp, _i64p, _i64p, _int, _int, _vp],
     "ckks_rescale": [_i64p, _i64, _i64p, _i64p, _i64, _int, _int, _i64p, _i64, _int, _i64p, _i64p, _i64p, _i64p, _i64p, _vp],
     "ckks_tensor_product": [_i64p, _i64p, _i64p, _i64p, _i64, _i64p, _i64p, _i64p, _i64, _int, _int,
                             _i64p, _i64p, _i64p, _i64p, _i64p, _vp],
@@ -52,9 +54,9 @@ SIGNATURES = {
     "ckks_moddown": [_i64p, _i64, _int, _int, _int, _i64p, _i64p, _i64p, _i64, _i64p, _i64, _i64p,
                      _i64p, _i64p, _i64p, _i64p, _i64p, _vp],
     "ckks_automorphism": [_i64p, _i64, _i64p, _i64, _int, _int, _i64, _int, _i64p, _vp],
-    "ckks_exec_tensor_stage": [_vp, _i64p, _i64p, _i64p, _i64p, _i64, _i64p, _i64p, _i64p, _i64p, _i64p, _i64p, _i64p, _i64p, _vp],
+    "ckks_exec_tensor_stage": [_vp, _i64p, _i64p, _i64p, _i64p, _i64, _i64p, _i64p, _i64p, _i64p, _i64p, _i64p, _i64p, _vp],
     "ckks_exec_digits": [_vp, _i64p, _i64, _i64p, _i64, _vp],
-    "ckks_exec_keyswitch_stage": [_vp, _vp, _i64, _vp, _vp, _i64, _i64p, _i64p, _i64, _i64p, _i64p, _i64, _i64p, _i64p, _vp],
+    "ckks_exec_keyswitch_stage": [_vp, _vp, _i64, _vp, _vp, _i64, _int, _i64p, _i64p, _i64, _i64p, _i64p, _i64, _i64p, _vp],
     "ckks_exec_keyswitch_ws_elems": [_int, _int, _int, _int],
     "ckks_rng_bytes": [_i64p, _int, _int, _vp, _vp, _vp, ctypes.c_uint64, _vp],
     "ckks_rng_randint": [_i64p, _int, _int, _vp, _i64, _vp, _vp, _vp, ctypes.c_uint64, _vp],
@@ -71,22 +73,51 @@ class CkksLibError(RuntimeError):
     pass
 
 
+ABI_VERSION = 3      # the version SIGNATURES (and fhe/executor.LevelT) were written for
+
+
+def _build_locked():
+    """(re)build the in-tree library under a file lock: with one process per GPU every rank may find it missing or stale"""
+    import fcntl
+    sys.path.insert(0, str(_CSRC))
+    try:
+        import build as _b
+        with open(_CSRC / ".build.lock", "w") as lock:
+            fcntl.flock(lock, fcntl.LOCK_EX)
+            try:
+                _b.build()          # no-op when another rank has just built it
+            finally:
+                fcntl.flock(lock, fcntl.LOCK_UN)
+    finally:
+        sys.path.pop(0)
+
+
 def _load():
+    in_tree = not os.environ.get("CKKS_B200_LIB")
+    have_nvcc = shutil.which("nvcc") is not None
     if not _LIBPATH.exists():
-        if shutil.which("nvcc") is None:
-            raise ImportError(f"{_LIBPATH} is missing and nvcc is not available to build it; "
+        if not (in_tree and have_nvcc):
+            raise ImportError(f"{_LIBPATH} is missing and cannot be built here (nvcc: {have_nvcc}); "
                               "liberate_b200 has no CPU fallback")
+        _build_locked()
+    elif in_tree and have_nvcc:
         sys.path.insert(0, str(_CSRC))
         try:
             import build as _b
-            _b.build()
+            stale = _b.stale()
         finally:
             sys.path.pop(0)
+        if stale:
+            _build_locked()
     lib = ctypes.CDLL(str(_LIBPATH))
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError here = header/library mismatch: fail loudly
         fn.argtypes = argtypes
         fn.restype = RESTYPES.get(name, ctypes.c_int)
+    got = lib.ckks_abi_version()
+    if got != ABI_VERSION:
+        raise ImportError(f"{_LIBPATH} has ABI version {got}, this package was written for {ABI_VERSION}: "
+                          "rebuild it (python liberate-fhe_b200/csrc/build.py --force)")
     return lib
 
 
@@ -105,7 +136,7 @@ class _Counted:
 
 
 lib = _Counted(_load())
-OPTION_KEYS = (1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16)
+OPTION_KEYS = (2, 9, 10, 11, 12, 16, 17, 18)
 _OPTION_DEFAULTS = {k: lib.ckks_get_option(k) for k in OPTION_KEYS}
 
 

@@ -186,10 +186,28 @@ class ckks_engine:
         self._plans = {}
         self._ws = {}
         self._dead_gather = {}
+        self._key_shadow = {}
 
         P = math.prod(c.q[-K:])
         self.mont_PR = [self._t([P * c.R % c.q[i] for i in p.destination_arrays[0][dev]], dev) if self._local(dev) else None
                         for dev in range(self.ntt.num_devices)]
+
+    def _permuted_key(self, t):
+        """the warp-interleaved copy of one key polynomial (all its rows on one device), made on first use and kept for
+        the life of the key tensor.  The fused key switch streams these copies; the user's key is never modified."""
+        hit = self._key_shadow.get(id(t))
+        if hit is None or hit[0] is not t:
+            if len(self._key_shadow) > 4096:        # stale ids of dropped keys: start over rather than grow for ever
+                self._key_shadow.clear()
+            hit = (t, fused.perm_rows(t))
+            self._key_shadow[id(t)] = hit
+        return hit[1]
+
+    def release_key_cache(self):
+        """drop the permuted key copies and pointer tables (they are rebuilt on the next use of a key)"""
+        self._key_shadow.clear()
+        for plan in self._plans.values():
+            plan._key_ptrs.clear()
 
     def _workspace(self, dev):
         ws = self._ws.get(dev)
@@ -703,10 +721,11 @@ class ckks_engine:
             dev = self.ntt.devices[d]
             out0[d] = torch.empty((plan.L, plan.N), dtype=torch.int64, device=dev)
             out1[d] = torch.empty((plan.L, plan.N), dtype=torch.int64, device=dev)
-            k0p, k1p, ks = plan.key_pointer_tables(self, ksk)
+            k0p, k1p, ks, permuted = plan.key_pointer_tables(self, ksk)
             add0 = add[0][d] if add is not None and add[0] is not None else None
             add1 = add[1][d] if add is not None and add[1] is not None else None
-            executor.keyswitch_stage(plan, plan.digit_pointer_table(blocks[d]), k0p, k1p, ks, add0, add1, out0[d], out1[d])
+            executor.keyswitch_stage(plan, plan.digit_pointer_table(blocks[d]), k0p, k1p, ks, permuted, add0, add1,
+                                     out0[d], out1[d])
         return out0, out1
 
     def _mult_fused(self, a, b, evk):
@@ -735,9 +754,9 @@ class ckks_engine:
             dev = self.ntt.devices[d]
             out0[d] = torch.empty((plan.L, plan.N), dtype=torch.int64, device=dev)
             out1[d] = torch.empty((plan.L, plan.N), dtype=torch.int64, device=dev)
-            k0p, k1p, ks = plan.key_pointer_tables(self, evk)
-            executor.keyswitch_stage(plan, plan.digit_pointer_table(blocks[d]), k0p, k1p, ks, plan.d[0], plan.d[1],
-                                     out0[d], out1[d], d2hat=plan.d2hat)
+            k0p, k1p, ks, permuted = plan.key_pointer_tables(self, evk)
+            executor.keyswitch_stage(plan, plan.digit_pointer_table(blocks[d]), k0p, k1p, ks, permuted, plan.d[0], plan.d[1],
+                                     out0[d], out1[d])
         return self._ct((out0, out1), nxt, "ct")
 
     def switch_key(self, ct: data_struct, ksk: data_struct) -> data_struct:

@@ -28,7 +28,10 @@ class LevelT(ctypes.Structure):
                 ("rescale_scale", _vp), ("round_at", ctypes.c_int64),
                 ("part_wide", _vp), ("Hm", _vp), ("Rd", _vp), ("C31", _vp),
                 ("Rinv", _vp), ("Pinv", _vp), ("L_small", ctypes.c_int32), ("amax", ctypes.c_int32),
-                ("sExitT", _vp), ("sExitT_sh", _vp), ("part_row0", _vp)]
+                ("twpf_u64", _vp), ("twpf_f64", _vp), ("twpi_u64", _vp), ("twpi_f64", _vp), ("qinv", _vp)]
+
+
+MAX_ALPHA = 8        # limbs per key-switch partition the fused kernels support (csrc/ckks_b200.cu)
 
 
 def _p(t):
@@ -69,6 +72,10 @@ class LevelPlan:
         owners = eng._part_owners(level)
         self.sids = sorted(owners)
         self.owners = owners
+        if max(o[2] for o in owners.values()) > MAX_ALPHA:
+            # (num_special_primes > 8 makes partitions of more than 8 limbs: the kernels would silently drop digits)
+            raise NotImplementedError(f"key-switch partitions of more than {MAX_ALPHA} limbs are not supported by the "
+                                      "fused path; construct the engine with fast=False")
         i32 = lambda v: hold(torch.tensor(v, dtype=torch.int32, device=device))
         i64 = lambda v: hold(torch.tensor(v, dtype=torch.int64, device=device))
         part_alpha = i32([owners[s][2] for s in self.sids])
@@ -85,22 +92,21 @@ class LevelPlan:
         loc_Y = i64([_p(x["Y_scalar"]) or 0 for x in g] or [0])
         loc_L = i64([_p(x["Ltri"]) or 0 for x in g] or [0])
 
-        sh_f, dbl_f = ntt.tw_fast_fwd[dev]
-        sh_i, dbl_i = ntt.tw_fast_inv[dev]
+        tf, ti = ntt.tw_fast_fwd[dev], ntt.tw_fast_inv[dev]
         sl = slice(a, b)
         T = lambda t: hold(t[dev][sl])
         d = LevelT()
         d.logN, d.L, d.K, d.nparts, d.nlocal = eng.ctx.logN, self.L, K, len(self.sids), len(local)
         d.q, d._2q, d.ql, d.qh, d.kl, d.kh, d.Rs = (_p(T(x)) for x in (ntt.q, ntt._2q, ntt.ql, ntt.qh, ntt.kl, ntt.kh, ntt.Rs))
-        d.twf_u64, d.twf_f64 = _p(hold(sh_f[sl])), _p(hold(dbl_f[sl]))
-        d.twi_u64, d.twi_f64 = _p(hold(sh_i[sl])), _p(hold(dbl_i[sl]))
+        d.twf_u64, d.twf_f64 = _p(hold(tf.sh[sl])), _p(hold(tf.dbl[sl]))
+        d.twi_u64, d.twi_f64 = _p(hold(ti.sh[sl])), _p(hold(ti.dbl[sl]))
+        d.twpf_u64, d.twpf_f64 = _p(hold(tf.psh[sl])), _p(hold(tf.pdbl[sl]))
+        d.twpi_u64, d.twpi_f64 = _p(hold(ti.psh[sl])), _p(hold(ti.pdbl[sl]))
+        d.qinv = _p(hold(ntt.qinv[dev][sl]))
         d.sR, d.sR_sh = _p(T(ntt.fs_R[0])), _p(T(ntt.fs_R[1]))
         d.sExit, d.sExit_sh = _p(T(ntt.fs_exit[0])), _p(T(ntt.fs_exit[1]))
-        d.sExitT, d.sExitT_sh = _p(T(ntt.fs_exit_tensor[0])), _p(T(ntt.fs_exit_tensor[1]))
         d.PiR = _p(hold(eng._moddown_table(level, dev)))
         d.part_alpha, d.Lenter = _p(part_alpha), _p(lenter_ptrs)
-        # first live row of every partition's own limbs on this device (-1: the partition lives elsewhere)
-        d.part_row0 = _p(i32([ntt.p.parts[level][dev][owners[s][1]][0] if owners[s][0] == dev else -1 for s in self.sids]))
         d.loc_row0, d.loc_alpha, d.loc_Y, d.loc_Ltri = _p(loc_row0), _p(loc_alpha), _p(loc_Y), _p(loc_L)
         if level > 0 and dev < len(eng.rescale_scales[level - 1]):
             d.rescale_scale = _p(hold(eng.rescale_scales[level - 1][dev]))
@@ -136,6 +142,7 @@ class LevelPlan:
             n_small += 1
         d.L_small = n_small
         d.amax = max(2, max(owners[s_][2] for s_ in self.sids))
+        self.fp64 = True      # Hm / Pinv tables present: the FP64 slab pipeline (the integer fall-back needs natural-order keys)
         self.desc = d
         self.ref = ctypes.byref(d)
         self._keep = keep
@@ -146,7 +153,6 @@ class LevelPlan:
         self.x = ws.get("x", 4 * L * N).view(4, L, N)
         self.d = ws.get("d", 3 * L * N).view(3, L, N)
         self.digits = ws.get("digits", max(L, 1) * N).view(max(L, 1), N)
-        self.d2hat = ws.get("d2hat", max(L, 1) * N).view(max(L, 1), N)   # NTT-domain d2 of the last tensor stage
         self.ks_ws = ws.get("ks", int(lib.ckks_exec_keyswitch_ws_elems(L, K, len(self.sids), N)))
         self.peer = {}                 # sid -> persistent copy of a remote partition's digits on this device
         self._digit_ptrs = None
@@ -166,20 +172,29 @@ class LevelPlan:
         return self._digit_ptrs
 
     def key_pointer_tables(self, eng, ksk):
+        """device tables of the row-0 pointers of every partition's key halves at this level -> (k0, k1, stride, permuted).
+        With option 18 (default) the stage keeps its NTT-domain data in warp-interleaved order, so the pointers go to
+        PERMUTED copies of the key rows (made once per key and device by ckks_perm_rows, cached on the engine)."""
         hit = self._key_ptrs.get(id(ksk.data))
-        if hit is None or hit[0] is not ksk.data:
+        permuted = bool(lib.ckks_get_option(18)) and self.fp64
+        if hit is None or hit[0] is not ksk.data or hit[4] != permuted:
             start = eng.ntt.starts[self.level][self.dev]
             p0, p1 = [], []
             for s in self.sids:
                 src, part_id, _alpha = self.owners[s]
                 kd = ksk.data[eng.parts_alloc[self.level][src][part_id]].data
-                p0.append(kd[0][self.dev][start:].data_ptr())
-                p1.append(kd[1][self.dev][start:].data_ptr())
+                h0, h1 = kd[0][self.dev], kd[1][self.dev]
+                if permuted:
+                    h0, h1 = eng._permuted_key(h0), eng._permuted_key(h1)
+                p0.append(h0[start:].data_ptr())
+                p1.append(h1[start:].data_ptr())
             dev = self.x.device
             hit = (ksk.data, torch.tensor(p0, dtype=torch.int64, device=dev),
-                   torch.tensor(p1, dtype=torch.int64, device=dev), ksk.data[0].data[0][self.dev].stride(0))
+                   torch.tensor(p1, dtype=torch.int64, device=dev), self.N, permuted) if permuted else \
+                  (ksk.data, torch.tensor(p0, dtype=torch.int64, device=dev),
+                   torch.tensor(p1, dtype=torch.int64, device=dev), ksk.data[0].data[0][self.dev].stride(0), permuted)
             self._key_ptrs[id(ksk.data)] = hit
-        return hit[1], hit[2], hit[3]
+        return hit[1], hit[2], hit[3], hit[4]
 
 
 def _stream(t):
@@ -189,17 +204,19 @@ def _stream(t):
 def tensor_stage(plan, polys, r0s):
     """polys: 4 tensors [L,N] (rows surviving the rescale, common row stride); r0s: 4 tensors [N] on this device"""
     s = polys[0].stride(0)
-    check(lib.ckks_exec_tensor_stage(plan.ref, *[_p(t) for t in polys], s, *[_p(t) for t in r0s], _p(plan.x), _p(plan.d),
-                                     _p(plan.digits), _p(plan.d2hat), _stream(plan.x)), "exec_tensor_stage")
+    with torch.cuda.device(plan.x.device):      # the C side launches on (and takes its side streams from) the CURRENT device
+        check(lib.ckks_exec_tensor_stage(plan.ref, *[_p(t) for t in polys], s, *[_p(t) for t in r0s], _p(plan.x), _p(plan.d),
+                                         _p(plan.digits), _stream(plan.x)), "exec_tensor_stage")
 
 
 def digits_stage(plan, a):
-    check(lib.ckks_exec_digits(plan.ref, _p(a), a.stride(0), _p(plan.digits), plan.N, _stream(a)), "exec_digits")
+    with torch.cuda.device(a.device):
+        check(lib.ckks_exec_digits(plan.ref, _p(a), a.stride(0), _p(plan.digits), plan.N, _stream(a)), "exec_digits")
 
 
-def keyswitch_stage(plan, digit_ptrs, k0p, k1p, kstride, add0, add1, out0, out1, d2hat=None):
-    """d2hat: plan.d2hat when the digits come from the tensor stage that has just run on this plan (relinearize)"""
+def keyswitch_stage(plan, digit_ptrs, k0p, k1p, kstride, permuted, add0, add1, out0, out1):
     add = add0 if add0 is not None else add1
-    check(lib.ckks_exec_keyswitch_stage(plan.ref, _p(digit_ptrs), plan.N, _p(k0p), _p(k1p), kstride, _p(add0), _p(add1),
-                                        add.stride(0) if add is not None else 0, _p(out0), _p(out1), plan.N,
-                                        _p(plan.ks_ws), _p(d2hat), _stream(out0)), "exec_keyswitch_stage")
+    with torch.cuda.device(out0.device):
+        check(lib.ckks_exec_keyswitch_stage(plan.ref, _p(digit_ptrs), plan.N, _p(k0p), _p(k1p), kstride, 1 if permuted else 0,
+                                            _p(add0), _p(add1), add.stride(0) if add is not None else 0, _p(out0), _p(out1),
+                                            plan.N, _p(plan.ks_ws), _stream(out0)), "exec_keyswitch_stage")

@@ -114,37 +114,79 @@ def automorphism(x, g, canon, _2q=None):
     return out
 
 
+class FastTables:
+    """fast-transform tables of one direction for the limbs of one device: plain {w, w'} / double tables plus the
+    PACKED copies of the last four stages (include/ckks_b200.h: ckks_fast_pack).  Slicing keeps the four in step."""
+
+    def __init__(self, sh, dbl, psh, pdbl):
+        self.sh, self.dbl, self.psh, self.pdbl = sh, dbl, psh, pdbl
+
+    def __getitem__(self, sl):
+        return FastTables(self.sh[sl], self.dbl[sl], self.psh[sl], self.pdbl[sl])
+
+    def __iter__(self):             # (sh, dbl) = tables: the two plain tables, as before
+        return iter((self.sh, self.dbl))
+
+
 def fast_tables(plain, q):
-    """plain canonical twiddles [C,N] -> (shoup [C,N,2] as int64 {w, floor(w 2^64/q)}, dbl [C,N] float64)"""
+    """plain canonical twiddles [C,N] -> FastTables (shoup [C,N,2] int64 {w, floor(w 2^64/q)}, dbl [C,N] float64, packed copies)"""
     C, N = plain.shape
+    logN = int(N).bit_length() - 1
     sh = torch.empty((C, N, 2), dtype=torch.int64, device=plain.device)
     dbl = torch.empty((C, N), dtype=torch.float64, device=plain.device)
+    psh, pdbl = torch.empty_like(sh), torch.empty_like(dbl)
     with _Launch(plain):
         check(lib.ckks_fast_tables(_ptr(plain), _ptr(_vec(q)), _ptr(sh), _ptr(dbl), C, N, _stream(plain)), "fast_tables")
-    return sh, dbl
+        check(lib.ckks_fast_pack(_ptr(sh), _ptr(dbl), _ptr(psh), _ptr(pdbl), C, logN, _stream(plain)), "fast_pack")
+    return FastTables(sh, dbl, psh, pdbl)
 
 
-def ntt_fast(x, tw_u64, tw_f64, q, scal=None, scal_sh=None, period=None, force_int=False):
-    """canonical-output forward NTT in place: x [rows,N] in [0,2q) -> NTT(x * scal) in [0,q)"""
+def reciprocals(q):
+    """[C] float64 1/q, correctly rounded (what the kernels would compute per CTA with an FP64 division)"""
+    return torch.tensor([1.0 / float(int(x)) for x in q.tolist()], dtype=torch.float64, device=q.device)
+
+
+def _tables(tables, tw_f64):
+    """accept FastTables or the (tw_u64, tw_f64) pair -> the four table pointers"""
+    if isinstance(tables, FastTables):
+        return _ptr(tables.sh), _ptr(tables.dbl), _ptr(tables.psh), _ptr(tables.pdbl)
+    return _ptr(tables), _ptr(tw_f64), None, None
+
+
+def ntt_fast(x, tables, tw_f64, q, scal=None, scal_sh=None, period=None, force_int=False, qinv=None):
+    """canonical-output forward NTT in place: x [rows,N] in [0,2q) -> NTT(x * scal) in [0,q).
+    tables: FastTables (tw_f64 ignored) or the plain {w, w'} table with tw_f64 the double table"""
     s = _rows(x, "ntt_fast")
     rows, N = x.shape
     logN = int(N).bit_length() - 1
     with _Launch(x):
-        check(lib.ckks_ntt_fast(_ptr(x), s, rows, period or rows, logN, _ptr(tw_u64), _ptr(tw_f64), _ptr(_vec(q)),
+        check(lib.ckks_ntt_fast(_ptr(x), s, rows, period or rows, logN, *_tables(tables, tw_f64), _ptr(_vec(q)),
+                                _ptr(qinv) if qinv is not None else None,
                                 _ptr(scal) if scal is not None else None,
                                 _ptr(scal_sh) if scal_sh is not None else None, 1 if force_int else 0, _stream(x)),
               "ntt_fast")
 
 
-def intt_fast(x, tw_u64, tw_f64, q, scal, scal_sh, centred=False, period=None, force_int=False):
+def intt_fast(x, tables, tw_f64, q, scal, scal_sh, centred=False, period=None, force_int=False, qinv=None):
     """canonical-output inverse NTT in place: x [rows,N] in [0,2q) -> iNTT(x) * scal in [0,q) (or centred)"""
     s = _rows(x, "intt_fast")
     rows, N = x.shape
     logN = int(N).bit_length() - 1
     with _Launch(x):
-        check(lib.ckks_intt_fast(_ptr(x), s, rows, period or rows, logN, _ptr(tw_u64), _ptr(tw_f64), _ptr(_vec(q)),
+        check(lib.ckks_intt_fast(_ptr(x), s, rows, period or rows, logN, *_tables(tables, tw_f64), _ptr(_vec(q)),
+                                 _ptr(qinv) if qinv is not None else None,
                                  _ptr(scal), _ptr(scal_sh), 1 if centred else 0, 1 if force_int else 0, _stream(x)),
               "intt_fast")
+
+
+def perm_rows(x, inverse=False):
+    """NTT-domain rows natural -> warp-interleaved order of the fused executor (inverse=True: back); returns a new tensor"""
+    s = _rows(x, "perm_rows")
+    rows, N = x.shape
+    out = torch.empty((rows, N), dtype=torch.int64, device=x.device)
+    with _Launch(x):
+        check(lib.ckks_perm_rows(_ptr(x), s, _ptr(out), N, rows, N, 1 if inverse else 0, _stream(x)), "perm_rows")
+    return out
 
 
 def ksk_inner(ext_all, parts, k0_ptrs, k1_ptrs, ksk_stride, acc0, acc1, mp):

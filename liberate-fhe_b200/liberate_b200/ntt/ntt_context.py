@@ -80,7 +80,8 @@ class ntt_context:
         self.Ninv = self.partition_variable([(ni * R) % q for ni, q in zip(c.N_inv, c.q)])
         self.mont_pack0 = [self.ql, self.qh, self.kl, self.kh]
         fwd, inv = c.psi_stage_factors()
-        # plain-twiddle tables of the canonical-output fast transforms: ({w, floor(w 2^64/q)} [rows,N,2], double [rows,N])
+        # plain-twiddle tables of the canonical-output fast transforms (fused.FastTables: {w, floor(w 2^64/q)} [rows,N,2],
+        # double [rows,N], and the packed copies of the last four stages)
         self.tw_fast_fwd = [None] * self.num_devices
         self.tw_fast_inv = [None] * self.num_devices
         self.psi = [self._grow_twiddles(d, fwd, self.tw_fast_fwd) if self.is_local(d) else None
@@ -89,12 +90,9 @@ class ntt_context:
                      for d in range(self.num_devices)]
         # per-limb plain scalars of the fast transforms with their Shoup companions (uint64 bit patterns)
         Rinv = [pow(R, -1, q) for q in c.q]
+        self.qinv = [fused.reciprocals(self.q[d]) if self.is_local(d) else None for d in range(self.num_devices)]
         self.fs_R = self._fast_scalar([R % q for q in c.q])                                   # "enter": x R
         self.fs_exit = self._fast_scalar([ni * ri % q for ni, ri, q in zip(c.N_inv, Rinv, c.q)])  # x N^-1 R^-1
-        # exit of the inverse transform with the tensor product fused into its load: the FP64 product of two
-        # Montgomery-form operands (scale primes, q < 2^42) carries R^2, the integer Montgomery product only R
-        self.fs_exit_tensor = self._fast_scalar([ni * ri * (ri if q < (1 << 42) else 1) % q
-                                                 for ni, ri, q in zip(c.N_inv, Rinv, c.q)])
         self.fs_ninv = self._fast_scalar(list(c.N_inv))                                        # x N^-1
 
     def _fast_scalar(self, values):
@@ -231,16 +229,16 @@ class ntt_context:
     def ntt_fast(self, x, lvl, dev, part=-1, enter=False, batched=False):
         """x: [rows, N] (or [parts*rows, N] with batched=True) in [0,2q) -> canonical NTT(x [* R])"""
         (_, a, b), = self.rows(lvl, dev, part)
-        sh, dbl = self.tw_fast_fwd[dev]
         sc = (self.fs_R[0][dev][a:b], self.fs_R[1][dev][a:b]) if enter else (None, None)
-        fused.ntt_fast(x, sh[a:b], dbl[a:b], self.q[dev][a:b], sc[0], sc[1], period=(b - a) if batched else None)
+        fused.ntt_fast(x, self.tw_fast_fwd[dev][a:b], None, self.q[dev][a:b], sc[0], sc[1],
+                       period=(b - a) if batched else None, qinv=self.qinv[dev][a:b])
 
     def intt_fast(self, x, lvl, dev, part=-1, exit=True, centred=False):
         """x: [rows, N] in [0,2q) -> canonical iNTT(x) * N^-1 [* R^-1]  (== intt_exit_reduce / intt + reduce)"""
         (_, a, b), = self.rows(lvl, dev, part)
-        sh, dbl = self.tw_fast_inv[dev]
         sc = self.fs_exit if exit else self.fs_ninv
-        fused.intt_fast(x, sh[a:b], dbl[a:b], self.q[dev][a:b], sc[0][dev][a:b], sc[1][dev][a:b], centred=centred)
+        fused.intt_fast(x, self.tw_fast_inv[dev][a:b], None, self.q[dev][a:b], sc[0][dev][a:b], sc[1][dev][a:b],
+                        centred=centred, qinv=self.qinv[dev][a:b])
 
     @staticmethod
     def _live(a):

@@ -264,6 +264,16 @@ void orc_enter_ntt(int64_t *a, ptrdiff_t as, const int64_t *Rs, int C, int logN,
     orc_ntt(a, as, C, logN, psi, ps, _2q, ql, qh, kl, kh);
 }
 
+/* the bench's reference arm sets its own thread count: torchrun exports OMP_NUM_THREADS=1 to every rank */
+void orc_set_num_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int orc_num_threads(void)
 {
 #ifdef _OPENMP

@@ -37,9 +37,12 @@ qd = torch.tensor(q, dtype=torch.int64, device="cuda")
 tw = (torch.randint(0, 1 << 62, (E, N), dtype=torch.int64, device="cuda", generator=g) % qd[:, None]).contiguous()
 twu = torch.empty((E, N, 2), dtype=torch.int64, device="cuda")
 twd = torch.empty((E, N), dtype=torch.float64, device="cuda")
+twpu, twpd = torch.empty_like(twu), torch.empty_like(twd)
 st = torch.cuda.current_stream().cuda_stream
 P = lambda t: t.data_ptr()
 check(lib.ckks_fast_tables(P(tw), P(qd), P(twu), P(twd), E, N, st), "tables")
+check(lib.ckks_fast_pack(P(twu), P(twd), P(twpu), P(twpd), E, logN, st), "pack")
+qinv = torch.tensor([1.0 / float(x) for x in q], dtype=torch.float64, device="cuda")
 sc = (torch.randint(1, 1 << 62, (E,), dtype=torch.int64, device="cuda", generator=g) % qd).contiguous()
 sc_sh = torch.tensor([((int(s) << 64) // int(m)) - (1 << 64) if ((int(s) << 64) // int(m)) >= (1 << 63) else (int(s) << 64) // int(m)
                       for s, m in zip(sc.tolist(), q)], dtype=torch.int64, device="cuda")
@@ -49,16 +52,18 @@ bufs = [src.clone() for _ in range(nbuf)]
 
 
 def fwd(b):
-    check(lib.ckks_ntt_fast(P(b), N, rows, E, logN, P(twu), P(twd), P(qd), None, None, 0, st), "ntt_fast")
+    check(lib.ckks_ntt_fast(P(b), N, rows, E, logN, P(twu), P(twd), P(twpu), P(twpd), P(qd), P(qinv), None, None, 0, st), "ntt_fast")
 
 
 def inv(b):
-    check(lib.ckks_intt_fast(P(b), N, rows, E, logN, P(twu), P(twd), P(qd), P(sc), P(sc_sh), 0, 0, st), "intt_fast")
+    check(lib.ckks_intt_fast(P(b), N, rows, E, logN, P(twu), P(twd), P(twpu), P(twpd), P(qd), P(qinv), P(sc), P(sc_sh), 0, 0, st), "intt_fast")
 
 
 def set_opts(o):
     for k, v in option_defaults().items():
         lib.ckks_set_option(k, v)
+    lib.ckks_set_option(5, 0)
+    lib.ckks_set_option(20, 0)
     for k, v in o:
         lib.ckks_set_option(k, v)
 
@@ -88,14 +93,19 @@ for o in optsets:
         if not o:
             ref[name] = x
             same = True
+        elif (20, 1) in o:      # warp-interleaved NTT domain: compare after undoing the permutation / on a permuted input
+            same = None
         else:
             same = bool(torch.equal(x, ref[name]))
         set_opts(o)
         t_all = timeit(fn)
-        set_opts(o + [(5, 2)])
-        t_col = timeit(fn)
-        set_opts(o + [(5, 1)])
-        t_blk = timeit(fn)
+        has_skip = lib.ckks_get_option(5) >= 0          # lab builds only (-DCKKS_LAB)
+        t_col = t_blk = float("nan")
+        if has_skip:
+            set_opts(o + [(5, 2)])
+            t_col = timeit(fn)
+            set_opts(o + [(5, 1)])
+            t_blk = timeit(fn)
         line[name] = dict(us=round(t_all, 1), col=round(t_col, 1), blk=round(t_blk, 1), same=same,
                           gbps=round(16.0 * rows * N / t_all / 1e3, 1))
     print(json.dumps({"lib": Path(str(lib._cdll._name)).name, "opts": o, **line}), flush=True)

@@ -128,11 +128,12 @@ def test_captured_graph_replays_the_same_bits(D):
     torch.cuda.synchronize()
 
 
-@pytest.mark.parametrize("opts", [[(12, 0)], [(13, 1)], [(14, 1)], [(13, 1), (14, 1)], [(10, 1), (9, 400)], [(9, 1)]],
-                         ids=["no-rescale-fusion", "tensor-fusion", "own-skip", "tensor+own", "one-stream", "many-slabs"])
+@pytest.mark.parametrize("opts", [[(12, 0)], [(18, 0)], [(17, 0)], [(17, 0), (18, 0)], [(10, 1), (9, 400)], [(9, 1)], [(16, 0)]],
+                         ids=["no-rescale-fusion", "natural-order", "plain-twiddles", "plain+natural", "one-stream",
+                              "many-slabs", "joint-tail"])
 def test_optional_fused_paths_reproduce_reference_tensors(opts):
-    """every ckks_set_option variant of the executor (rescale / tensor-product fusion, own-partition skip, slab and
-    side-stream settings) must hit the same golden digests as the default path"""
+    """every ckks_set_option variant of the executor (rescale fusion, warp-interleaved NTT-domain order with permuted key
+    copies, packed twiddles, slab and side-stream settings) must hit the same golden digests as the default path"""
     from liberate_b200._lib import lib, option_defaults
     g = json.loads((GOLDEN / "engine_D2.json").read_text())
     full = np.load(GOLDEN / "engine_D2_full.npz")

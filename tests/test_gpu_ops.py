@@ -220,10 +220,10 @@ def test_fused_keyswitch_pieces_bit_exact(logN, alpha, K):
         assert eq(got, ref2), "automorphism+canon"
 
 
-# kernel variants of the fast transforms selected by ckks_set_option (key, value); every one must give the same bits
-FAST_VARIANTS = {"default": [], "classic": [(3, 0), (4, 0)], "warp": [(3, 1), (4, 0)], "pp": [(3, 2), (4, 1)],
-                 "pp-3ctas": [(3, 2), (4, 1), (7, 3)], "swapped-grid": [(8, 1)], "warp+swapped": [(3, 1), (8, 1)],
-                 "hybrid-twiddles": [(3, 3)], "no-hybrid": [(15, 0)], "hybrid-everywhere": [(15, 7)]}   # 3 persistent CTAs in total: each walks many tiles and limbs
+# variants of the fast transforms: library knobs (ckks_set_option) and whether the caller passes the packed tables;
+# every one must give the same bits
+FAST_VARIANTS = {"default": ([], True), "plain-tables": ([], False), "packed-off": ([(17, 0)], True),
+                 "no-prefetch": ([(2, 0)], True), "one-stream": ([(10, 1)], True), "small-slabs": ([(11, 1)], True)}
 
 
 @pytest.mark.parametrize("logN", [12, 13, 14, 15, 16, 17])
@@ -233,16 +233,17 @@ def test_fast_transforms_equal_reference_sequences_after_reduction(logN, force_i
     """ckks_ntt_fast == {enter_ntt; reduce_2q}, ckks_intt_fast == intt_exit_reduce[_signed] (canonical outputs):
     FP64 error-free butterflies for the scale primes, Shoup/Harvey for the 60-bit primes."""
     from liberate_b200._lib import lib, option_defaults
+    opts, packed = FAST_VARIANTS[variant]
     try:
-        for k, v in FAST_VARIANTS[variant]:
-            lib.ckks_set_option(k, v)
-        _check_fast_transforms(logN, force_int)
+        for k, v in opts:
+            assert lib.ckks_set_option(k, v) == 0
+        _check_fast_transforms(logN, force_int, packed)
     finally:
         for k, v in option_defaults().items():
             lib.ckks_set_option(k, v)
 
 
-def _check_fast_transforms(logN, force_int):
+def _check_fast_transforms(logN, force_int, packed=True):
     from liberate_b200.ntt import fused
     P = O.Params(primes_for(logN, 3, 2), logN)
     t = packs(P)
@@ -250,9 +251,13 @@ def _check_fast_transforms(logN, force_int):
     rng = np.random.default_rng(300 + logN)
     q = np.array(P.q, dtype=np.int64)
     R = O.R
-    sh_f, dbl_f = fused.fast_tables(T(P.psi_plain), t["_2q"] // 2)
-    sh_i, dbl_i = fused.fast_tables(T(P.ipsi_plain), t["_2q"] // 2)
+    tf = fused.fast_tables(T(P.psi_plain), t["_2q"] // 2)
+    ti = fused.fast_tables(T(P.ipsi_plain), t["_2q"] // 2)
+    # packed=True: the FastTables object (block passes read the packed last-group tables); False: the two plain tables
+    sh_f, dbl_f = (tf, None) if packed else tuple(tf)
+    sh_i, dbl_i = (ti, None) if packed else tuple(ti)
     qd = T(q)
+    qinv = fused.reciprocals(qd) if packed else None
 
     def shoup(s):
         out = []
@@ -265,14 +270,14 @@ def _check_fast_transforms(logN, force_int):
     a = rng.integers(0, 2 * q[:, None], (C, N), dtype=np.int64)
     Rp = np.array([R % int(m) for m in q], dtype=np.int64)
     x = T(a)
-    fused.ntt_fast(x, sh_f, dbl_f, qd, T(Rp), T(shoup(Rp)), force_int=force_int)
+    fused.ntt_fast(x, sh_f, dbl_f, qd, T(Rp), T(shoup(Rp)), force_int=force_int, qinv=qinv)
     ref = a.copy()
     O.C.enter_ntt(ref, P.Rs, P.psi, P._2q, *P.mont)
     O.C.reduce_2q(ref, P._2q)
     assert eq(x, ref), "ntt_fast(enter)"
     # forward without scalar
     x = T(a)
-    fused.ntt_fast(x, sh_f, dbl_f, qd, force_int=force_int)
+    fused.ntt_fast(x, sh_f, dbl_f, qd, force_int=force_int, qinv=qinv)
     ref2 = a.copy()
     O.C.ntt(ref2, P.psi, P._2q, *P.mont)
     O.C.reduce_2q(ref2, P._2q)
@@ -283,46 +288,38 @@ def _check_fast_transforms(logN, force_int):
     ex = np.array([pow(N, -1, int(m)) * pow(R, -1, int(m)) % int(m) for m in q], dtype=np.int64)
     for centred, mode in ((False, 2), (True, 3)):
         y = T(lazy)
-        fused.intt_fast(y, sh_i, dbl_i, qd, T(ex), T(shoup(ex)), centred=centred, force_int=force_int)
+        fused.intt_fast(y, sh_i, dbl_i, qd, T(ex), T(shoup(ex)), centred=centred, force_int=force_int, qinv=qinv)
         r = lazy.copy()
         O.C.intt(r, P.ipsi, P.Ninv, P._2q, *P.mont, exit_mode=mode)
         assert eq(y, r), f"intt_fast centred={centred}"
     # batched rows: 2 x C rows share the C limbs' constants (period = C)
     reps = 5
     big = T(np.concatenate([a] * reps))
-    fused.ntt_fast(big, sh_f, dbl_f, qd, period=C, force_int=force_int)
+    fused.ntt_fast(big, sh_f, dbl_f, qd, period=C, force_int=force_int, qinv=qinv)
     for i in range(reps):
         assert eq(big[i * C:(i + 1) * C], ref2), f"batched period, replica {i}"
     big = T(np.concatenate([lazy] * reps))
-    fused.intt_fast(big, sh_i, dbl_i, qd, T(ex), T(shoup(ex)), period=C, centred=False, force_int=force_int)
+    fused.intt_fast(big, sh_i, dbl_i, qd, T(ex), T(shoup(ex)), period=C, centred=False, force_int=force_int, qinv=qinv)
     r = lazy.copy()
     O.C.intt(r, P.ipsi, P.Ninv, P._2q, *P.mont, exit_mode=2)
     for i in range(reps):
         assert eq(big[i * C:(i + 1) * C], r), f"batched inverse, replica {i}"
 
 
-@pytest.mark.parametrize("logN", [12, 14, 16, 17])
-def test_fast_forward_persistent_blockpass_option(logN):
-    """ckks_set_option(1, 1): the block pass runs as one CTA per SM fed by a TMA ring; results do not change."""
-    from liberate_b200._lib import lib
+@pytest.mark.parametrize("logN", [12, 16])
+def test_perm_rows_is_the_documented_permutation(logN):
+    """ckks_perm_rows: inside every 512-coefficient tile, coefficient 16 t + k <-> ((k >> 1) * 32 + t) * 2 + (k & 1)"""
     from liberate_b200.ntt import fused
-    P = O.Params(primes_for(logN, 3, 2), logN)
-    t = packs(P)
-    C = len(P.q)
-    rng = np.random.default_rng(900 + logN)
-    q = np.array(P.q, dtype=np.int64)
-    sh_f, dbl_f = fused.fast_tables(T(P.psi_plain), t["_2q"] // 2)
-    a = rng.integers(0, 2 * q[:, None], (C, P.N), dtype=np.int64)
-    ref = a.copy()
-    O.C.ntt(ref, P.psi, P._2q, *P.mont)
-    O.C.reduce_2q(ref, P._2q)
-    reps = 7                                  # enough tiles that every CTA loops and slots wrap around
-    big = T(np.concatenate([a] * reps))
-    try:
-        lib.ckks_set_option(1, 1)
-        fused.ntt_fast(big, sh_f, dbl_f, T(q), period=C)
-        torch.cuda.synchronize()
-    finally:
-        lib.ckks_set_option(1, 0)
-    for r in range(reps):
-        assert eq(big[r * C:(r + 1) * C], ref), f"persistent block pass, replica {r}"
+    N = 1 << logN
+    x = torch.arange(3 * N, dtype=torch.int64, device="cuda").view(3, N)
+    i = np.arange(N)
+    tile, t, k = i >> 9, (i >> 4) & 31, i & 15
+    pos = (tile << 9) + (((k >> 1) * 32 + t) << 1) + (k & 1)
+    want = np.empty((3, N), dtype=np.int64)
+    want[:, pos] = x.cpu().numpy()
+    y = fused.perm_rows(x)
+    assert eq(y, want)
+    assert eq(fused.perm_rows(y, inverse=True), x.cpu().numpy())
+    # strided rows in, contiguous rows out
+    big = torch.arange(6 * N, dtype=torch.int64, device="cuda").view(6, N)
+    assert eq(fused.perm_rows(big[1:4]), fused.perm_rows(big[1:4].clone()).cpu().numpy())
