@@ -100,13 +100,14 @@ int ckks_fast_tables(const int64_t* plain, const int64_t* q, void* tw_u64, doubl
  * 15 twiddles there; per 512-coefficient warp tile they are stored lane-interleaved so that the loads of a warp are
  * contiguous 256/512-byte runs (ntt_fast.cuh: TwPacked).  Same sizes as the plain tables: [C][N] x 16 B and [C][N] x 8 B. */
 int ckks_fast_pack(const void* tw_u64, const double* tw_f64, void* twp_u64, double* twp_f64, int C, int logN, void* stream);
-/* twp_u64 / twp_f64: the packed tables or NULL; qinv: [period] doubles 1/q or NULL (then computed per CTA) */
+/* twp_u64 / twp_f64: the packed tables or NULL; qinv: [period] doubles 1/q or NULL (then computed per CTA);
+ * perm != 0: the NTT-domain side (forward output / inverse input) is in warp-interleaved order (see ckks_perm_rows) */
 int ckks_ntt_fast(int64_t* a, int64_t a_stride, int rows, int period, int logN, const void* tw_u64,
                   const double* tw_f64, const void* twp_u64, const double* twp_f64, const int64_t* q, const double* qinv,
-                  const int64_t* scal, const uint64_t* scal_sh, int force_int, void* stream);
+                  const int64_t* scal, const uint64_t* scal_sh, int force_int, int perm, void* stream);
 int ckks_intt_fast(int64_t* a, int64_t a_stride, int rows, int period, int logN, const void* tw_u64,
                    const double* tw_f64, const void* twp_u64, const double* twp_f64, const int64_t* q, const double* qinv,
-                   const int64_t* scal, const uint64_t* scal_sh, int centred, int force_int, void* stream);
+                   const int64_t* scal, const uint64_t* scal_sh, int centred, int force_int, int perm, void* stream);
 /* NTT-domain rows between natural order and the executor's warp-interleaved order (inverse != 0: back to natural):
  * inside every 512-coefficient tile, coefficient 16 t + k <-> position ((k >> 1) * 32 + t) * 2 + (k & 1).  Out of place.
  * Used once per evaluation / rotation key (the engine caches the permuted copy). */

@@ -442,9 +442,9 @@ static int launch_inv_block(const NttArgs& A, dim3 grid, cudaStream_t st) {
 }
 
 // ---- tuning knobs (ckks_set_option) -------------------------------------------------------------------------------
-int g_prefetch = PREFETCH_ROWS_AHEAD;   // 2: L2 prefetch distance in rows (0 = off)
+int g_prefetch = 0;       // 2: L2 prefetch distance in rows (0 = off: with the row-slab pipelines the next tile is in L2 anyway)
 int g_slab_mb = 100;      // 9: MB of extended rows per key-switch slab (L2 residency vs grid size)
-int g_pipes = 2;          // 10: internal side streams used by the slab pipelines (1 = everything on the caller's stream)
+int g_pipes = 3;          // 10: internal side streams used by the slab pipelines (1 = everything on the caller's stream)
 int g_ntt_slab_mb = 24;   // 11: MB of rows per slab of a big batched transform
 int g_fuse_rescale = 1;   // 12: rescale fused into the tensor stage's column pass
 int g_split_tail = 1;     // 16: inverse transform + ModDown of the two output polynomials on two streams
@@ -452,22 +452,50 @@ int g_packed = 1;         // 17: block passes read the last-group twiddles from 
 int g_perm = 1;           // 18: the executor keeps NTT-domain data in warp-interleaved order (needs permuted key copies)
 #ifdef CKKS_LAB
 int g_skip = 0;           // 5 (lab builds only): measurement -- bit 0 skips the column pass, bit 1 the block pass
-int g_lab_perm = 0;       // 20 (lab builds only): ckks_ntt_fast / ckks_intt_fast keep the NTT domain warp-interleaved
+int g_lab = 0;            // 21 (lab builds only): FastArgs::lab -- bit 0 no butterflies, bit 1 no global loads / stores
 #else
 constexpr int g_skip = 0;
-constexpr int g_lab_perm = 0;
 #endif
 inline bool aligned32(const void* p, long long stride) { return (((uintptr_t)p) & 31) == 0 && (stride & 3) == 0; }
 
-static int launch_fast_col(bool fwd, const FastArgs& F, dim3 grid, cudaStream_t st) {
+template <int B>
+static int launch_fast_col_b(bool fwd, const FastArgs& F, dim3 grid, cudaStream_t st) {
     if (fwd) {
-        cudaFuncSetAttribute(fast_fwd_colpass<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, COL_SMEM_BYTES);
-        fast_fwd_colpass<0><<<grid, NTT_THREADS, COL_SMEM_BYTES, st>>>(F);
+        cudaFuncSetAttribute(fast_fwd_colpass<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, COL_SMEM_BYTES);
+        fast_fwd_colpass<B><<<grid, NTT_THREADS, COL_SMEM_BYTES, st>>>(F);
     } else {
-        cudaFuncSetAttribute(fast_inv_colpass<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, COL_SMEM_BYTES);
-        fast_inv_colpass<0><<<grid, NTT_THREADS, COL_SMEM_BYTES, st>>>(F);
+        cudaFuncSetAttribute(fast_inv_colpass<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, COL_SMEM_BYTES);
+        fast_inv_colpass<B><<<grid, NTT_THREADS, COL_SMEM_BYTES, st>>>(F);
     }
     return launch_status();
+}
+static int launch_fast_col(bool fwd, const FastArgs& F, dim3 grid, cudaStream_t st) {
+    switch (F.logN - 8) {
+        case 4: return launch_fast_col_b<4>(fwd, F, grid, st);
+        case 5: return launch_fast_col_b<5>(fwd, F, grid, st);
+        case 6: return launch_fast_col_b<6>(fwd, F, grid, st);
+        case 7: return launch_fast_col_b<7>(fwd, F, grid, st);
+        case 8: return launch_fast_col_b<8>(fwd, F, grid, st);
+        case 9: return launch_fast_col_b<9>(fwd, F, grid, st);
+    }
+    return CKKS_E_LOGN;
+}
+template <int B>
+static int launch_col_rescale_b(const FastArgs& F, const RescaleIn& R, dim3 grid, cudaStream_t st) {
+    cudaFuncSetAttribute(fast_fwd_colpass_rescale<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, COL_SMEM_BYTES);
+    fast_fwd_colpass_rescale<B><<<grid, NTT_THREADS, COL_SMEM_BYTES, st>>>(F, R);
+    return launch_status();
+}
+static int launch_col_rescale(const FastArgs& F, const RescaleIn& R, dim3 grid, cudaStream_t st) {
+    switch (F.logN - 8) {
+        case 4: return launch_col_rescale_b<4>(F, R, grid, st);
+        case 5: return launch_col_rescale_b<5>(F, R, grid, st);
+        case 6: return launch_col_rescale_b<6>(F, R, grid, st);
+        case 7: return launch_col_rescale_b<7>(F, R, grid, st);
+        case 8: return launch_col_rescale_b<8>(F, R, grid, st);
+        case 9: return launch_col_rescale_b<9>(F, R, grid, st);
+    }
+    return CKKS_E_LOGN;
 }
 template <int B>
 static int launch_fast_block(bool fwd, const FastArgs& F, dim3 grid, cudaStream_t st) {
@@ -613,6 +641,9 @@ static FastArgs fast_args(int64_t* a, long long as, const void* tw_u64, const do
     F.q = q; F.qinv = qinv; F.scal = scal; F.scal_sh = scal_sh;
     F.period = period; F.logN = logN;
     F.prefetch = g_prefetch;
+#ifdef CKKS_LAB
+    F.lab = g_lab;
+#endif
     return F;
 }
 static int fast_check(const void* a, long long as, int rows, int period, int logN, const void* tw_u64, const double* tw_f64,
@@ -637,7 +668,7 @@ static int* option_slot(int key) {
         case 2: return &g_prefetch;
 #ifdef CKKS_LAB
         case 5: return &g_skip;
-        case 20: return &g_lab_perm;
+        case 21: return &g_lab;
 #endif
         case 9: return &g_slab_mb;
         case 10: return &g_pipes;
@@ -828,25 +859,25 @@ int ckks_perm_rows(const int64_t* in, int64_t in_stride, int64_t* out, int64_t o
 
 int ckks_ntt_fast(int64_t* a, int64_t as, int rows, int period, int logN, const void* tw_u64, const double* tw_f64,
                   const void* twp_u64, const double* twp_f64, const int64_t* q, const double* qinv, const int64_t* scal,
-                  const uint64_t* scal_sh, int force_int, void* stream) {
+                  const uint64_t* scal_sh, int force_int, int perm, void* stream) {
     CHECK_PTRS(a, tw_u64, q);
     if (scal && !scal_sh) return CKKS_E_BADARG;
     RC(fast_check(a, as, rows, period, logN, tw_u64, tw_f64, twp_u64, twp_f64, force_int));
     FastArgs F = fast_args(a, as, tw_u64, tw_f64, twp_u64, twp_f64, q, qinv, scal, scal_sh, period, logN);
     F.force_int = force_int ? 1 : 0;
-    F.perm = g_lab_perm;
+    F.perm = perm ? 1 : 0;
     return fast_transform(true, F, rows, S(stream));
 }
 
 int ckks_intt_fast(int64_t* a, int64_t as, int rows, int period, int logN, const void* tw_u64, const double* tw_f64,
                    const void* twp_u64, const double* twp_f64, const int64_t* q, const double* qinv, const int64_t* scal,
-                   const uint64_t* scal_sh, int centred, int force_int, void* stream) {
+                   const uint64_t* scal_sh, int centred, int force_int, int perm, void* stream) {
     CHECK_PTRS(a, tw_u64, q, scal, scal_sh);
     RC(fast_check(a, as, rows, period, logN, tw_u64, tw_f64, twp_u64, twp_f64, force_int));
     FastArgs F = fast_args(a, as, tw_u64, tw_f64, twp_u64, twp_f64, q, qinv, scal, scal_sh, period, logN);
     F.force_int = force_int ? 1 : 0;
     F.centred = centred;
-    F.perm = g_lab_perm;
+    F.perm = perm ? 1 : 0;
     return fast_transform(false, F, rows, S(stream));
 }
 
@@ -982,9 +1013,7 @@ int ckks_exec_tensor_stage(const ckks_level_t* lv, const int64_t* a0, const int6
         FastArgs F = level_fast(lv, x, N, true, lv->sR, lv->sR_sh, L);
         F.prefetch = 0;
         const dim3 grid(N / TILE, 4 * L);
-        cudaFuncSetAttribute(fast_fwd_colpass_rescale<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, COL_SMEM_BYTES);
-        fast_fwd_colpass_rescale<0><<<grid, NTT_THREADS, COL_SMEM_BYTES, st>>>(F, R);
-        RC(launch_status());
+        RC(launch_col_rescale(F, R, grid, st));
         F.scal = nullptr;
         F.prefetch = g_prefetch;
         F.perm = perm;

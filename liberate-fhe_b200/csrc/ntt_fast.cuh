@@ -281,6 +281,11 @@ constexpr int PREFETCH_ROWS_AHEAD = 28;   // x 16 chunks ~ one wave of 3 CTAs x 
 __device__ __forceinline__ void l2_prefetch_bulk(const void* gptr, unsigned bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
 }
+// pulls one line into L1 without keeping a register (the destination is never read)
+__device__ __forceinline__ void l1_touch(const void* gptr) {
+    unsigned dummy;
+    asm volatile("ld.global.nc.L1::evict_last.b32 %0, [%1];" : "=r"(dummy) : "l"(gptr));
+}
 __device__ __forceinline__ void l2_prefetch_line(const void* gptr) {
     asm volatile("prefetch.global.L2 [%0];" ::"l"(gptr));
 }
@@ -405,7 +410,17 @@ struct FastArgs {
     // so the block passes move a thread's 16 contiguous coefficients as eight lane-contiguous 128-bit accesses
     // (512 contiguous bytes per warp instruction) instead of four 256-bit accesses 128 bytes apart (32 lines per instruction).
     int perm;
+    // lab builds (-DCKKS_LAB) only: bit 0 = skip the butterfly rounds, bit 1 = skip the global loads / stores of the
+    // forward passes -- separates "FP64 work" from "memory + overhead" when timing a pass (scripts/ntt_lab.py)
+    int lab;
 };
+#ifdef CKKS_LAB
+#define LAB_SKIP_MATH(F) ((F).lab & 1)
+#define LAB_SKIP_MEM(F) ((F).lab & 2)
+#else
+#define LAB_SKIP_MATH(F) false
+#define LAB_SKIP_MEM(F) false
+#endif
 
 __device__ __forceinline__ int grid_row(const FastArgs& F) { return blockIdx.y; }
 __device__ __forceinline__ unsigned grid_chunk(const FastArgs& F) { return blockIdx.x; }
@@ -526,13 +541,16 @@ struct RescaleIn {
     int L;
 };
 
-template <class A>
-__device__ __forceinline__ void rescale_load(const FastArgs& F, const RescaleIn& R, typename A::T (&e)[16], int limb,
-                                             long long drow, const typename A::C& c);
-template <>
-__device__ __forceinline__ void rescale_load<ArithF64>(const FastArgs& F, const RescaleIn& R, double (&e)[16], int limb,
-                                                       long long drow, const F64C& c) {
-    const int tau = threadIdx.x, b = F.logN - 8;
+// (B = logN - 8 is a template parameter of the column passes: the row stride 2^B becomes an immediate offset of every
+//  load / store -- with a run-time shift the address arithmetic was a third of the FP64 path's instructions)
+template <class A, int B>
+struct RescaleLoad;
+template <int B>
+struct RescaleLoad<ArithF64, B> {
+  static __device__ __forceinline__ void run(const FastArgs& F, const RescaleIn& R, double (&e)[16], int limb,
+                                             long long drow, const F64C& c) {
+    constexpr int b = B;
+    const int tau = threadIdx.x;
     const int g = (int)(drow / R.L);
     const long long base = (long long)grid_chunk(F) * 16 + ((long long)(tau >> 4) << b) + (tau & 15);
     const int64_t* __restrict__ src = R.in[g] + (long long)limb * R.in_stride + base;
@@ -549,11 +567,14 @@ __device__ __forceinline__ void rescale_load<ArithF64>(const FastArgs& F, const 
         const double v = f64_mulmod(i2d(x[k] - y[k]), s1, c);
         e[k] = (y[k] > R.round_at) ? __dadd_rn(v, rm) : v;
     }
-}
-template <>
-__device__ __forceinline__ void rescale_load<ArithU64>(const FastArgs& F, const RescaleIn& R, uint64_t (&e)[16], int limb,
-                                                       long long drow, const U64C& c) {
-    const int tau = threadIdx.x, b = F.logN - 8;
+  }
+};
+template <int B>
+struct RescaleLoad<ArithU64, B> {
+  static __device__ __forceinline__ void run(const FastArgs& F, const RescaleIn& R, uint64_t (&e)[16], int limb,
+                                             long long drow, const U64C& c) {
+    constexpr int b = B;
+    const int tau = threadIdx.x;
     const int g = (int)(drow / R.L);
     const long long base = (long long)grid_chunk(F) * 16 + ((long long)(tau >> 4) << b) + (tau & 15);
     const int64_t* __restrict__ src = R.in[g] + (long long)limb * R.in_stride + base;
@@ -568,14 +589,15 @@ __device__ __forceinline__ void rescale_load<ArithU64>(const FastArgs& F, const 
         o += (o < 0) ? q : 0;
         e[i] = ArithU64::mul((uint64_t)o, s, c);
     }
-}
+  }
+};
 
-template <class A, bool STAGED, bool RESC>
+template <class A, int B, bool STAGED, bool RESC>
 __device__ __forceinline__ void fast_fwd_col_body(const FastArgs& F, const RescaleIn& R, int64_t* sm, int limb, long long drow) {
     using T = typename A::T;
     using TW = typename A::TW;
     const int tau = threadIdx.x;
-    const int b = F.logN - 8;
+    constexpr int b = B;
     const typename A::C c = make_const<A>(F, limb);
     int64_t* __restrict__ row0 = F.a + drow * F.a_stride + (long long)grid_chunk(F) * 16;
     const TW* __restrict__ W = tw_row<A>(F, limb);
@@ -590,11 +612,16 @@ __device__ __forceinline__ void fast_fwd_col_body(const FastArgs& F, const Resca
     T e[16];
     {
         if constexpr (RESC) {
-            rescale_load<A>(F, R, e, limb, drow, c);
+            RescaleLoad<A, B>::run(F, R, e, limb, drow, c);
         } else {
             const int r0 = tau >> 4, col = tau & 15;
+            if (LAB_SKIP_MEM(F)) {
 #pragma unroll
-            for (int k = 0; k < 16; ++k) e[k] = A::load_in(row0[((long long)(r0 + 16 * k) << b) + col], F.in_raw);
+                for (int k = 0; k < 16; ++k) e[k] = A::load_in((int64_t)(tau * 16 + k), 0);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 16; ++k) e[k] = A::load_in(row0[((long long)(r0 + 16 * k) << b) + col], F.in_raw);
+            }
             if (F.scal) {
                 const TW s = scalar_tw<A>(F, limb);
 #pragma unroll
@@ -603,9 +630,9 @@ __device__ __forceinline__ void fast_fwd_col_body(const FastArgs& F, const Resca
         }
         if constexpr (STAGED) {
             mbar_wait(bar, 0);
-            fast_fwd_round<A, 0>(e, TwSharedCol<TW>{tws, 0, 0u}, c);
+            if (!LAB_SKIP_MATH(F)) fast_fwd_round<A, 0>(e, TwSharedCol<TW>{tws, 0, 0u}, c);
         } else {
-            fast_fwd_round<A, 0>(e, TwGlobal<TW>{W, 0, 0u}, c);
+            if (!LAB_SKIP_MATH(F)) fast_fwd_round<A, 0>(e, TwGlobal<TW>{W, 0, 0u}, c);
         }
         smx_store(sm, e, tau, 8);
     }
@@ -613,37 +640,46 @@ __device__ __forceinline__ void fast_fwd_col_body(const FastArgs& F, const Resca
     {
         smx_load(sm, e, tau, 4);
         const int hi = tau >> 4, col = tau & 15;
-        if constexpr (STAGED)
-            fast_fwd_round<A, 0>(e, TwSharedCol<TW>{tws, 4, (unsigned)hi}, c);
-        else
-            fast_fwd_round<A, 0>(e, TwGlobal<TW>{W, 4, (unsigned)hi}, c);
+        if (!LAB_SKIP_MATH(F)) {
+            if constexpr (STAGED)
+                fast_fwd_round<A, 0>(e, TwSharedCol<TW>{tws, 4, (unsigned)hi}, c);
+            else
+                fast_fwd_round<A, 0>(e, TwGlobal<TW>{W, 4, (unsigned)hi}, c);
+        }
+        if (LAB_SKIP_MEM(F)) {      // keep the values alive: one store that never happens
+            int64_t acc = 0;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) acc ^= A::store_mid(e[k], c);
+            if (acc == 0x7fff123456789abcll) row0[0] = acc;
+            return;
+        }
 #pragma unroll
         for (int k = 0; k < 16; ++k) row0[((long long)(hi * 16 + k) << b) + col] = A::store_mid(e[k], c);
     }
 }
 
-template <int DUMMY>
+template <int B>
 __global__ void __launch_bounds__(NTT_THREADS, FAST_COL_CTAS) fast_fwd_colpass(const FastArgs F) {
     extern __shared__ __align__(16) int64_t sm[];
     const RowId rid = fast_row(F);
     const int limb = rid.limb;
     const RescaleIn none{};
     if (fast_use_f64(F, rid))
-        fast_fwd_col_body<ArithF64, true, false>(F, none, sm, limb, rid.data_row);
+        fast_fwd_col_body<ArithF64, B, true, false>(F, none, sm, limb, rid.data_row);
     else
-        fast_fwd_col_body<ArithU64, false, false>(F, none, sm, limb, rid.data_row);
+        fast_fwd_col_body<ArithU64, B, false, false>(F, none, sm, limb, rid.data_row);
 }
 
 // the tensor stage's column pass: rescale fused into the load (rows = 4 polynomials x L limbs, period L, F.scal = R mod q)
-template <int DUMMY>
+template <int B>
 __global__ void __launch_bounds__(NTT_THREADS, FAST_COL_CTAS) fast_fwd_colpass_rescale(const FastArgs F, const RescaleIn R) {
     extern __shared__ __align__(16) int64_t sm[];
     const RowId rid = fast_row(F);
     const int limb = rid.limb;
     if (fast_use_f64(F, rid))
-        fast_fwd_col_body<ArithF64, true, true>(F, R, sm, limb, rid.data_row);
+        fast_fwd_col_body<ArithF64, B, true, true>(F, R, sm, limb, rid.data_row);
     else
-        fast_fwd_col_body<ArithU64, false, true>(F, R, sm, limb, rid.data_row);
+        fast_fwd_col_body<ArithU64, B, false, true>(F, R, sm, limb, rid.data_row);
 }
 
 // ---- ModUp basis extension for the fast path ---------------------------------------------------------------------
@@ -967,22 +1003,39 @@ __device__ __forceinline__ void fast_fwd_block_body(const FastArgs& F, int64_t* 
     }
     T e[16];
     constexpr int P1 = B - 4;
-    {
+    if (LAB_SKIP_MEM(F)) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) e[k] = A::load_in((int64_t)(tau * 16 + k), 0);
+    } else {
         const int zb = zbase(tau, P1);
 #pragma unroll
         for (int k = 0; k < 16; ++k) e[k] = A::load_mid(g[zb | (k << P1)]);
     }
+    if constexpr (B > 4) {
+        // The last round's twiddles (the warp tile's packed block, 4 or 8 KB = one 128-byte line per lane and half) are
+        // needed only after the first rounds, and there is no register to hold them until then: touch the lines now, so
+        // that the loads of the last round hit L1 instead of waiting ~600 clk for L2 at each of its four stages
+        // (14 % of the FP64 path's stall samples in profiles/r02_ncu_fwd_ntt_v2_steady.txt).
+        const TW* __restrict__ WP = twp_row<A>(F, limb);
+        if (WP) {
+            const char* line = reinterpret_cast<const char*>(WP + ((long long)(chunk * 8u + (unsigned)(tau >> 5))) * PACK_TILE) +
+                               (tau & 31) * 128;
+            l1_touch(line);
+            if constexpr (sizeof(TW) == 16) l1_touch(line + 4096);
+        }
+    }
     if constexpr (B == 4) {
         fast_fwd_last_round<A, 0>(e, F, limb, chunk, c);
     } else {
-        fast_fwd_round<A, 0>(e, TwGlobal<TW>{W, logN - 4 - P1, (chunk << (8 - P1)) | (unsigned)(tau >> P1)}, c);
+        if (!LAB_SKIP_MATH(F))
+            fast_fwd_round<A, 0>(e, TwGlobal<TW>{W, logN - 4 - P1, (chunk << (8 - P1)) | (unsigned)(tau >> P1)}, c);
         smx_store(sm, e, tau, P1);
         __syncwarp();
         if constexpr (B >= 8) {
             constexpr int P2 = B - 8;
             smx_load(sm, e, tau, P2);
             if constexpr (B == 8) {
-                fast_fwd_last_round<A, 0>(e, F, limb, chunk, c);
+                if (!LAB_SKIP_MATH(F)) fast_fwd_last_round<A, 0>(e, F, limb, chunk, c);
             } else {
                 fast_fwd_round<A, 0>(e, TwGlobal<TW>{W, logN - 4 - P2, (chunk << (8 - P2)) | (unsigned)(tau >> P2)}, c);
                 __syncwarp();
@@ -999,6 +1052,13 @@ __device__ __forceinline__ void fast_fwd_block_body(const FastArgs& F, int64_t* 
     int64_t r[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) r[k] = A::store_out(e[k], c, F.out_raw);
+    if (LAB_SKIP_MEM(F)) {
+        int64_t acc = 0;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) acc ^= r[k];
+        if (acc == 0x7fff123456789abcll) g[0] = acc;
+        return;
+    }
     tile_store16<T>(g, r, tau, F.perm);
 }
 
@@ -1082,12 +1142,12 @@ __global__ void __launch_bounds__(NTT_THREADS, FAST_BLK_CTAS) fast_inv_blockpass
 
 
 // ---- inverse pass A' (levels b..logN-1), x scalar, canonical out ---------------------------------------------
-template <class A, bool STAGED>
+template <class A, int B, bool STAGED>
 __device__ __forceinline__ void fast_inv_col_body(const FastArgs& F, int64_t* sm, int limb, long long drow) {
     using T = typename A::T;
     using TW = typename A::TW;
     const int tau = threadIdx.x;
-    const int b = F.logN - 8;
+    constexpr int b = B;
     const typename A::C c = make_const<A>(F, limb);
     int64_t* __restrict__ row0 = F.a + drow * F.a_stride + (long long)grid_chunk(F) * 16;
     const TW* __restrict__ W = tw_row<A>(F, limb);
@@ -1127,15 +1187,15 @@ __device__ __forceinline__ void fast_inv_col_body(const FastArgs& F, int64_t* sm
     }
 }
 
-template <int DUMMY>
+template <int B>
 __global__ void __launch_bounds__(NTT_THREADS, FAST_COL_CTAS) fast_inv_colpass(const FastArgs F) {
     extern __shared__ __align__(16) int64_t sm[];
     const RowId rid = fast_row(F);
     const int limb = rid.limb;
     if (fast_use_f64(F, rid))
-        fast_inv_col_body<ArithF64, true>(F, sm, limb, rid.data_row);
+        fast_inv_col_body<ArithF64, B, true>(F, sm, limb, rid.data_row);
     else
-        fast_inv_col_body<ArithU64, false>(F, sm, limb, rid.data_row);
+        fast_inv_col_body<ArithU64, B, false>(F, sm, limb, rid.data_row);
 }
 
 // ---- table construction ----------------------------------------------------------------------------------------

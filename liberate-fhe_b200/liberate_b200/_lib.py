@@ -41,8 +41,8 @@ SIGNATURES = {
     "ckks_fast_tables": [_i64p, _i64p, _vp, _vp, _int, _int, _vp],
     "ckks_fast_pack": [_vp, _vp, _vp, _vp, _int, _int, _vp],
     "ckks_perm_rows": [_i64p, _i64, _i64p, _i64, _int, _int, _int, _vp],
-    "ckks_ntt_fast": [_i64p, _i64, _int, _int, _int, _vp, _vp, _vp, _vp, _i64p, _vp, _i64p, _i64p, _int, _vp],
-    "ckks_intt_fast": [_i64p, _i64, _int, _int, _int, _vp, _vp, _vp, _vp, _i64p, _vp, _i64p, _i64p, _int, _int, _vp],
+    "ckks_ntt_fast": [_i64p, _i64, _int, _int, _int, _vp, _vp, _vp, _vp, _i64p, _vp, _i64p, _i64p, _int, _int, _vp],
+    "ckks_intt_fast": [_i64p, _i64, _int, _int, _int, _vp, _vp, _vp, _vp, _i64p, _vp, _i64p, _i64p, _int, _int, _int, _vp],
     "ckks_rescale": [_i64p, _i64, _i64p, _i64p, _i64, _int, _int, _i64p, _i64, _int, _i64p, _i64p, _i64p, _i64p, _i64p, _vp],
     "ckks_tensor_product": [_i64p, _i64p, _i64p, _i64p, _i64, _i64p, _i64p, _i64p, _i64, _int, _int,
                             _i64p, _i64p, _i64p, _i64p, _i64p, _vp],

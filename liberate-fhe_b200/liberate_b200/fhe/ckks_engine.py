@@ -1146,40 +1146,147 @@ class ckks_engine:
         return self.cc_mult(ct, ct, evk, relin=relin)
 
     # -----------------------------------------------------------------------------------------------
-    # host <-> device, save / load (:1790-2029): prime-ordered CPU tensors, pickled
+    # host <-> device, save / load (:1790-2029).  WIRE FORMAT = the reference's: every polynomial becomes ONE CPU tensor
+    # whose rows are in absolute prime order (destination_arrays[_with_special][level], shifted to start at 0), wrapped in
+    # a one-element list; nested data_structs (keys) are walked recursively.  A pickle written by either engine loads in
+    # the other, for any number of devices on either side.
     # -----------------------------------------------------------------------------------------------
-    def _map_tensors(self, text, fn):
-        def walk(d):
-            if isinstance(d, data_struct):
-                return d._replace(data=walk(d.data))
-            if isinstance(d, (list, tuple)):
-                return type(d)(walk(x) for x in d) if isinstance(d, list) else tuple(walk(x) for x in d)
-            return fn(d) if isinstance(d, torch.Tensor) else d
-        return walk(text)
+    def _dest(self, level, include_special):
+        dest = (self.ntt.p.destination_arrays_with_special if include_special else self.ntt.p.destination_arrays)[level]
+        lo = min(min(d) for d in dest if len(d))
+        return [[i - lo for i in d] for d in dest]
+
+    def download_to_cpu(self, gpu_data, level, include_special):
+        """per-device tensors of one polynomial -> [one prime-ordered CPU tensor] (:1794-1822)"""
+        dest = self._dest(level, include_special)
+        cpu_tensor = torch.empty((sum(len(d) for d in dest), self.ctx.N), dtype=self.ctx.torch_dtype, device="cpu")
+        for dev, rows in enumerate(dest):
+            if not len(rows):
+                continue
+            t = gpu_data[dev] if dev < len(gpu_data) else None
+            if isinstance(self.comm, LocalComm):
+                if t is None or t.device.type != "cuda":
+                    raise Exception("To download data to the CPU, it must already be in a GPU!!!")
+            else:       # one process per GPU: the owner broadcasts its rows, every rank assembles the whole tensor
+                got = self.comm.bcast(t if self._local(dev) else None, dev, range(self.ntt.num_devices),
+                                      shape=(len(rows), self.ctx.N))
+                t = got[self.local_ids[0]]
+            cpu_tensor[rows] = t.cpu()
+        return [cpu_tensor]
+
+    def upload_to_gpu(self, cpu_data, level, include_special):
+        """[one prime-ordered CPU tensor] -> per-device tensors (None for devices other ranks own) (:1824-1852)"""
+        cpu_tensor = cpu_data[0]
+        if cpu_tensor.device.type != "cpu":
+            raise Exception("To upload data to GPUs, it must already be in the CPU!!!")
+        out = []
+        for dev, rows in enumerate(self._dest(level, include_special)):
+            out.append(cpu_tensor[rows].to(device=self.ntt.devices[dev]) if self._local(dev) else None)
+        return out
+
+    def move_tensors(self, data, level, include_special, direction):
+        func = {"gpu2cpu": self.download_to_cpu, "cpu2gpu": self.upload_to_gpu}[direction]
+        if not isinstance(data[0], (list, tuple)):
+            return func(data, level, include_special)
+        return [func(part, level, include_special) for part in data]
+
+    def move_to(self, text, direction="gpu2cpu"):
+        if not isinstance(text.data[0], data_struct):
+            return text._replace(data=self.move_tensors(text.data, text.level, text.include_special, direction))
+        return text._replace(data=[self.move_to(d, direction) for d in text.data])
 
     def cpu(self, ct):
-        return self._map_tensors(ct, lambda t: t.cpu())
+        return self.move_to(ct, "gpu2cpu")
 
     def cuda(self, ct):
-        def per_poly(d):
-            if isinstance(d, data_struct):
-                return d._replace(data=per_poly(d.data))
-            if isinstance(d, (list, tuple)) and len(d) and isinstance(d[0], torch.Tensor):
-                return [t.to(self.ntt.devices[i]) for i, t in enumerate(d)]
-            if isinstance(d, (list, tuple)):
-                return type(d)(per_poly(x) for x in d)
-            return d
-        return per_poly(ct)
+        return self.move_to(ct, "cpu2gpu")
+
+    def tensor_device(self, data):
+        first = data[0] if not isinstance(data[0], (list, tuple)) else data[0][0]
+        live = [t for t in (data if not isinstance(data[0], (list, tuple)) else data[0]) if t is not None]
+        return (live[0] if live else first).device.type
+
+    def device(self, text):
+        if not isinstance(text.data[0], data_struct):
+            return self.tensor_device(text.data)
+        return self.device(text.data[0])
+
+    def auto_generate_filename(self, fmt_str="%Y%m%d%H%M%S%f"):
+        import datetime
+        return datetime.datetime.now().strftime(fmt_str) + ".pkl"
 
     def save(self, text, filename=None):
+        """pickle of the prime-ordered CPU form.  The file names the REFERENCE's container class
+        (liberate.fhe.data_struct.data_struct, a NamedTuple with the same fields), so the reference's own load()
+        (pickle.load + move_to, :2015-2029) reads it without this package installed; our load() maps that name back."""
         if filename is None:
-            import datetime
-            filename = datetime.datetime.now().strftime("%Y%m%d%H%M%S%f") + ".pkl"
-        with open(filename, "wb") as f:
-            pickle.dump(self.cpu(text), f)
+            filename = self.auto_generate_filename()
+        cpu_text = self.cpu(text) if self.device(text) != "cpu" else text
+        with open(filename, "wb") as f, _wire_class() as wire:
+            pickle.dump(_as(cpu_text, wire), f)
         return filename
 
     def load(self, filename, move_to_gpu=True):
         with open(filename, "rb") as f:
-            text = pickle.load(f)
+            text = _as(_WireUnpickler(f).load(), data_struct)
         return self.cuda(text) if move_to_gpu else text
+
+
+# ---------------------------------------------------------------------------------------------------
+# pickle interoperability with the reference (same NamedTuple, different module path)
+# ---------------------------------------------------------------------------------------------------
+_WIRE_MODULE = "liberate.fhe.data_struct"
+
+
+def _as(x, cls):
+    """rebuild a (nested) container as `cls` -- the fields are identical"""
+    if hasattr(x, "_fields") and hasattr(x, "origin"):
+        data = x.data
+        if len(data) and hasattr(data[0], "_fields"):
+            data = [_as(d, cls) for d in data]
+        return cls(data, *tuple(x)[1:])
+    return x
+
+
+class _WireUnpickler(pickle.Unpickler):
+    def find_class(self, module, name):
+        if name == "data_struct" and module in (_WIRE_MODULE, data_struct.__module__):
+            return data_struct
+        return super().find_class(module, name)
+
+
+class _wire_class:
+    """context manager giving the class object that pickles as liberate.fhe.data_struct.data_struct: the reference's own
+    class when that package is loaded in this process, otherwise a twin registered under that module path for the
+    duration of the dump only (pickle verifies the import path at dump time)"""
+
+    def __enter__(self):
+        import sys
+        import types as pytypes
+        from typing import NamedTuple
+        self.added = []
+        mod = sys.modules.get(_WIRE_MODULE)
+        if mod is not None and getattr(mod.data_struct, "__module__", None) == _WIRE_MODULE:
+            return mod.data_struct
+        twin = NamedTuple("data_struct", [(f, object) for f in data_struct._fields])
+        twin.__module__ = _WIRE_MODULE
+        parts = _WIRE_MODULE.split(".")
+        self.saved = {}
+        for i in range(1, len(parts) + 1):
+            name = ".".join(parts[:i])
+            self.saved[name] = sys.modules.get(name)
+            if i == len(parts) or name not in sys.modules:
+                m = pytypes.ModuleType(name)
+                sys.modules[name] = m
+                self.added.append(name)
+        sys.modules[_WIRE_MODULE].data_struct = twin
+        return twin
+
+    def __exit__(self, *exc):
+        import sys
+        for name in self.added:
+            if self.saved.get(name) is None:
+                sys.modules.pop(name, None)
+            else:
+                sys.modules[name] = self.saved[name]
+        return False

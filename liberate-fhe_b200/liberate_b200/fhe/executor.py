@@ -117,13 +117,17 @@ class LevelPlan:
         SMALL = 1 << 42
         f64 = lambda v: hold(torch.tensor(v, dtype=torch.float64, device=device))
         wide, hm_ptrs = [], []
+        mixed = False
         for s_ in self.sids:
             src, part_id, alpha = owners[s_]
             primes = ntt.parts_pack[src][tuple(ntt.p.p[level][src][part_id])]["prime_ids"]
             m = [eng.ctx.q[i] for i in primes]
             is_wide = any(x >= SMALL for x in m)
             if is_wide and alpha != 1 and any(qt < SMALL for qt in qrows):
-                raise NotImplementedError("multi-limb partitions of primes >= 2^42 next to FP64 target limbs")
+                # scale_bits = 42: the table's primes alternate around 2^42, so a multi-limb partition can hold digits
+                # beyond 2^51 while some target limbs are FP64 limbs.  The FP64 extension splits only ONE wide digit
+                # (the base-prime partition): such contexts take the integer key-switch pipeline (natural-order keys).
+                mixed = True
             wide.append(1 if is_wide else 0)
             if alpha > 1:
                 hm = f64([[float(m[i] % qt) for qt in qrows] for i in range(alpha - 1)])
@@ -142,7 +146,9 @@ class LevelPlan:
             n_small += 1
         d.L_small = n_small
         d.amax = max(2, max(owners[s_][2] for s_ in self.sids))
-        self.fp64 = True      # Hm / Pinv tables present: the FP64 slab pipeline (the integer fall-back needs natural-order keys)
+        self.fp64 = not mixed    # Hm / Pinv tables present: the FP64 slab pipeline (the integer fall-back needs natural-order keys)
+        if mixed:
+            d.Hm, d.Pinv = None, None
         self.desc = d
         self.ref = ctypes.byref(d)
         self._keep = keep

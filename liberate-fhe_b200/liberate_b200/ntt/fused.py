@@ -153,7 +153,7 @@ def _tables(tables, tw_f64):
     return _ptr(tables), _ptr(tw_f64), None, None
 
 
-def ntt_fast(x, tables, tw_f64, q, scal=None, scal_sh=None, period=None, force_int=False, qinv=None):
+def ntt_fast(x, tables, tw_f64, q, scal=None, scal_sh=None, period=None, force_int=False, qinv=None, perm=False):
     """canonical-output forward NTT in place: x [rows,N] in [0,2q) -> NTT(x * scal) in [0,q).
     tables: FastTables (tw_f64 ignored) or the plain {w, w'} table with tw_f64 the double table"""
     s = _rows(x, "ntt_fast")
@@ -163,11 +163,11 @@ def ntt_fast(x, tables, tw_f64, q, scal=None, scal_sh=None, period=None, force_i
         check(lib.ckks_ntt_fast(_ptr(x), s, rows, period or rows, logN, *_tables(tables, tw_f64), _ptr(_vec(q)),
                                 _ptr(qinv) if qinv is not None else None,
                                 _ptr(scal) if scal is not None else None,
-                                _ptr(scal_sh) if scal_sh is not None else None, 1 if force_int else 0, _stream(x)),
-              "ntt_fast")
+                                _ptr(scal_sh) if scal_sh is not None else None, 1 if force_int else 0, 1 if perm else 0,
+                                _stream(x)), "ntt_fast")
 
 
-def intt_fast(x, tables, tw_f64, q, scal, scal_sh, centred=False, period=None, force_int=False, qinv=None):
+def intt_fast(x, tables, tw_f64, q, scal, scal_sh, centred=False, period=None, force_int=False, qinv=None, perm=False):
     """canonical-output inverse NTT in place: x [rows,N] in [0,2q) -> iNTT(x) * scal in [0,q) (or centred)"""
     s = _rows(x, "intt_fast")
     rows, N = x.shape
@@ -175,8 +175,8 @@ def intt_fast(x, tables, tw_f64, q, scal, scal_sh, centred=False, period=None, f
     with _Launch(x):
         check(lib.ckks_intt_fast(_ptr(x), s, rows, period or rows, logN, *_tables(tables, tw_f64), _ptr(_vec(q)),
                                  _ptr(qinv) if qinv is not None else None,
-                                 _ptr(scal), _ptr(scal_sh), 1 if centred else 0, 1 if force_int else 0, _stream(x)),
-              "intt_fast")
+                                 _ptr(scal), _ptr(scal_sh), 1 if centred else 0, 1 if force_int else 0, 1 if perm else 0,
+                                 _stream(x)), "intt_fast")
 
 
 def perm_rows(x, inverse=False):

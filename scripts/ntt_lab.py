@@ -19,12 +19,14 @@ ap.add_argument("--logN", type=int, default=16)
 ap.add_argument("--rows", type=int, default=380)
 ap.add_argument("--period", type=int, default=38)
 ap.add_argument("--big", type=int, default=5, help="60-bit limbs per period (integer path)")
-ap.add_argument("--opts", default="3=1")
+ap.add_argument("--opts", default="")
+ap.add_argument("--perm", type=int, default=1, help="NTT-domain side in warp-interleaved order (as the executor runs it)")
 ap.add_argument("--iters", type=int, default=20)
 ap.add_argument("--nbuf", type=int, default=3, help="buffers rotated between calls (1 + small rows = L2-resident)")
 args = ap.parse_args()
 
 logN, rows, E = args.logN, args.rows, args.period
+PERM = args.perm
 N = 1 << logN
 ctx = json.loads((ROOT / "tests/golden/context.json").read_text())["contexts"]
 qall = [c for c in ctx if c["args"]["logN"] == 17][0]["q"]
@@ -52,18 +54,18 @@ bufs = [src.clone() for _ in range(nbuf)]
 
 
 def fwd(b):
-    check(lib.ckks_ntt_fast(P(b), N, rows, E, logN, P(twu), P(twd), P(twpu), P(twpd), P(qd), P(qinv), None, None, 0, st), "ntt_fast")
+    check(lib.ckks_ntt_fast(P(b), N, rows, E, logN, P(twu), P(twd), P(twpu), P(twpd), P(qd), P(qinv), None, None, 0, PERM, st), "ntt_fast")
 
 
 def inv(b):
-    check(lib.ckks_intt_fast(P(b), N, rows, E, logN, P(twu), P(twd), P(twpu), P(twpd), P(qd), P(qinv), P(sc), P(sc_sh), 0, 0, st), "intt_fast")
+    check(lib.ckks_intt_fast(P(b), N, rows, E, logN, P(twu), P(twd), P(twpu), P(twpd), P(qd), P(qinv), P(sc), P(sc_sh), 0, 0, PERM, st), "intt_fast")
 
 
 def set_opts(o):
     for k, v in option_defaults().items():
         lib.ckks_set_option(k, v)
     lib.ckks_set_option(5, 0)
-    lib.ckks_set_option(20, 0)
+    lib.ckks_set_option(21, 0)
     for k, v in o:
         lib.ckks_set_option(k, v)
 
@@ -93,8 +95,6 @@ for o in optsets:
         if not o:
             ref[name] = x
             same = True
-        elif (20, 1) in o:      # warp-interleaved NTT domain: compare after undoing the permutation / on a permuted input
-            same = None
         else:
             same = bool(torch.equal(x, ref[name]))
         set_opts(o)

@@ -70,3 +70,46 @@ def hot_path_flow(eng, rec, deep=True):
             rec(f"rot_l{x.level}", eng.rotate_single(x, rotk1))
         rec("pt_dec_deep", eng.decrypt(x, sk))
     return dict(sk=sk, pk=pk, evk=evk, rotk1=rotk1, ct_a=ct_a, ct_b=ct_b, ct_ab=ct_ab, ma=ma, mb=mb)
+
+
+class fixed_encode:
+    """engine.encode is FFT-dependent (and random-rounds): inside mc_mult / mc_add the engine calls it itself, so for the
+    duration of such a call route it through rec.fix -- recorded in generation, replaced by the golden value in tests"""
+
+    def __init__(self, eng, rec, name):
+        self.eng, self.rec, self.name = eng, rec, name
+
+    def __enter__(self):
+        orig = self.eng.encode
+        self.orig = orig
+        rec, name = self.rec, self.name
+
+        def enc(m, level=0, padding=True):
+            return rec.fix(name, orig(m, level, padding))
+        self.eng.encode = enc
+        return self
+
+    def __exit__(self, *exc):
+        del self.eng.encode          # back to the class method
+        return False
+
+
+def extra_flow(eng, rec, objs):
+    """Galois keys and composite rotations, plaintext (message) operands: create_galois_key (engine.py:1216-1232),
+    rotate_galois (:1234-1266), mc_mult / mc_add / mc_sub and their cm_ twins through the dispatchers (:2052-2219)."""
+    sk, ct_a, ct_ab, mb = objs["sk"], objs["ct_a"], objs["ct_ab"], objs["mb"]
+    gk = eng.create_galois_key(sk)
+    rec("galk", gk)
+    rec("rotg_a_5", eng.rotate_galois(ct_a, gk, 5))
+    rec("rotg_ab_m3", eng.rotate_galois(ct_ab, gk, -3))
+    with fixed_encode(eng, rec, "pt_mc_mult"):
+        rec("mc_mult", eng.mult(mb, ct_a))
+    with fixed_encode(eng, rec, "pt_cm_mult"):
+        rec("cm_mult_l1", eng.mult(ct_ab, mb))
+    with fixed_encode(eng, rec, "pt_mc_add"):
+        rec("mc_add", eng.add(mb, ct_a))
+    with fixed_encode(eng, rec, "pt_cm_sub"):
+        rec("cm_sub", eng.sub(ct_a, mb))
+    with fixed_encode(eng, rec, "pt_mc_sub"):
+        rec("mc_sub", eng.sub(mb, ct_ab))
+    return dict(galk=gk)

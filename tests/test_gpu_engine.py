@@ -39,12 +39,38 @@ def test_engine_reproduces_reference_tensors(D, mode):
     assert [int(x) for x in eng.ctx.q] == g["q"]
     chk = Checker(g["digests"], full, eng.ntt.devices)
     objs = flows.hot_path_flow(eng, chk)
+    flows.extra_flow(eng, chk, objs)       # Galois key + rotate_galois, mc_/cm_ mult / add / sub
     assert set(chk.seen) == set(g["digests"]), set(g["digests"]) ^ set(chk.seen)
     assert not chk.failures, chk.failures[:8]
     # float side: decode of the (bit-identical) ciphertexts agrees with the reference's decode
     dec = eng.decrode(objs["ct_ab"], objs["sk"])
     assert np.abs(dec - full["decode_ab"]).max() < 1e-9
     assert np.abs(dec - full["ma"] * full["mb"]).max() < 1e-6
+
+
+@pytest.mark.parametrize("mode", ["executor", "faithful"])
+@pytest.mark.parametrize("D", [1, 2])
+@pytest.mark.parametrize("tag", ["_sb30", "_sb42", "_sb45"])
+def test_engine_reproduces_reference_tensors_at_other_scale_bits(tag, D, mode):
+    """the reference's own engine tests sweep scale_bits 20..45 (src/liberate/fhe/tests/test_generate_engine.py:40-46).
+    scale_bits = 30: FP64 butterflies with 2^30 primes; scale_bits = 45: every prime is >= 2^42, so the whole fused path
+    (transforms, ModUp extension of multi-limb partitions of wide primes, inner product, ModDown) runs on the 64-bit
+    integer kernels -- the other side of the q < 2^42 boundary of the FP64 path; scale_bits = 42: the cached primes
+    alternate around 2^42, FP64 limbs and wide limbs share partitions and the key switch takes the integer pipeline."""
+    g = json.loads((GOLDEN / f"engine_D{D}{tag}.json").read_text())
+    full = np.load(GOLDEN / f"engine_D{D}{tag}_full.npz")
+    eng = make_engine(D, g["params"], mode)
+    assert [int(x) for x in eng.ctx.q] == g["q"]
+    sb = g["params"]["scale_bits"]
+    n_wide = sum(q >= (1 << 42) for q in eng.ctx.q[:eng.ctx.num_scales])
+    assert n_wide == (0 if sb < 42 else eng.ctx.num_scales if sb > 42 else n_wide) and (sb != 42 or 0 < n_wide < eng.ctx.num_scales)
+    chk = Checker(g["digests"], full, eng.ntt.devices)
+    objs = flows.hot_path_flow(eng, chk)
+    flows.extra_flow(eng, chk, objs)
+    assert set(chk.seen) == set(g["digests"]), set(g["digests"]) ^ set(chk.seen)
+    assert not chk.failures, chk.failures[:8]
+    dec = eng.decrode(objs["ct_ab"], objs["sk"])
+    assert np.abs(dec - full["decode_ab"]).max() < 1e-9
 
 
 @pytest.mark.parametrize("D", [1, 2, 3])

@@ -292,6 +292,15 @@ def _check_fast_transforms(logN, force_int, packed=True):
         r = lazy.copy()
         O.C.intt(r, P.ipsi, P.Ninv, P._2q, *P.mont, exit_mode=mode)
         assert eq(y, r), f"intt_fast centred={centred}"
+    # warp-interleaved NTT-domain order (what the executor uses between its kernels) == the permutation of the natural result
+    x = T(a)
+    fused.ntt_fast(x, sh_f, dbl_f, qd, force_int=force_int, qinv=qinv, perm=True)
+    assert eq(fused.perm_rows(x, inverse=True), ref2), "ntt_fast(perm)"
+    y = fused.perm_rows(T(lazy))
+    fused.intt_fast(y, sh_i, dbl_i, qd, T(ex), T(shoup(ex)), force_int=force_int, qinv=qinv, perm=True)
+    r = lazy.copy()
+    O.C.intt(r, P.ipsi, P.Ninv, P._2q, *P.mont, exit_mode=2)
+    assert eq(y, r), "intt_fast(perm)"
     # batched rows: 2 x C rows share the C limbs' constants (period = C)
     reps = 5
     big = T(np.concatenate([a] * reps))

@@ -52,3 +52,37 @@ def test_ckks_context_matches_reference():
         kw = {k: v for k, v in params[name].items() if k != "devices"}
         c = ckks_context(**kw)
         assert (c.num_scales + 1, c.num_special_primes) == (L, K), name
+
+
+def test_base_prime_is_a_partition_of_its_own_and_scale_tables_straddle_2_42_only_at_42_bits():
+    """fhe/executor.LevelPlan chooses the FP64 key-switch pipeline unless a MULTI-limb partition holds a prime >= 2^42 while
+    FP64 target limbs exist.  (1) the base prime (60 bits) is always a partition of its own (part.py:29-34; golden sweep + a
+    denser sweep), so with scale primes below 2^42 the only wide partition has one limb; (2) a scale_bits table lies
+    entirely below 2^42 (bits <= 41) or entirely above (bits >= 43) -- only the 42-bit tables straddle the limit, which is
+    the one case that takes the integer pipeline (tests/test_gpu_engine.py: _sb42)."""
+    import json
+    from conftest import GOLDEN
+    from liberate_b200.ntt.rns_partition import rns_partition
+    cases = [tuple(it["args"]) for it in json.loads((GOLDEN / "partition.json").read_text()) if "error" not in it]
+    cases += [(L, K, D) for L in range(4, 40, 3) for K in (1, 2, 3, 4, 6) for D in (1, 2, 4, 8) if L > K * D]
+    for L, K, D in cases:
+        try:
+            p = rns_partition(L, K, D)
+        except IndexError:
+            continue
+        own = [part for part in p.partitions if p.base_prime_idx in part]
+        assert own == [[p.base_prime_idx]], (L, K, D, own)
+    from liberate_b200.fhe.context.ckks_context import tables
+    t = tables()
+    for key, primes in t["scale_primes"].items():
+        if not primes:
+            continue
+        bits = int(key.split(",")[0])
+        n_wide = sum(q >= (1 << 42) for q in primes)
+        if bits <= 41:
+            assert n_wide == 0, key
+        elif bits >= 43:
+            assert n_wide == len(primes), key
+        else:
+            assert 0 < n_wide < len(primes), key
+    assert all(q >= (1 << 42) for per_n in t["message_special_primes"]["60"].values() for q in per_n)
