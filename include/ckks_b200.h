@@ -212,19 +212,24 @@ int ckks_exec_tensor_stage(const ckks_level_t* lv, const int64_t* a0, const int6
                            const int64_t* r0b0, const int64_t* r0b1, int64_t* x, int64_t* d, int64_t* digits,
                            void* stream);
 /* Garner digits of the local partitions of a [L][N] polynomial (pre_extend for every partition, one launch).
+ * galois = 0, or an odd g < 2N: the digits of the Galois image of a (encdec.py:224-246 + engine.py:1196-1200: out[(g j) mod N]
+ * = +-a[j], canonical) are computed by gathering from the UNROTATED canonical rows (a != digits then).
  * CKKS_E_BADARG when a partition has more than 8 limbs (lv->amax). */
 int ckks_exec_digits(const ckks_level_t* lv, const int64_t* a, int64_t a_stride, int64_t* digits, int64_t d_stride,
-                     void* stream);
+                     int64_t galois, void* stream);
 /* extend (all partitions) -> batched NTT -> evk inner product -> batched iNTT+exit -> ModDown (+add, reduce)
  * (create_switcher engine.py:812-904 + the relinearize / switch_key tails).  digit_ptrs: device [nparts] pointers to
  * each partition's [alpha][N] digit block (rows digit_stride apart) -- local or received from a peer;
  * k0_ptrs / k1_ptrs: device [nparts] row-0 pointers of the key halves; keys_permuted != 0: they point to copies made
  * with ckks_perm_rows (the stage then keeps its NTT-domain data in the same order);
+ * add0_galois = 0, or an odd g < 2N: the polynomial added to output 0 is the Galois image of add0 (rotate_single: the
+ * rotated c0, engine.py:1194-1200, 947), gathered from the unrotated canonical rows inside the ModDown kernel;
  * ws: ckks_exec_keyswitch_ws_elems(...) int64 elements. */
 int ckks_exec_keyswitch_stage(const ckks_level_t* lv, const int64_t* const* digit_ptrs, int64_t digit_stride,
                               const int64_t* const* k0_ptrs, const int64_t* const* k1_ptrs, int64_t ksk_stride,
                               int keys_permuted, const int64_t* add0, const int64_t* add1, int64_t add_stride,
-                              int64_t* out0, int64_t* out1, int64_t out_stride, int64_t* ws, void* stream);
+                              int64_t add0_galois, int64_t* out0, int64_t* out1, int64_t out_stride, int64_t* ws,
+                              void* stream);
 int64_t ckks_exec_keyswitch_ws_elems(int L, int K, int nparts, int N);
 
 /* ---- sampler: ChaCha20 counter mode (replaces src/liberate/csprng/: chacha20 / randint / discrete_gaussian / randround

@@ -315,11 +315,21 @@ __global__ void k_moddown_special(const int64_t* __restrict__ d, long long ds, i
     }
 }
 
+// coefficient `o` of the Galois image of a canonical row: out[(g j) mod N] = +-in[j]  <=>  out[o] = +-in[(ginv o) mod N], with the
+// minus sign when (ginv o) mod 2N >= N; then make_unsigned + reduce_2q (engine.py:1196-1200), i.e. q - v for a flipped v != 0.
+// Lets the kernels that READ a rotated polynomial (Garner digits, the ModDown tail's addend) take it straight from the
+// unrotated ciphertext: rotate never writes the rotated ciphertext to HBM.
+__device__ __forceinline__ int64_t galois_gather(const int64_t* __restrict__ row, unsigned o, unsigned ginv, unsigned N, int64_t q) {
+    const unsigned t = (ginv * o) & (2u * N - 1);
+    const int64_t v = row[t & (N - 1)];
+    return (t >= N && v != 0) ? q - v : v;
+}
+
 // ModDown, part 2: ordinary rows.  grid (N/2/EW_THREADS, L)
 __global__ void k_moddown_ordinary(const int64_t* __restrict__ d, long long ds, int L, int K, int N,
                                    const int64_t* __restrict__ Rs, const int64_t* __restrict__ PiR,
                                    const int64_t* __restrict__ eff, const int64_t* __restrict__ add, long long adds,
-                                   int64_t* __restrict__ out, long long os, int row0, MontPack m) {
+                                   int64_t* __restrict__ out, long long os, int row0, MontPack m, unsigned add_ginv) {
     const int t = row0 + blockIdx.y;
     const int j = 2 * (blockIdx.x * EW_THREADS + threadIdx.x);
     if (j >= N) return;
@@ -339,7 +349,13 @@ __global__ void k_moddown_ordinary(const int64_t* __restrict__ d, long long ds, 
     v.x = reduce_q(mont_redc(v.x, k.q4, k.k), q);
     v.y = reduce_q(mont_redc(v.y, k.q4, k.k), q);
     if (add) {
-        const longlong2 a = ld2(add + t * adds + j);
+        longlong2 a;
+        if (add_ginv) {
+            a.x = galois_gather(add + t * adds, (unsigned)j, add_ginv, (unsigned)N, q);
+            a.y = galois_gather(add + t * adds, (unsigned)j + 1, add_ginv, (unsigned)N, q);
+        } else {
+            a = ld2(add + t * adds + j);
+        }
         v.x = reduce_q(lazy_add(a.x, v.x, q2), q);
         v.y = reduce_q(lazy_add(a.y, v.y, q2), q);
     }
@@ -365,7 +381,8 @@ __global__ void k_automorphism(const int64_t* __restrict__ in, long long is, int
 // all local partitions in one launch: grid (N/EW_THREADS, nlocal); partition p covers rows [row0[p], row0[p]+alpha[p])
 __global__ void k_garner_batched(const int64_t* __restrict__ a, long long as, int64_t* __restrict__ st, long long ss, int N,
                                  const int32_t* __restrict__ row0, const int32_t* __restrict__ alphas,
-                                 const int64_t* const* __restrict__ Yp, const int64_t* const* __restrict__ Lp, MontPack m) {
+                                 const int64_t* const* __restrict__ Yp, const int64_t* const* __restrict__ Lp, MontPack m,
+                                 unsigned ginv, const int64_t* __restrict__ q_rows) {
     const int p = blockIdx.y;
     const int j = blockIdx.x * EW_THREADS + threadIdx.x;
     if (j >= N) return;
@@ -375,7 +392,9 @@ __global__ void k_garner_batched(const int64_t* __restrict__ a, long long as, in
     int64_t s[MAX_ALPHA], av[MAX_ALPHA];
 #pragma unroll
     for (int r = 0; r < MAX_ALPHA; ++r)
-        if (r < alpha) av[r] = a[(long long)(r0 + r) * as + j];
+        if (r < alpha)
+            av[r] = ginv ? galois_gather(a + (long long)(r0 + r) * as, (unsigned)j, ginv, (unsigned)N, q_rows[r0 + r])
+                         : a[(long long)(r0 + r) * as + j];
 #pragma unroll
     for (int r = 0; r < MAX_ALPHA; ++r) s[r] = av[0];
 #pragma unroll
@@ -458,6 +477,19 @@ constexpr int g_skip = 0;
 #endif
 inline bool aligned32(const void* p, long long stride) { return (((uintptr_t)p) & 31) == 0 && (stride & 3) == 0; }
 
+// g^-1 mod 2N for odd g (Newton iteration on 32-bit words; 2N <= 2^18)
+unsigned galois_inverse(unsigned g, unsigned N) {
+    unsigned x = g;                          // correct to 3 bits for odd g
+    for (int i = 0; i < 5; ++i) x *= 2u - g * x;
+    return x & (2u * N - 1);
+}
+int sm_count() {
+    static int n[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (!n[dev]) cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev);
+    return n[dev] > 0 ? n[dev] : 148;
+}
 template <int B>
 static int launch_fast_col_b(bool fwd, const FastArgs& F, dim3 grid, cudaStream_t st) {
     if (fwd) {
@@ -965,19 +997,21 @@ int ckks_moddown(int64_t* d, int64_t ds, int L, int K, int N, const int64_t* Rs,
     k_moddown_special<<<col_grid(N), EW_THREADS, 0, S(stream)>>>(d, ds, L, K, N, PiR, eff, m);
     int rc = launch_status();
     if (rc) return rc;
-    k_moddown_ordinary<<<ew_grid(N, L), EW_THREADS, 0, S(stream)>>>(d, ds, L, K, N, Rs, PiR, eff, add, adds, out, os, 0, m);
+    k_moddown_ordinary<<<ew_grid(N, L), EW_THREADS, 0, S(stream)>>>(d, ds, L, K, N, Rs, PiR, eff, add, adds, out, os, 0, m, 0u);
     return launch_status();
 }
 
 // ---- level 3: the fused executor (one C call = a whole stage of the hot path) ------------------------------
-int ckks_exec_digits(const ckks_level_t* lv, const int64_t* a, int64_t as, int64_t* digits, int64_t ds, void* stream) {
+int ckks_exec_digits(const ckks_level_t* lv, const int64_t* a, int64_t as, int64_t* digits, int64_t ds, int64_t galois,
+                     void* stream) {
     CHECK_PTRS(lv, a, digits);
     if (lv->nlocal <= 0) return 0;
     if (lv->amax > MAX_ALPHA) return CKKS_E_BADARG;   // k_garner_batched keeps at most MAX_ALPHA digits per partition
     const int N = 1 << lv->logN;
+    if (galois && (!(galois & 1) || galois < 0 || galois >= 2ll * N || a == digits)) return CKKS_E_BADARG;
     k_garner_batched<<<dim3((N + EW_THREADS - 1) / EW_THREADS, lv->nlocal), EW_THREADS, 0, S(stream)>>>(
         a, as, digits, ds, N, lv->loc_row0, lv->loc_alpha, lv->loc_Y, lv->loc_Ltri,
-        MontPack{nullptr, lv->ql, lv->qh, lv->kl, lv->kh});
+        MontPack{nullptr, lv->ql, lv->qh, lv->kl, lv->kh}, galois ? galois_inverse((unsigned)galois, (unsigned)N) : 0u, lv->q);
     return launch_status();
 }
 
@@ -1032,14 +1066,18 @@ int ckks_exec_tensor_stage(const ckks_level_t* lv, const int64_t* a0, const int6
     FastArgs Fi = level_fast(lv, d, N, false, lv->sExit, lv->sExit_sh, L);
     Fi.perm = perm;
     RC(fast_transform(false, Fi, 3 * L, st));
-    return ckks_exec_digits(lv, d + 2 * LN, N, digits, N, stream);
+    return ckks_exec_digits(lv, d + 2 * LN, N, digits, N, 0, stream);
 }
 
 int ckks_exec_keyswitch_stage(const ckks_level_t* lv, const int64_t* const* digit_ptrs, int64_t digit_stride,
                               const int64_t* const* k0_ptrs, const int64_t* const* k1_ptrs, int64_t ksk_stride,
                               int keys_permuted, const int64_t* add0, const int64_t* add1, int64_t add_stride,
-                              int64_t* out0, int64_t* out1, int64_t out_stride, int64_t* ws, void* stream) {
+                              int64_t add0_galois, int64_t* out0, int64_t* out1, int64_t out_stride, int64_t* ws,
+                              void* stream) {
     CHECK_PTRS(lv, digit_ptrs, k0_ptrs, k1_ptrs, out0, out1, ws);
+    if (add0_galois && (!(add0_galois & 1) || add0_galois < 0 || add0_galois >= (2ll << lv->logN) || !add0 || add0 == out0))
+        return CKKS_E_BADARG;
+    const unsigned add_ginv[2] = {add0_galois ? galois_inverse((unsigned)add0_galois, 1u << lv->logN) : 0u, 0u};
     if (lv->amax > MAX_ALPHA) return CKKS_E_BADARG;   // the extension kernels keep at most MAX_ALPHA digits per partition
     const int L = lv->L, K = lv->K, E = L + K, P = lv->nparts, N = 1 << lv->logN;
     int64_t* ext = ws;                                  // [P*E][N]
@@ -1136,13 +1174,14 @@ int ckks_exec_keyswitch_stage(const ckks_level_t* lv, const int64_t* const* digi
         k_moddown_special<<<col_grid(N), EW_THREADS, 0, st>>>(dh, N, L, K, N, lv->PiR, effh, m);
         RC(launch_status());
         if (Ls > 0) {
-            ModDownArgs M{dh, effh, adds[h], add_stride, outs[h], out_stride, lv->Pinv, lv->C31, lv->q, L, K, E, N, lv->qinv};
+            ModDownArgs M{dh, effh, adds[h], add_stride, outs[h], out_stride, lv->Pinv, lv->C31, lv->q, L, K, E, N, lv->qinv,
+                          add_ginv[h]};
             k_moddown_fast<<<dim3((N / 2 + 255) / 256, Ls), 256, 0, st>>>(M);
             RC(launch_status());
         }
         if (Ls < L) {
             k_moddown_ordinary<<<ew_grid(N, L - Ls), EW_THREADS, 0, st>>>(dh, N, L, K, N, lv->Rs, lv->PiR, effh, adds[h],
-                                                                        add_stride, outs[h], out_stride, Ls, m);
+                                                                        add_stride, outs[h], out_stride, Ls, m, add_ginv[h]);
             RC(launch_status());
         }
     }

@@ -439,12 +439,12 @@ __device__ __forceinline__ long long fast_row_ahead(const FastArgs& F, int ahead
     return (long long)g * F.group_rows + F.slab_t0 + m;
 }
 
-__device__ __forceinline__ RowId fast_row(const FastArgs& F) {
-    const int r = grid_row(F);
+__device__ __forceinline__ RowId fast_row_of(const FastArgs& F, int r) {
     if (F.slab_rows == 0) return RowId{r, (F.row0 + r) % F.period};
     const int g = r / F.slab_rows, m = r - g * F.slab_rows;
     return RowId{(long long)g * F.group_rows + F.slab_t0 + m, F.slab_t0 + m};
 }
+__device__ __forceinline__ RowId fast_row(const FastArgs& F) { return fast_row_of(F, grid_row(F)); }
 __device__ __forceinline__ bool fast_use_f64(const FastArgs& F, const RowId& rid) {
     return (uint64_t)F.q[rid.limb] < SMALL_PRIME_LIMIT && F.force_int == 0;
 }
@@ -891,6 +891,7 @@ struct ModDownArgs {
     const int64_t* q;
     int L, K, E, N;
     const double* qinv;                 // [E] 1/q_t, or nullptr
+    unsigned add_ginv;                  // != 0: the addend is the Galois image of `add` (g^-1 mod 2N), gathered on the fly
 };
 
 __global__ void __launch_bounds__(256) k_moddown_fast(const ModDownArgs X) {
@@ -914,8 +915,17 @@ __global__ void __launch_bounds__(256) k_moddown_fast(const ModDownArgs X) {
     r.x = ArithF64::store_canon(vx, c, false);
     r.y = ArithF64::store_canon(vy, c, false);
     if (X.add) {   // the reference's integer tail mont_add + reduce_2q, exact for ANY addend (conjugate feeds signed values)
-        const longlong2 a = *reinterpret_cast<const longlong2*>(X.add + (long long)t * X.add_stride + j);
         const int64_t qi = (int64_t)q;
+        longlong2 a;
+        if (X.add_ginv) {   // rotate: the addend is the rotated c0, read from the unrotated ciphertext (canonical rows)
+            const int64_t* __restrict__ row = X.add + (long long)t * X.add_stride;
+            const unsigned t0 = (X.add_ginv * (unsigned)j) & (2u * X.N - 1), t1 = (X.add_ginv * ((unsigned)j + 1)) & (2u * X.N - 1);
+            const int64_t v0 = row[t0 & (X.N - 1)], v1 = row[t1 & (X.N - 1)];
+            a.x = (t0 >= (unsigned)X.N && v0 != 0) ? qi - v0 : v0;
+            a.y = (t1 >= (unsigned)X.N && v1 != 0) ? qi - v1 : v1;
+        } else {
+            a = *reinterpret_cast<const longlong2*>(X.add + (long long)t * X.add_stride + j);
+        }
         r.x = reduce_q(lazy_add(a.x, r.x, 2 * qi), qi);
         r.y = reduce_q(lazy_add(a.y, r.y, 2 * qi), qi);
     }

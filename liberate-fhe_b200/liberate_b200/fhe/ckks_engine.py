@@ -709,12 +709,15 @@ class ckks_engine:
             out1[dst] = fused.moddown(acc1, E - K, K, Rs, PiR, pack, add=add1, eff=eff)
         return out0, out1
 
-    def _keyswitch_fused(self, a, ksk, level, add=None):
-        """create_switcher through the C executor: digits (1 launch) -> exchange -> one keyswitch stage call"""
+    def _keyswitch_fused(self, a, ksk, level, add=None, galois=0):
+        """create_switcher through the C executor: digits (1 launch) -> exchange -> one keyswitch stage call.
+        galois != 0 (rotate_single): `a` and add[0] are the UNROTATED c1 and c0; the Galois map (encdec.py:224-246 +
+        make_unsigned + reduce_2q, engine.py:1196-1200) is applied by the kernels that read them -- the Garner digit kernel
+        and the ModDown tail -- so the rotated ciphertext is never written to HBM."""
         n_dev = self.len_devices[level]
         plans = {d: self._plan(level, d) for d in range(n_dev) if self._local(d)}
         for d, plan in plans.items():
-            executor.digits_stage(plan, a[d])
+            executor.digits_stage(plan, a[d], galois)
         blocks = self._deliver_digits(plans, level)
         out0, out1 = [None] * n_dev, [None] * n_dev
         for d, plan in plans.items():
@@ -725,7 +728,7 @@ class ckks_engine:
             add0 = add[0][d] if add is not None and add[0] is not None else None
             add1 = add[1][d] if add is not None and add[1] is not None else None
             executor.keyswitch_stage(plan, plan.digit_pointer_table(blocks[d]), k0p, k1p, ks, permuted, add0, add1,
-                                     out0[d], out1[d])
+                                     out0[d], out1[d], add0_galois=galois)
         return out0, out1
 
     def _mult_fused(self, a, b, evk):
@@ -869,7 +872,12 @@ class ckks_engine:
             raise errors.NotMatchType(origin=rotk.origin, to=types.origins["rotk"])
         delta = int(rotk.origin.split(":")[-1])
         N = self.ctx.N
-        data = self._galois(ct, pow(3, delta % N, 2 * N), canon=True)
+        g = pow(3, delta % N, 2 * N)
+        if self.fast and self.use_executor and not ct.ntt_state and not ct.include_special:
+            # the automorphism is folded into the loads of the key switch (no rotated ciphertext in HBM)
+            new0, d1 = self._keyswitch_fused(ct.data[1], rotk, ct.level, add=(ct.data[0], None), galois=g)
+            return self._ct((new0, d1), ct.level, "ct")
+        data = self._galois(ct, g, canon=True)
         moved = self._ct(data, ct.level, "ct", include_special=ct.include_special, ntt_state=ct.ntt_state,
                          montgomery_state=ct.montgomery_state)
         return self.switch_key(moved, rotk)

@@ -215,14 +215,16 @@ def tensor_stage(plan, polys, r0s):
                                          _p(plan.digits), _stream(plan.x)), "exec_tensor_stage")
 
 
-def digits_stage(plan, a):
+def digits_stage(plan, a, galois=0):
+    """galois != 0: digits of the Galois image of `a` (canonical rows), gathered from the unrotated polynomial"""
     with torch.cuda.device(a.device):
-        check(lib.ckks_exec_digits(plan.ref, _p(a), a.stride(0), _p(plan.digits), plan.N, _stream(a)), "exec_digits")
+        check(lib.ckks_exec_digits(plan.ref, _p(a), a.stride(0), _p(plan.digits), plan.N, int(galois), _stream(a)), "exec_digits")
 
 
-def keyswitch_stage(plan, digit_ptrs, k0p, k1p, kstride, permuted, add0, add1, out0, out1):
+def keyswitch_stage(plan, digit_ptrs, k0p, k1p, kstride, permuted, add0, add1, out0, out1, add0_galois=0):
+    """add0_galois != 0: the addend of output 0 is the Galois image of add0, gathered inside the ModDown kernel"""
     add = add0 if add0 is not None else add1
     with torch.cuda.device(out0.device):
         check(lib.ckks_exec_keyswitch_stage(plan.ref, _p(digit_ptrs), plan.N, _p(k0p), _p(k1p), kstride, 1 if permuted else 0,
-                                            _p(add0), _p(add1), add.stride(0) if add is not None else 0, _p(out0), _p(out1),
-                                            plan.N, _p(plan.ks_ws), _stream(out0)), "exec_keyswitch_stage")
+                                            _p(add0), _p(add1), add.stride(0) if add is not None else 0, int(add0_galois),
+                                            _p(out0), _p(out1), plan.N, _p(plan.ks_ws), _stream(out0)), "exec_keyswitch_stage")

@@ -58,8 +58,18 @@ def main():
             return _enc(m, level, padding)
         eng.encode = encode
         chk = Checker(g["digests"], full, eng.ntt.devices)
-        flows.hot_path_flow(eng, chk)
+        objs = flows.hot_path_flow(eng, chk)
+        flows.extra_flow(eng, chk, objs)
         failures += [f"[{mode}] {f}" for f in chk.failures]
+        if mode == "executor":     # the wire format in distributed mode: every rank assembles the whole prime-ordered tensor
+            host = eng.cpu(objs["ct_ab"])
+            want = np.concatenate([full[f"ct_ab_host/{c}"] for c in (0, 1)]) if "ct_ab_host/0" in full else None
+            back = eng.cuda(host)
+            for c in (0, 1):
+                mine, again = objs["ct_ab"].data[c][rank], back.data[c][rank]
+                if mine is not None and not torch.equal(mine, again):
+                    failures.append(f"[{mode}] cpu()/cuda() round trip differs on rank {rank}")
+            del want
     ok = torch.tensor([0 if failures else 1], device="cuda")
     dist.all_reduce(ok, op=dist.ReduceOp.MIN)
     if failures:

@@ -50,24 +50,29 @@ def test_unmodified_reference_engine_on_our_ntt_cuda():
         swapped = fhe2.ckks_engine(devices=[0], cache_folder=cache, **params)
         assert swapped.hash == stock.hash
 
-        def both(fn):
+        def both(fn, what):
             a, b = fn(stock), fn(swapped)
-            assert same(a, b), fn.__name__
+            for pi, (pa, pb) in enumerate(zip(a.data, b.data)):
+                for di, (u, v) in enumerate(zip(pa, pb)):
+                    if not torch.equal(u, v):
+                        rows = (u != v).any(dim=1).nonzero().flatten().tolist()
+                        raise AssertionError(f"{what}: polynomial {pi} device {di}: {int((u != v).sum())} elements differ in rows "
+                                             f"{rows[:8]} of {u.size(0)}; first pair {u[u != v][0].item()} vs {v[u != v][0].item()}")
             return a
 
         # deterministic operators on shared inputs, at several levels
         x = ct
         for _ in range(3):
-            trip = both(lambda e: e.cc_mult(x, x, evk, relin=False))
-            both(lambda e: e.relinearize(e.clone(trip), evk))
-            y = both(lambda e: e.cc_mult(x, x, evk))
-            both(lambda e: e.rotate_single(y, rotk))
-            both(lambda e: e.rescale(x))
+            trip = both(lambda e: e.cc_mult(x, x, evk, relin=False), f"cc_mult(relin=False) at level {x.level}")
+            both(lambda e: e.relinearize(e.clone(trip), evk), f"relinearize at level {trip.level}")
+            y = both(lambda e: e.cc_mult(x, x, evk), f"cc_mult at level {x.level}")
+            both(lambda e: e.rotate_single(y, rotk), f"rotate_single at level {y.level}")
+            both(lambda e: e.rescale(x), f"rescale at level {x.level}")
             x = y
-        both(lambda e: e.cc_add(ct, ct))
-        both(lambda e: e.level_up(ct, 2))
-        both(lambda e: e.mult_scalar(ct, 0.5))
-        both(lambda e: e.mc_mult(m, ct))
+        both(lambda e: e.cc_add(ct, ct), "cc_add")
+        both(lambda e: e.level_up(ct, 2), "level_up")
+        both(lambda e: e.mult_scalar(ct, 0.5), "mult_scalar")
+        # (mc_mult is not compared: the reference's encode draws fresh random-rounding bits on every call)
         dec_a, dec_b = stock.decrode(x, sk), swapped.decrode(x, sk)
         assert np.array_equal(dec_a, dec_b)
         # key generation and encryption through the swapped engine (its own randomness): the results work in the stock engine

@@ -223,7 +223,7 @@ def test_fused_keyswitch_pieces_bit_exact(logN, alpha, K):
 # variants of the fast transforms: library knobs (ckks_set_option) and whether the caller passes the packed tables;
 # every one must give the same bits
 FAST_VARIANTS = {"default": ([], True), "plain-tables": ([], False), "packed-off": ([(17, 0)], True),
-                 "no-prefetch": ([(2, 0)], True), "one-stream": ([(10, 1)], True), "small-slabs": ([(11, 1)], True)}
+                 "prefetch": ([(2, 28)], True), "one-stream": ([(10, 1)], True), "small-slabs": ([(11, 1)], True)}
 
 
 @pytest.mark.parametrize("logN", [12, 13, 14, 15, 16, 17])
