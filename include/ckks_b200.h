@@ -224,12 +224,15 @@ int ckks_exec_digits(const ckks_level_t* lv, const int64_t* a, int64_t a_stride,
  * with ckks_perm_rows (the stage then keeps its NTT-domain data in the same order);
  * add0_galois = 0, or an odd g < 2N: the polynomial added to output 0 is the Galois image of add0 (rotate_single: the
  * rotated c0, engine.py:1194-1200, 947), gathered from the unrotated canonical rows inside the ModDown kernel;
- * ws: ckks_exec_keyswitch_ws_elems(...) int64 elements. */
+ * ws: ckks_exec_keyswitch_ws_elems(...) int64 elements;
+ * phase: 3 = the whole stage; 1 = only extend + batched NTT (the NTT-domain extended block stays in ws); 2 = only inner
+ * product + inverse NTT + ModDown on the block a phase-1 call left in ws -- hoisted rotations share one phase-1 call among
+ * many keys (engine.rotate_hoisted; keys_permuted must be the same in both calls). */
 int ckks_exec_keyswitch_stage(const ckks_level_t* lv, const int64_t* const* digit_ptrs, int64_t digit_stride,
                               const int64_t* const* k0_ptrs, const int64_t* const* k1_ptrs, int64_t ksk_stride,
                               int keys_permuted, const int64_t* add0, const int64_t* add1, int64_t add_stride,
                               int64_t add0_galois, int64_t* out0, int64_t* out1, int64_t out_stride, int64_t* ws,
-                              void* stream);
+                              int phase, void* stream);
 int64_t ckks_exec_keyswitch_ws_elems(int L, int K, int nparts, int N);
 
 /* ---- sampler: ChaCha20 counter mode (replaces src/liberate/csprng/: chacha20 / randint / discrete_gaussian / randround

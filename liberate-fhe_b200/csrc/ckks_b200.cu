@@ -1073,8 +1073,12 @@ int ckks_exec_keyswitch_stage(const ckks_level_t* lv, const int64_t* const* digi
                               const int64_t* const* k0_ptrs, const int64_t* const* k1_ptrs, int64_t ksk_stride,
                               int keys_permuted, const int64_t* add0, const int64_t* add1, int64_t add_stride,
                               int64_t add0_galois, int64_t* out0, int64_t* out1, int64_t out_stride, int64_t* ws,
-                              void* stream) {
-    CHECK_PTRS(lv, digit_ptrs, k0_ptrs, k1_ptrs, out0, out1, ws);
+                              int phase, void* stream) {
+    if (phase < 1 || phase > 3) return CKKS_E_BADARG;
+    const bool do_fwd = phase & 1, do_tail = phase & 2;
+    CHECK_PTRS(lv, ws);
+    if (do_fwd) CHECK_PTRS(digit_ptrs);
+    if (do_tail) CHECK_PTRS(k0_ptrs, k1_ptrs, out0, out1);
     if (add0_galois && (!(add0_galois & 1) || add0_galois < 0 || add0_galois >= (2ll << lv->logN) || !add0 || add0 == out0))
         return CKKS_E_BADARG;
     const unsigned add_ginv[2] = {add0_galois ? galois_inverse((unsigned)add0_galois, 1u << lv->logN) : 0u, 0u};
@@ -1122,18 +1126,21 @@ int ckks_exec_keyswitch_stage(const ckks_level_t* lv, const int64_t* const* digi
         for (int t0 = 0; t0 < E; t0 += slab, ++slab_no) {
             cudaStream_t st = pipes ? pipes->s[slab_no % npipes] : main_st;
             const int t1 = (t0 + slab < E) ? t0 + slab : E;
-            const dim3 eg((N / 2 + 255) / 256, P);
-            if (lv->amax <= 2) k_extend_fast<2><<<eg, 256, 0, st>>>(X, t0, t1);
-            else if (lv->amax <= 4) k_extend_fast<4><<<eg, 256, 0, st>>>(X, t0, t1);
-            else k_extend_fast<8><<<eg, 256, 0, st>>>(X, t0, t1);
-            RC(launch_status());
-            FastArgs F = level_fast(lv, ext, N, true, nullptr, nullptr, E);
-            F.slab_rows = t1 - t0; F.group_rows = E; F.slab_t0 = t0;
-            F.in_raw = 1; F.out_raw = 1;
-            const dim3 grid(N / TILE, P * (t1 - t0));
-            RC(launch_fast_col(true, F, grid, st));
-            F.perm = perm;
-            RC(launch_fast_block_any(true, F, grid, st));
+            if (do_fwd) {
+                const dim3 eg((N / 2 + 255) / 256, P);
+                if (lv->amax <= 2) k_extend_fast<2><<<eg, 256, 0, st>>>(X, t0, t1);
+                else if (lv->amax <= 4) k_extend_fast<4><<<eg, 256, 0, st>>>(X, t0, t1);
+                else k_extend_fast<8><<<eg, 256, 0, st>>>(X, t0, t1);
+                RC(launch_status());
+                FastArgs F = level_fast(lv, ext, N, true, nullptr, nullptr, E);
+                F.slab_rows = t1 - t0; F.group_rows = E; F.slab_t0 = t0;
+                F.in_raw = 1; F.out_raw = 1;
+                const dim3 grid(N / TILE, P * (t1 - t0));
+                RC(launch_fast_col(true, F, grid, st));
+                F.perm = perm;
+                RC(launch_fast_block_any(true, F, grid, st));
+            }
+            if (!do_tail) continue;
             InnerArgs I{};
             I.ext = ext; I.k0 = k0_ptrs; I.k1 = k1_ptrs; I.k_stride = ksk_stride;
             I.acc0 = acc; I.acc1 = acc + (long long)E * N;
@@ -1145,14 +1152,18 @@ int ckks_exec_keyswitch_stage(const ckks_level_t* lv, const int64_t* const* digi
         RC(scope.join());
     } else {
         if (perm) return CKKS_E_BADARG;   // the integer fall-back works on natural-order keys only
-        k_extend_batched<<<ew_grid(N, P * E), EW_THREADS, 0, S(stream)>>>(digit_ptrs, digit_stride, lv->part_alpha, ext, N, E,
-                                                                          N, lv->Rs, lv->Lenter, m);
-        RC(launch_status());
-        FastArgs F = level_fast(lv, ext, N, true, nullptr, nullptr, E);
-        RC(fast_transform(true, F, P * E, S(stream)));
-        RC(ckks_ksk_inner(ext, N, P, k0_ptrs, k1_ptrs, ksk_stride, acc, acc + (long long)E * N, N, E, N, lv->_2q, lv->ql,
-                          lv->qh, lv->kl, lv->kh, stream));
+        if (do_fwd) {
+            k_extend_batched<<<ew_grid(N, P * E), EW_THREADS, 0, S(stream)>>>(digit_ptrs, digit_stride, lv->part_alpha, ext, N,
+                                                                              E, N, lv->Rs, lv->Lenter, m);
+            RC(launch_status());
+            FastArgs F = level_fast(lv, ext, N, true, nullptr, nullptr, E);
+            RC(fast_transform(true, F, P * E, S(stream)));
+        }
+        if (do_tail)
+            RC(ckks_ksk_inner(ext, N, P, k0_ptrs, k1_ptrs, ksk_stride, acc, acc + (long long)E * N, N, E, N, lv->_2q, lv->ql,
+                              lv->qh, lv->kl, lv->kh, stream));
     }
+    if (!do_tail) return 0;
     // The two output polynomials are independent from here on: inverse transform + ModDown of each half run on their
     // own internal stream, so the small latency-bound ModDown kernels of one half overlap the transform of the other.
     int64_t* outs[2] = {out0, out1};

@@ -203,6 +203,38 @@ class ckks_engine:
             self._key_shadow[id(t)] = hit
         return hit[1]
 
+    def _galois_ntt_index(self, g, dev):
+        """P with NTT(pi_g(x))[i] == NTT(x)[P[i]] for the reference's bit-reversed NTT order: slot i evaluates at
+        psi^(2 bitrev(i) + 1), and pi_g: X -> X^g moves that point to its g-th power."""
+        key = ("gal_ntt", g, str(dev))
+        P = self._ptr_cache.get(key)
+        if P is None:
+            logN, N = self.ctx.logN, self.ctx.N
+            i = torch.arange(N, dtype=torch.int64, device=dev)
+
+            def bitrev(x):
+                r = torch.zeros_like(x)
+                for b in range(logN):
+                    r |= ((x >> b) & 1) << (logN - 1 - b)
+                return r
+            e = ((2 * bitrev(i) + 1) * g) % (2 * N)
+            P = bitrev((e - 1) // 2)
+            self._ptr_cache[key] = P
+        return P
+
+    def _hoist_key(self, t, g, permuted):
+        """the key polynomial K' with NTT-domain pi_g(K') = K, i.e. K'[i] = K[P_{g^-1}[i]] (and then, for the executor, in
+        warp-interleaved order).  Hoisted rotations switch with K' and apply pi_g to the RESULT, so one ModUp serves all
+        rotations of a ciphertext.  Made once per (key, g), kept like the permuted copies."""
+        ck = (id(t), g, permuted)
+        hit = self._key_shadow.get(ck)
+        if hit is None or hit[0] is not t:
+            ginv = pow(g, -1, 2 * self.ctx.N)
+            moved = t[:, self._galois_ntt_index(ginv, t.device)].contiguous()
+            hit = (t, fused.perm_rows(moved) if permuted else moved)
+            self._key_shadow[ck] = hit
+        return hit[1]
+
     def release_key_cache(self):
         """drop the permuted key copies and pointer tables (they are rebuilt on the next use of a key)"""
         self._key_shadow.clear()
@@ -881,6 +913,45 @@ class ckks_engine:
         moved = self._ct(data, ct.level, "ct", include_special=ct.include_special, ntt_state=ct.ntt_state,
                          montgomery_state=ct.montgomery_state)
         return self.switch_key(moved, rotk)
+
+    def rotate_hoisted(self, ct: data_struct, rotks: list) -> list:
+        """B200 addition (no reference counterpart): the rotations of ONE ciphertext by every key of
+        `rotks`, sharing the expensive half of the key switch.  rotate_single(ct, k) = switch(pi_g(c1), k) + pi_g(c0) pays
+        Garner digits -> ModUp -> beta*E NTTs per rotation; here c1 is decomposed, extended and transformed ONCE, every
+        rotation takes only the inner product with K' = pi_g^-1(k) (NTT-domain pre-image, cached per key), the two
+        inverse transforms and ModDown, and pi_g is applied to the result.  The outputs are valid rotations that decrypt
+        like rotate_single's (same noise level) but are not the same bits: Garner digits do not commute with pi_g."""
+        if ct.origin != types.origins["ct"] or ct.ntt_state or ct.include_special:
+            raise errors.NotMatchType(origin=ct.origin, to=types.origins["ct"])
+        for k in rotks:
+            if types.origins["rotk"] not in k.origin:
+                raise errors.NotMatchType(origin=k.origin, to=types.origins["rotk"])
+        if not (self.fast and self.use_executor):
+            return [self.rotate_single(ct, k) for k in rotks]
+        level, N = ct.level, self.ctx.N
+        n_dev = self.len_devices[level]
+        plans = {d: self._plan(level, d) for d in range(n_dev) if self._local(d)}
+        for d, plan in plans.items():
+            executor.digits_stage(plan, ct.data[1][d])
+        blocks = self._deliver_digits(plans, level)
+        for d, plan in plans.items():       # extend + batched NTT, once
+            executor.keyswitch_stage(plan, plan.digit_pointer_table(blocks[d]), None, None, 0, plan.permuted_keys(), None, None,
+                                     None, None, phase=1)
+        outs = []
+        for k in rotks:
+            g = pow(3, int(k.origin.split(":")[-1]) % N, 2 * N)
+            out0, out1 = [None] * n_dev, [None] * n_dev
+            for d, plan in plans.items():
+                dev = self.ntt.devices[d]
+                t0 = torch.empty((plan.L, N), dtype=torch.int64, device=dev)
+                t1 = torch.empty((plan.L, N), dtype=torch.int64, device=dev)
+                k0p, k1p, ks, permuted = plan.key_pointer_tables(self, k, hoist_g=g)
+                executor.keyswitch_stage(plan, None, k0p, k1p, ks, permuted, ct.data[0][d], None, t0, t1, phase=2)
+                _2q = self.ntt._sel(self.ntt._2q, level, d, -1)[0]
+                out0[d] = fused.automorphism(t0, g, True, _2q)
+                out1[d] = fused.automorphism(t1, g, True, _2q)
+            outs.append(self._ct((out0, out1), level, "ct"))
+        return outs
 
     def rotate_galois(self, ct: data_struct, gk: data_struct, delta: int, return_circuit=False) -> data_struct:
         if ct.origin != types.origins["ct"]:

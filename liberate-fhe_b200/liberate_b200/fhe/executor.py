@@ -177,11 +177,16 @@ class LevelPlan:
             self._blocks = blocks
         return self._digit_ptrs
 
-    def key_pointer_tables(self, eng, ksk):
+    def permuted_keys(self):
+        """does this plan's key-switch stage keep its NTT domain in warp-interleaved order (option 18, FP64 pipeline only)?"""
+        return bool(lib.ckks_get_option(18)) and self.fp64
+
+    def key_pointer_tables(self, eng, ksk, hoist_g=0):
         """device tables of the row-0 pointers of every partition's key halves at this level -> (k0, k1, stride, permuted).
         With option 18 (default) the stage keeps its NTT-domain data in warp-interleaved order, so the pointers go to
         PERMUTED copies of the key rows (made once per key and device by ckks_perm_rows, cached on the engine)."""
-        hit = self._key_ptrs.get(id(ksk.data))
+        ck = (id(ksk.data), hoist_g)
+        hit = self._key_ptrs.get(ck)
         permuted = bool(lib.ckks_get_option(18)) and self.fp64
         if hit is None or hit[0] is not ksk.data or hit[4] != permuted:
             start = eng.ntt.starts[self.level][self.dev]
@@ -190,16 +195,17 @@ class LevelPlan:
                 src, part_id, _alpha = self.owners[s]
                 kd = ksk.data[eng.parts_alloc[self.level][src][part_id]].data
                 h0, h1 = kd[0][self.dev], kd[1][self.dev]
-                if permuted:
+                if hoist_g:     # hoisted rotation: the NTT-domain pre-image of the key under the Galois map (made once per key)
+                    h0, h1 = eng._hoist_key(h0, hoist_g, permuted), eng._hoist_key(h1, hoist_g, permuted)
+                elif permuted:
                     h0, h1 = eng._permuted_key(h0), eng._permuted_key(h1)
                 p0.append(h0[start:].data_ptr())
                 p1.append(h1[start:].data_ptr())
             dev = self.x.device
-            hit = (ksk.data, torch.tensor(p0, dtype=torch.int64, device=dev),
-                   torch.tensor(p1, dtype=torch.int64, device=dev), self.N, permuted) if permuted else \
-                  (ksk.data, torch.tensor(p0, dtype=torch.int64, device=dev),
-                   torch.tensor(p1, dtype=torch.int64, device=dev), ksk.data[0].data[0][self.dev].stride(0), permuted)
-            self._key_ptrs[id(ksk.data)] = hit
+            stride = self.N if (permuted or hoist_g) else ksk.data[0].data[0][self.dev].stride(0)
+            hit = (ksk.data, torch.tensor(p0, dtype=torch.int64, device=dev), torch.tensor(p1, dtype=torch.int64, device=dev),
+                   stride, permuted)
+            self._key_ptrs[ck] = hit
         return hit[1], hit[2], hit[3], hit[4]
 
 
@@ -221,10 +227,13 @@ def digits_stage(plan, a, galois=0):
         check(lib.ckks_exec_digits(plan.ref, _p(a), a.stride(0), _p(plan.digits), plan.N, int(galois), _stream(a)), "exec_digits")
 
 
-def keyswitch_stage(plan, digit_ptrs, k0p, k1p, kstride, permuted, add0, add1, out0, out1, add0_galois=0):
-    """add0_galois != 0: the addend of output 0 is the Galois image of add0, gathered inside the ModDown kernel"""
+def keyswitch_stage(plan, digit_ptrs, k0p, k1p, kstride, permuted, add0, add1, out0, out1, add0_galois=0, phase=3):
+    """add0_galois != 0: the addend of output 0 is the Galois image of add0, gathered inside the ModDown kernel.
+    phase 1: extend + NTT only (k*/add*/out* may be None); phase 2: inner product + tail on the block phase 1 left behind"""
     add = add0 if add0 is not None else add1
-    with torch.cuda.device(out0.device):
-        check(lib.ckks_exec_keyswitch_stage(plan.ref, _p(digit_ptrs), plan.N, _p(k0p), _p(k1p), kstride, 1 if permuted else 0,
+    dev = plan.x.device
+    with torch.cuda.device(dev):
+        check(lib.ckks_exec_keyswitch_stage(plan.ref, _p(digit_ptrs), plan.N, _p(k0p), _p(k1p), kstride or 0, 1 if permuted else 0,
                                             _p(add0), _p(add1), add.stride(0) if add is not None else 0, int(add0_galois),
-                                            _p(out0), _p(out1), plan.N, _p(plan.ks_ws), _stream(out0)), "exec_keyswitch_stage")
+                                            _p(out0), _p(out1), plan.N, _p(plan.ks_ws), int(phase), _stream(plan.x)),
+              "exec_keyswitch_stage")

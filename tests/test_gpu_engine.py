@@ -173,3 +173,34 @@ def test_optional_fused_paths_reproduce_reference_tensors(opts):
     finally:
         for k, v in option_defaults().items():
             lib.ckks_set_option(k, v)
+
+
+def test_hoisted_rotations_decrypt_like_single_rotations():
+    """engine.rotate_hoisted: one ModUp (digits -> extension -> beta*E NTTs) shared by all rotations of a ciphertext; every
+    rotation then takes the inner product with the NTT-domain pre-image of its key, the inverse transforms, ModDown and the
+    Galois map on the result.  Valid rotations with rotate_single's accuracy (not the same bits: Garner digits do not commute
+    with the Galois map)."""
+    from liberate_b200 import fhe
+    for D in (1, 2):
+        eng = fhe.ckks_engine(devices=["cuda:0"] * D, logN=13, num_scales=6, num_special_primes=2, scale_bits=40, is_secured=False)
+        sk = eng.create_secret_key()
+        pk = eng.create_public_key(sk)
+        evk = eng.create_evk(sk)
+        m = eng.example(-1, 1)
+        ct = eng.mult(eng.encorypt(m, pk), eng.encorypt(m, pk), evk)      # level 1
+        deltas = [1, 2, 8, 64, 1000]
+        keys = [eng.create_rotation_key(sk, d) for d in deltas]
+        outs = eng.rotate_hoisted(ct, keys)
+        for d, k, o in zip(deltas, keys, outs):
+            want = np.roll(m * m, d)
+            single = eng.decrode(eng.rotate_single(ct, k), sk)
+            got = eng.decrode(o, sk)
+            assert np.abs(got - want).max() < 1e-6, (D, d)
+            assert np.abs(got - single).max() < 1e-6, (D, d)
+            assert o.level == ct.level and not o.ntt_state
+            for poly in o.data:                     # canonical rows, like every ciphertext the engine hands out
+                for dev, t in enumerate(poly):
+                    assert int(t.min()) >= 0 and bool((t < eng.ntt.q[dev][eng.ntt.starts[o.level][dev]:eng.ntt.starts[o.level][dev] + t.size(0), None]).all())
+        # a second call reuses the cached key pre-images and gives the same bits
+        again = eng.rotate_hoisted(ct, keys)
+        assert all(torch.equal(x, y) for a, b in zip(outs, again) for pa, pb in zip(a.data, b.data) for x, y in zip(pa, pb))
