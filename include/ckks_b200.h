@@ -227,12 +227,14 @@ int ckks_exec_digits(const ckks_level_t* lv, const int64_t* a, int64_t a_stride,
  * ws: ckks_exec_keyswitch_ws_elems(...) int64 elements;
  * phase: 3 = the whole stage; 1 = only extend + batched NTT (the NTT-domain extended block stays in ws); 2 = only inner
  * product + inverse NTT + ModDown on the block a phase-1 call left in ws -- hoisted rotations share one phase-1 call among
- * many keys (engine.rotate_hoisted; keys_permuted must be the same in both calls). */
+ * many keys (engine.rotate_hoisted; keys_permuted must be the same in both calls);
+ * part_begin, part_end: phase 1 only -- the range of partitions (positions in lv's partition order) to extend and transform,
+ * -1, -1 = all: one process per GPU transforms its own partitions while the peers' digit blocks are still arriving. */
 int ckks_exec_keyswitch_stage(const ckks_level_t* lv, const int64_t* const* digit_ptrs, int64_t digit_stride,
                               const int64_t* const* k0_ptrs, const int64_t* const* k1_ptrs, int64_t ksk_stride,
                               int keys_permuted, const int64_t* add0, const int64_t* add1, int64_t add_stride,
                               int64_t add0_galois, int64_t* out0, int64_t* out1, int64_t out_stride, int64_t* ws,
-                              int phase, void* stream);
+                              int phase, int part_begin, int part_end, void* stream);
 int64_t ckks_exec_keyswitch_ws_elems(int L, int K, int nparts, int N);
 
 /* ---- sampler: ChaCha20 counter mode (replaces src/liberate/csprng/: chacha20 / randint / discrete_gaussian / randround

@@ -1073,10 +1073,15 @@ int ckks_exec_keyswitch_stage(const ckks_level_t* lv, const int64_t* const* digi
                               const int64_t* const* k0_ptrs, const int64_t* const* k1_ptrs, int64_t ksk_stride,
                               int keys_permuted, const int64_t* add0, const int64_t* add1, int64_t add_stride,
                               int64_t add0_galois, int64_t* out0, int64_t* out1, int64_t out_stride, int64_t* ws,
-                              int phase, void* stream) {
+                              int phase, int part_begin, int part_end, void* stream) {
     if (phase < 1 || phase > 3) return CKKS_E_BADARG;
     const bool do_fwd = phase & 1, do_tail = phase & 2;
     CHECK_PTRS(lv, ws);
+    // partition range of a forward-only call: one process per GPU transforms its own partitions while the peers' digits
+    // are still on the wire, and the rest when they have arrived
+    const int pb = (part_begin < 0) ? 0 : part_begin, pe = (part_end < 0) ? lv->nparts : part_end;
+    if (pb < 0 || pe > lv->nparts || pb > pe || ((pb != 0 || pe != lv->nparts) && phase != 1)) return CKKS_E_BADARG;
+    if (pb == pe) return 0;
     if (do_fwd) CHECK_PTRS(digit_ptrs);
     if (do_tail) CHECK_PTRS(k0_ptrs, k1_ptrs, out0, out1);
     if (add0_galois && (!(add0_galois & 1) || add0_galois < 0 || add0_galois >= (2ll << lv->logN) || !add0 || add0 == out0))
@@ -1097,23 +1102,24 @@ int ckks_exec_keyswitch_stage(const ckks_level_t* lv, const int64_t* const* digi
         // Measured (profiles/r01_lab_notes.txt): L2-sized slabs (32-64 MB) lose more to small grids than they gain from
         // L2 residency of the extended block; two 100 MB slabs on two streams are the best setting at gold.
         ExtArgs X{};
-        X.digit_ptrs = digit_ptrs;
+        X.digit_ptrs = digit_ptrs ? digit_ptrs + pb : nullptr;
         X.d_stride = digit_stride;
-        X.alphas = lv->part_alpha;
-        X.wide = lv->part_wide;
-        X.Hm = lv->Hm;
+        X.alphas = lv->part_alpha + pb;
+        X.wide = lv->part_wide + pb;
+        X.Hm = lv->Hm + pb;
         X.Rd = lv->Rd;
         X.C31 = lv->C31;
-        X.Lenter = lv->Lenter;
+        X.Lenter = lv->Lenter + pb;
         X.Rs = lv->Rs;
         X.q = lv->q; X._2q = lv->_2q; X.ql = lv->ql; X.qh = lv->qh; X.kl = lv->kl; X.kh = lv->kh;
-        X.out = ext;
+        X.out = ext + (long long)pb * E * N;
         X.E = E;
         X.N = N;
         X.raw = 1;   // scale-prime rows travel as raw doubles from the extension to the inverse transform
         X.qinv = lv->qinv;
         const long long slab_budget = (long long)g_slab_mb << 20;   // bytes of extended rows per slab
-        const long long all_bytes = (long long)P * E * N * 8;
+        const int Pr = pe - pb;                                      // partitions this call transforms
+        const long long all_bytes = (long long)Pr * E * N * 8;
         const int nslabs = (int)((all_bytes + slab_budget - 1) / slab_budget);
         const int slab = (E + nslabs - 1) / nslabs;
         if (slab > EXT_MAX_E) return CKKS_E_BADARG;
@@ -1127,15 +1133,15 @@ int ckks_exec_keyswitch_stage(const ckks_level_t* lv, const int64_t* const* digi
             cudaStream_t st = pipes ? pipes->s[slab_no % npipes] : main_st;
             const int t1 = (t0 + slab < E) ? t0 + slab : E;
             if (do_fwd) {
-                const dim3 eg((N / 2 + 255) / 256, P);
+                const dim3 eg((N / 2 + 255) / 256, Pr);
                 if (lv->amax <= 2) k_extend_fast<2><<<eg, 256, 0, st>>>(X, t0, t1);
                 else if (lv->amax <= 4) k_extend_fast<4><<<eg, 256, 0, st>>>(X, t0, t1);
                 else k_extend_fast<8><<<eg, 256, 0, st>>>(X, t0, t1);
                 RC(launch_status());
-                FastArgs F = level_fast(lv, ext, N, true, nullptr, nullptr, E);
+                FastArgs F = level_fast(lv, ext + (long long)pb * E * N, N, true, nullptr, nullptr, E);
                 F.slab_rows = t1 - t0; F.group_rows = E; F.slab_t0 = t0;
                 F.in_raw = 1; F.out_raw = 1;
-                const dim3 grid(N / TILE, P * (t1 - t0));
+                const dim3 grid(N / TILE, Pr * (t1 - t0));
                 RC(launch_fast_col(true, F, grid, st));
                 F.perm = perm;
                 RC(launch_fast_block_any(true, F, grid, st));
@@ -1153,11 +1159,13 @@ int ckks_exec_keyswitch_stage(const ckks_level_t* lv, const int64_t* const* digi
     } else {
         if (perm) return CKKS_E_BADARG;   // the integer fall-back works on natural-order keys only
         if (do_fwd) {
-            k_extend_batched<<<ew_grid(N, P * E), EW_THREADS, 0, S(stream)>>>(digit_ptrs, digit_stride, lv->part_alpha, ext, N,
-                                                                              E, N, lv->Rs, lv->Lenter, m);
+            const int Pr = pe - pb;
+            int64_t* extp = ext + (long long)pb * E * N;
+            k_extend_batched<<<ew_grid(N, Pr * E), EW_THREADS, 0, S(stream)>>>(digit_ptrs + pb, digit_stride, lv->part_alpha + pb,
+                                                                               extp, N, E, N, lv->Rs, lv->Lenter + pb, m);
             RC(launch_status());
-            FastArgs F = level_fast(lv, ext, N, true, nullptr, nullptr, E);
-            RC(fast_transform(true, F, P * E, S(stream)));
+            FastArgs F = level_fast(lv, extp, N, true, nullptr, nullptr, E);
+            RC(fast_transform(true, F, Pr * E, S(stream)));
         }
         if (do_tail)
             RC(ckks_ksk_inner(ext, N, P, k0_ptrs, k1_ptrs, ksk_stride, acc, acc + (long long)E * N, N, E, N, lv->_2q, lv->ql,

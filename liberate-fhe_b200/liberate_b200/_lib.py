@@ -56,7 +56,7 @@ SIGNATURES = {
     "ckks_automorphism": [_i64p, _i64, _i64p, _i64, _int, _int, _i64, _int, _i64p, _vp],
     "ckks_exec_tensor_stage": [_vp, _i64p, _i64p, _i64p, _i64p, _i64, _i64p, _i64p, _i64p, _i64p, _i64p, _i64p, _i64p, _vp],
     "ckks_exec_digits": [_vp, _i64p, _i64, _i64p, _i64, _i64, _vp],
-    "ckks_exec_keyswitch_stage": [_vp, _vp, _i64, _vp, _vp, _i64, _int, _i64p, _i64p, _i64, _i64, _i64p, _i64p, _i64, _i64p, _int, _vp],
+    "ckks_exec_keyswitch_stage": [_vp, _vp, _i64, _vp, _vp, _i64, _int, _i64p, _i64p, _i64, _i64, _i64p, _i64p, _i64, _i64p, _int, _int, _int, _vp],
     "ckks_exec_keyswitch_ws_elems": [_int, _int, _int, _int],
     "ckks_rng_bytes": [_i64p, _int, _int, _vp, _vp, _vp, ctypes.c_uint64, _vp],
     "ckks_rng_randint": [_i64p, _int, _int, _vp, _i64, _vp, _vp, _vp, ctypes.c_uint64, _vp],

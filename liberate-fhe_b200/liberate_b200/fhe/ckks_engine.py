@@ -187,6 +187,8 @@ class ckks_engine:
         self._ws = {}
         self._dead_gather = {}
         self._key_shadow = {}
+        self._gather_stream = None
+        self._gather_pending = False
 
         P = math.prod(c.q[-K:])
         self.mont_PR = [self._t([P * c.R % c.q[i] for i in p.destination_arrays[0][dev]], dev) if self._local(dev) else None
@@ -277,6 +279,8 @@ class ckks_engine:
             return out
         # DistComm: ONE all_gather into a persistent buffer.  Every rank takes part, also ranks whose device holds
         # no ordinary limb any more at this level (they contribute an empty block and receive nothing they use).
+        # The gather runs on a side stream: the caller transforms its OWN partitions (whose digits are already in place)
+        # while the peers' blocks are on the wire, then calls _digits_ready() before touching those.
         world = self.comm.world
         owners = self._part_owners(level)
         rows_of = [0] * world
@@ -296,16 +300,52 @@ class ckks_engine:
                 st = plan.local_state(sid)
                 mine[r:r + st.size(0)].copy_(st)
                 r += st.size(0)
-        self.comm.dist.all_gather_into_tensor(gathered.view(-1, N), mine, group=self.comm.group)
+        main = torch.cuda.current_stream()
+        if self._gather_stream is None:
+            self._gather_stream = torch.cuda.Stream()
+        self._gather_stream.wait_stream(main)
+        with torch.cuda.stream(self._gather_stream):
+            self.comm.dist.all_gather_into_tensor(gathered.view(-1, N), mine, group=self.comm.group)
+        self._gather_pending = True
         if plan is None:
             return {}
         cursor = [0] * world
         blocks = {}
-        for sid in plan.sids:
+        for sid in sorted(plan.sids):
             src, _pid, alpha = plan.owners[sid]
-            blocks[sid] = gathered[src, cursor[src]:cursor[src] + alpha]
+            blocks[sid] = plan.local_state(sid) if src == me else gathered[src, cursor[src]:cursor[src] + alpha]
             cursor[src] += alpha
         return {me: blocks}
+
+    def _digits_ready(self):
+        """the peers' digit blocks of the last _deliver_digits have arrived (no-op in one process)"""
+        if self._gather_pending:
+            torch.cuda.current_stream().wait_stream(self._gather_stream)
+            self._gather_pending = False
+
+    def _switch_stages(self, plans, blocks, ksk, add, outs, galois=0, hoist_g=0, forward=True, tail=True):
+        """extend + NTT -> inner product -> inverse NTT -> ModDown on every local device.  One process per GPU: the
+        extension and transforms of the device's own partitions run while the all_gather is in flight."""
+        for d, plan in plans.items():
+            ptrs = plan.digit_pointer_table(blocks[d])
+            keys = plan.key_pointer_tables(self, ksk, hoist_g=hoist_g) if tail else (None, None, 0, plan.permuted_keys())
+            k0p, k1p, ks, permuted = keys
+            add0 = add[0][d] if add is not None and add[0] is not None else None
+            add1 = add[1][d] if add is not None and add[1] is not None else None
+            out0, out1 = (outs[0][d], outs[1][d]) if tail else (None, None)
+            n_local = len(plan.local_sids)
+            if forward and self._gather_pending and 0 < n_local < len(plan.sids):
+                executor.keyswitch_stage(plan, ptrs, None, None, 0, permuted, None, None, None, None, phase=1, parts=(0, n_local))
+                self._digits_ready()
+                executor.keyswitch_stage(plan, ptrs, None, None, 0, permuted, None, None, None, None, phase=1,
+                                         parts=(n_local, len(plan.sids)))
+                if tail:
+                    executor.keyswitch_stage(plan, None, k0p, k1p, ks, permuted, add0, add1, out0, out1, add0_galois=galois, phase=2)
+            else:
+                self._digits_ready()
+                phase = (1 if forward else 0) | (2 if tail else 0)
+                executor.keyswitch_stage(plan, ptrs, k0p, k1p, ks, permuted, add0, add1, out0, out1, add0_galois=galois, phase=phase)
+        self._digits_ready()          # (ranks without a plan at this level still took part in the gather)
 
     def _moddown_table(self, level, dev):
         """[K, E] row-major table of P_j^-1 * R for the rows of `dev` live at `level` (zero where a row is dead)"""
@@ -756,11 +796,7 @@ class ckks_engine:
             dev = self.ntt.devices[d]
             out0[d] = torch.empty((plan.L, plan.N), dtype=torch.int64, device=dev)
             out1[d] = torch.empty((plan.L, plan.N), dtype=torch.int64, device=dev)
-            k0p, k1p, ks, permuted = plan.key_pointer_tables(self, ksk)
-            add0 = add[0][d] if add is not None and add[0] is not None else None
-            add1 = add[1][d] if add is not None and add[1] is not None else None
-            executor.keyswitch_stage(plan, plan.digit_pointer_table(blocks[d]), k0p, k1p, ks, permuted, add0, add1,
-                                     out0[d], out1[d], add0_galois=galois)
+        self._switch_stages(plans, blocks, ksk, add, (out0, out1), galois=galois)
         return out0, out1
 
     def _mult_fused(self, a, b, evk):
@@ -789,9 +825,9 @@ class ckks_engine:
             dev = self.ntt.devices[d]
             out0[d] = torch.empty((plan.L, plan.N), dtype=torch.int64, device=dev)
             out1[d] = torch.empty((plan.L, plan.N), dtype=torch.int64, device=dev)
-            k0p, k1p, ks, permuted = plan.key_pointer_tables(self, evk)
-            executor.keyswitch_stage(plan, plan.digit_pointer_table(blocks[d]), k0p, k1p, ks, permuted, plan.d[0], plan.d[1],
-                                     out0[d], out1[d])
+        add = ([plans[d].d[0] if d in plans else None for d in range(n_after)],
+               [plans[d].d[1] if d in plans else None for d in range(n_after)])
+        self._switch_stages(plans, blocks, evk, add, (out0, out1))
         return self._ct((out0, out1), nxt, "ct")
 
     def switch_key(self, ct: data_struct, ksk: data_struct) -> data_struct:
@@ -934,22 +970,21 @@ class ckks_engine:
         for d, plan in plans.items():
             executor.digits_stage(plan, ct.data[1][d])
         blocks = self._deliver_digits(plans, level)
-        for d, plan in plans.items():       # extend + batched NTT, once
-            executor.keyswitch_stage(plan, plan.digit_pointer_table(blocks[d]), None, None, 0, plan.permuted_keys(), None, None,
-                                     None, None, phase=1)
+        self._switch_stages(plans, blocks, None, None, None, forward=True, tail=False)      # extend + batched NTT, once
         outs = []
         for k in rotks:
             g = pow(3, int(k.origin.split(":")[-1]) % N, 2 * N)
-            out0, out1 = [None] * n_dev, [None] * n_dev
+            tmp0, tmp1 = [None] * n_dev, [None] * n_dev
             for d, plan in plans.items():
                 dev = self.ntt.devices[d]
-                t0 = torch.empty((plan.L, N), dtype=torch.int64, device=dev)
-                t1 = torch.empty((plan.L, N), dtype=torch.int64, device=dev)
-                k0p, k1p, ks, permuted = plan.key_pointer_tables(self, k, hoist_g=g)
-                executor.keyswitch_stage(plan, None, k0p, k1p, ks, permuted, ct.data[0][d], None, t0, t1, phase=2)
+                tmp0[d] = torch.empty((plan.L, N), dtype=torch.int64, device=dev)
+                tmp1[d] = torch.empty((plan.L, N), dtype=torch.int64, device=dev)
+            self._switch_stages(plans, blocks, k, (ct.data[0], None), (tmp0, tmp1), hoist_g=g, forward=False, tail=True)
+            out0, out1 = [None] * n_dev, [None] * n_dev
+            for d in plans:
                 _2q = self.ntt._sel(self.ntt._2q, level, d, -1)[0]
-                out0[d] = fused.automorphism(t0, g, True, _2q)
-                out1[d] = fused.automorphism(t1, g, True, _2q)
+                out0[d] = fused.automorphism(tmp0[d], g, True, _2q)
+                out1[d] = fused.automorphism(tmp1[d], g, True, _2q)
             outs.append(self._ct((out0, out1), level, "ct"))
         return outs
 

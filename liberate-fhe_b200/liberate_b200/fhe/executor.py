@@ -70,7 +70,9 @@ class LevelPlan:
             return t
 
         owners = eng._part_owners(level)
-        self.sids = sorted(owners)
+        # partition order of this plan: the partitions whose digits this device makes first (their extension and transforms
+        # can start before the peers' digits have arrived), then the others; sums over partitions do not depend on the order
+        self.sids = sorted(owners, key=lambda s_: (owners[s_][0] != dev, s_))
         self.owners = owners
         if max(o[2] for o in owners.values()) > MAX_ALPHA:
             # (num_special_primes > 8 makes partitions of more than 8 limbs: the kernels would silently drop digits)
@@ -227,7 +229,7 @@ def digits_stage(plan, a, galois=0):
         check(lib.ckks_exec_digits(plan.ref, _p(a), a.stride(0), _p(plan.digits), plan.N, int(galois), _stream(a)), "exec_digits")
 
 
-def keyswitch_stage(plan, digit_ptrs, k0p, k1p, kstride, permuted, add0, add1, out0, out1, add0_galois=0, phase=3):
+def keyswitch_stage(plan, digit_ptrs, k0p, k1p, kstride, permuted, add0, add1, out0, out1, add0_galois=0, phase=3, parts=(-1, -1)):
     """add0_galois != 0: the addend of output 0 is the Galois image of add0, gathered inside the ModDown kernel.
     phase 1: extend + NTT only (k*/add*/out* may be None); phase 2: inner product + tail on the block phase 1 left behind"""
     add = add0 if add0 is not None else add1
@@ -235,5 +237,6 @@ def keyswitch_stage(plan, digit_ptrs, k0p, k1p, kstride, permuted, add0, add1, o
     with torch.cuda.device(dev):
         check(lib.ckks_exec_keyswitch_stage(plan.ref, _p(digit_ptrs), plan.N, _p(k0p), _p(k1p), kstride or 0, 1 if permuted else 0,
                                             _p(add0), _p(add1), add.stride(0) if add is not None else 0, int(add0_galois),
-                                            _p(out0), _p(out1), plan.N, _p(plan.ks_ws), int(phase), _stream(plan.x)),
+                                            _p(out0), _p(out1), plan.N, _p(plan.ks_ws), int(phase), int(parts[0]), int(parts[1]),
+                                            _stream(plan.x)),
               "exec_keyswitch_stage")
