@@ -758,6 +758,19 @@ def run_ours(args):
     # ---- N > 1: the distributed result is the single-process result, bit for bit (mult and rotate) -----------
     if world > 1:
         line["n_gt1_bit_exact"] = check_against_single_process(H, PRESET, ct_a, ct_b, evk, prod, rotk, rot)
+        # what the two collectives cost inside the step: the same graph captured with one / both left out (results are then
+        # wrong by construction -- timing only; engine.debug_skip_collectives)
+        comm = {"step_ms": ms}
+        for name, skip in (("no_digit_all_gather_ms", {"gather"}), ("no_rescale_broadcast_ms", {"bcast"}),
+                           ("no_collectives_ms", {"gather", "bcast"})):
+            eng.debug_skip_collectives = skip
+            if use_graph:
+                sstep, _, _g = H.graphed(eng, eng.mult, ct_a, ct_b, evk)
+            else:
+                sstep = lambda: eng.mult(ct_a, ct_b, evk)
+            comm[name], _, _ = timed(sstep, args.steps, args.warmup)
+        eng.debug_skip_collectives = set()
+        line["comm_breakdown"] = comm
 
     # ---- the reference's own CUDA path on the same box ---------------------------------------------------
     if not args.no_reference_cuda:

@@ -189,6 +189,9 @@ class ckks_engine:
         self._key_shadow = {}
         self._gather_stream = None
         self._gather_pending = False
+        # MEASUREMENT ONLY (bench.py's comm_breakdown at N > 1): names of collectives to leave out -- "gather" (ModUp digit
+        # all_gather) / "bcast" (rescale limbs).  Results are then wrong by construction; timing shows what each one costs.
+        self.debug_skip_collectives = set()
 
         P = math.prod(c.q[-K:])
         self.mont_PR = [self._t([P * c.R % c.q[i] for i in p.destination_arrays[0][dev]], dev) if self._local(dev) else None
@@ -305,7 +308,8 @@ class ckks_engine:
             self._gather_stream = torch.cuda.Stream()
         self._gather_stream.wait_stream(main)
         with torch.cuda.stream(self._gather_stream):
-            self.comm.dist.all_gather_into_tensor(gathered.view(-1, N), mine, group=self.comm.group)
+            if "gather" not in self.debug_skip_collectives:
+                self.comm.dist.all_gather_into_tensor(gathered.view(-1, N), mine, group=self.comm.group)
         self._gather_pending = True
         if plan is None:
             return {}
@@ -813,7 +817,11 @@ class ckks_engine:
         else:
             # ONE broadcast of the four dropped limbs, packed
             packed = torch.stack([poly[src][0] for poly in polys]) if self._local(src) else None
-            got = self.comm.bcast(packed, src, range(n_before), shape=(4, self.ctx.N))
+            if "bcast" in self.debug_skip_collectives:
+                z = packed if packed is not None else torch.zeros((4, self.ctx.N), dtype=torch.int64, device=self.ntt.devices[self.local_ids[0]])
+                got = {d: z for d in self.local_ids}
+            else:
+                got = self.comm.bcast(packed, src, range(n_before), shape=(4, self.ctx.N))
             r0 = [{d: t[i] for d, t in got.items()} for i in range(4)]
         plans = {d: self._plan(nxt, d) for d in range(n_after) if self._local(d)}
         for d, plan in plans.items():
