@@ -35,7 +35,9 @@ int ckks_abi_version(void);                 /* 3; the Python loader refuses any 
  *   10 = internal side streams (2; 1..4);  11 = MB per row slab of a big batched transform (24);
  *   12 = rescale fused into the tensor stage's column pass (1);  16 = the two ModDown tails on two streams (1);
  *   17 = block passes read the last-group twiddles from the packed tables (1);
- *   18 = the executor keeps NTT-domain data in warp-interleaved order (1; needs permuted key copies, ckks_perm_rows).
+ *   18 = the executor keeps NTT-domain data in warp-interleaved order (1; needs permuted key copies, ckks_perm_rows);
+ *   19 = hot-path kernels launched with programmatic stream serialization (1): the next grid ramps up under the tail of
+ *        the previous one; every such kernel waits (griddepcontrol.wait) before its first global access.
  * Unknown keys return CKKS_E_BADARG.  The library is single-threaded per device (one host thread per device issues calls). */
 int ckks_set_option(int key, int value);
 int ckks_get_option(int key);               /* current value of a knob (negative: unknown key) */

@@ -20,6 +20,23 @@ constexpr int EW_THREADS = 256;
 inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 long long g_launches = 0;   // kernels launched by this library since load (ckks_launch_count)
 inline int launch_status() { ++g_launches; return (int)cudaGetLastError(); }
+int g_pdl = 1;   // ckks_set_option(19, v): hot-path kernels are launched with programmatic stream serialization (pdl_enter())
+template <class... KArgs, class... Args>
+inline int launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = g_pdl ? 1 : 0;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+    ++g_launches;
+    return (int)(e != cudaSuccess ? e : cudaGetLastError());
+}
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 inline bool row_ok(const void* p, long long stride) { return aligned16(p) && (stride % 2 == 0); }
 
@@ -159,6 +176,7 @@ __global__ void k_rescale(const int64_t* __restrict__ in, long long is, const in
 __global__ void k_tensor(const int64_t* __restrict__ x0, const int64_t* __restrict__ x1, const int64_t* __restrict__ y0,
                          const int64_t* __restrict__ y1, long long is, int64_t* __restrict__ d0,
                          int64_t* __restrict__ d1, int64_t* __restrict__ d2, long long os, int N, MontPack m) {
+    pdl_enter();
     const int i = blockIdx.y;
     const int j = 2 * (blockIdx.x * EW_THREADS + threadIdx.x);
     if (j >= N) return;
@@ -290,6 +308,7 @@ __global__ void k_ksk_acc(const int64_t* __restrict__ ext, long long es, const i
 // eff[i][j] = value of special row E-1-i at the moment step i reads it.  One thread per coefficient.
 __global__ void k_moddown_special(const int64_t* __restrict__ d, long long ds, int L, int K, int N,
                                   const int64_t* __restrict__ PiR, int64_t* __restrict__ eff, MontPack m) {
+    pdl_enter();
     const int j = blockIdx.x * EW_THREADS + threadIdx.x;
     if (j >= N) return;
     const int E = L + K;
@@ -330,6 +349,7 @@ __global__ void k_moddown_ordinary(const int64_t* __restrict__ d, long long ds, 
                                    const int64_t* __restrict__ Rs, const int64_t* __restrict__ PiR,
                                    const int64_t* __restrict__ eff, const int64_t* __restrict__ add, long long adds,
                                    int64_t* __restrict__ out, long long os, int row0, MontPack m, unsigned add_ginv) {
+    pdl_enter();
     const int t = row0 + blockIdx.y;
     const int j = 2 * (blockIdx.x * EW_THREADS + threadIdx.x);
     if (j >= N) return;
@@ -383,6 +403,7 @@ __global__ void k_garner_batched(const int64_t* __restrict__ a, long long as, in
                                  const int32_t* __restrict__ row0, const int32_t* __restrict__ alphas,
                                  const int64_t* const* __restrict__ Yp, const int64_t* const* __restrict__ Lp, MontPack m,
                                  unsigned ginv, const int64_t* __restrict__ q_rows) {
+    pdl_enter();
     const int p = blockIdx.y;
     const int j = blockIdx.x * EW_THREADS + threadIdx.x;
     if (j >= N) return;
@@ -494,12 +515,11 @@ template <int B>
 static int launch_fast_col_b(bool fwd, const FastArgs& F, dim3 grid, cudaStream_t st) {
     if (fwd) {
         cudaFuncSetAttribute(fast_fwd_colpass<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, COL_SMEM_BYTES);
-        fast_fwd_colpass<B><<<grid, NTT_THREADS, COL_SMEM_BYTES, st>>>(F);
+        return launch_k(fast_fwd_colpass<B>, grid, dim3(NTT_THREADS), COL_SMEM_BYTES, st, F);
     } else {
         cudaFuncSetAttribute(fast_inv_colpass<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, COL_SMEM_BYTES);
-        fast_inv_colpass<B><<<grid, NTT_THREADS, COL_SMEM_BYTES, st>>>(F);
+        return launch_k(fast_inv_colpass<B>, grid, dim3(NTT_THREADS), COL_SMEM_BYTES, st, F);
     }
-    return launch_status();
 }
 static int launch_fast_col(bool fwd, const FastArgs& F, dim3 grid, cudaStream_t st) {
     switch (F.logN - 8) {
@@ -515,8 +535,7 @@ static int launch_fast_col(bool fwd, const FastArgs& F, dim3 grid, cudaStream_t 
 template <int B>
 static int launch_col_rescale_b(const FastArgs& F, const RescaleIn& R, dim3 grid, cudaStream_t st) {
     cudaFuncSetAttribute(fast_fwd_colpass_rescale<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, COL_SMEM_BYTES);
-    fast_fwd_colpass_rescale<B><<<grid, NTT_THREADS, COL_SMEM_BYTES, st>>>(F, R);
-    return launch_status();
+    return launch_k(fast_fwd_colpass_rescale<B>, grid, dim3(NTT_THREADS), COL_SMEM_BYTES, st, F, R);
 }
 static int launch_col_rescale(const FastArgs& F, const RescaleIn& R, dim3 grid, cudaStream_t st) {
     switch (F.logN - 8) {
@@ -534,12 +553,11 @@ static int launch_fast_block(bool fwd, const FastArgs& F, dim3 grid, cudaStream_
     if (!aligned32(F.a, F.a_stride)) return CKKS_E_ALIGN;   // 256-bit accesses: rows must be 32-byte aligned
     if (fwd) {
         cudaFuncSetAttribute(fast_fwd_blockpass<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, BLK_SMEM_BYTES);
-        fast_fwd_blockpass<B><<<grid, NTT_THREADS, BLK_SMEM_BYTES, st>>>(F);
+        return launch_k(fast_fwd_blockpass<B>, grid, dim3(NTT_THREADS), BLK_SMEM_BYTES, st, F);
     } else {
         cudaFuncSetAttribute(fast_inv_blockpass<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, BLK_SMEM_BYTES);
-        fast_inv_blockpass<B><<<grid, NTT_THREADS, BLK_SMEM_BYTES, st>>>(F);
+        return launch_k(fast_inv_blockpass<B>, grid, dim3(NTT_THREADS), BLK_SMEM_BYTES, st, F);
     }
-    return launch_status();
 }
 static int launch_fast_block_any(bool fwd, FastArgs F, dim3 grid, cudaStream_t st) {
     if (!g_packed) { F.twp_u64 = nullptr; F.twp_f64 = nullptr; }
@@ -709,6 +727,7 @@ static int* option_slot(int key) {
         case 16: return &g_split_tail;
         case 17: return &g_packed;
         case 18: return &g_perm;
+        case 19: return &g_pdl;
     }
     return nullptr;
 }
@@ -1009,10 +1028,10 @@ int ckks_exec_digits(const ckks_level_t* lv, const int64_t* a, int64_t as, int64
     if (lv->amax > MAX_ALPHA) return CKKS_E_BADARG;   // k_garner_batched keeps at most MAX_ALPHA digits per partition
     const int N = 1 << lv->logN;
     if (galois && (!(galois & 1) || galois < 0 || galois >= 2ll * N || a == digits)) return CKKS_E_BADARG;
-    k_garner_batched<<<dim3((N + EW_THREADS - 1) / EW_THREADS, lv->nlocal), EW_THREADS, 0, S(stream)>>>(
-        a, as, digits, ds, N, lv->loc_row0, lv->loc_alpha, lv->loc_Y, lv->loc_Ltri,
-        MontPack{nullptr, lv->ql, lv->qh, lv->kl, lv->kh}, galois ? galois_inverse((unsigned)galois, (unsigned)N) : 0u, lv->q);
-    return launch_status();
+    return launch_k(k_garner_batched, dim3((N + EW_THREADS - 1) / EW_THREADS, lv->nlocal), dim3(EW_THREADS), 0, S(stream),
+                    a, as, digits, ds, N, lv->loc_row0, lv->loc_alpha, lv->loc_Y, lv->loc_Ltri,
+                    MontPack{nullptr, lv->ql, lv->qh, lv->kl, lv->kh}, galois ? galois_inverse((unsigned)galois, (unsigned)N) : 0u,
+                    lv->q);
 }
 
 static FastArgs level_fast(const ckks_level_t* lv, int64_t* a, long long as, bool fwd, const int64_t* scal, const int64_t* scal_sh,
@@ -1060,9 +1079,8 @@ int ckks_exec_tensor_stage(const ckks_level_t* lv, const int64_t* a0, const int6
         F.perm = perm;
         RC(fast_transform(true, F, 4 * L, st));
     }
-    k_tensor<<<ew_grid(N, L), EW_THREADS, 0, st>>>(x, x + LN, x + 2 * LN, x + 3 * LN, N, d, d + LN, d + 2 * LN, N, N,
-                                                   MontPack{lv->_2q, lv->ql, lv->qh, lv->kl, lv->kh});
-    RC(launch_status());
+    RC(launch_k(k_tensor, ew_grid(N, L), dim3(EW_THREADS), 0, st, x, x + LN, x + 2 * LN, x + 3 * LN, N, d, d + LN, d + 2 * LN, N, N,
+                MontPack{lv->_2q, lv->ql, lv->qh, lv->kl, lv->kh}));
     FastArgs Fi = level_fast(lv, d, N, false, lv->sExit, lv->sExit_sh, L);
     Fi.perm = perm;
     RC(fast_transform(false, Fi, 3 * L, st));
@@ -1134,10 +1152,9 @@ int ckks_exec_keyswitch_stage(const ckks_level_t* lv, const int64_t* const* digi
             const int t1 = (t0 + slab < E) ? t0 + slab : E;
             if (do_fwd) {
                 const dim3 eg((N / 2 + 255) / 256, Pr);
-                if (lv->amax <= 2) k_extend_fast<2><<<eg, 256, 0, st>>>(X, t0, t1);
-                else if (lv->amax <= 4) k_extend_fast<4><<<eg, 256, 0, st>>>(X, t0, t1);
-                else k_extend_fast<8><<<eg, 256, 0, st>>>(X, t0, t1);
-                RC(launch_status());
+                if (lv->amax <= 2) RC(launch_k(k_extend_fast<2>, eg, dim3(256), 0, st, X, t0, t1));
+                else if (lv->amax <= 4) RC(launch_k(k_extend_fast<4>, eg, dim3(256), 0, st, X, t0, t1));
+                else RC(launch_k(k_extend_fast<8>, eg, dim3(256), 0, st, X, t0, t1));
                 FastArgs F = level_fast(lv, ext + (long long)pb * E * N, N, true, nullptr, nullptr, E);
                 F.slab_rows = t1 - t0; F.group_rows = E; F.slab_t0 = t0;
                 F.in_raw = 1; F.out_raw = 1;
@@ -1152,8 +1169,7 @@ int ckks_exec_keyswitch_stage(const ckks_level_t* lv, const int64_t* const* digi
             I.acc0 = acc; I.acc1 = acc + (long long)E * N;
             I.q = lv->q; I._2q = lv->_2q; I.ql = lv->ql; I.qh = lv->qh; I.kl = lv->kl; I.kh = lv->kh;
             I.P = P; I.E = E; I.N = N; I.t0 = t0; I.raw = 1; I.qinv = lv->qinv;
-            k_ksk_inner_fast<<<dim3((N / 2 + 255) / 256, t1 - t0), 256, 0, st>>>(I);
-            RC(launch_status());
+            RC(launch_k(k_ksk_inner_fast, dim3((N / 2 + 255) / 256, t1 - t0), dim3(256), 0, st, I));
         }
         RC(scope.join());
     } else {
@@ -1190,18 +1206,15 @@ int ckks_exec_keyswitch_stage(const ckks_level_t* lv, const int64_t* const* digi
             Fi.perm = perm;
             RC(fast_transform(false, Fi, tail ? E : 2 * E, st));
         }
-        k_moddown_special<<<col_grid(N), EW_THREADS, 0, st>>>(dh, N, L, K, N, lv->PiR, effh, m);
-        RC(launch_status());
+        RC(launch_k(k_moddown_special, col_grid(N), dim3(EW_THREADS), 0, st, dh, N, L, K, N, lv->PiR, effh, m));
         if (Ls > 0) {
             ModDownArgs M{dh, effh, adds[h], add_stride, outs[h], out_stride, lv->Pinv, lv->C31, lv->q, L, K, E, N, lv->qinv,
                           add_ginv[h]};
-            k_moddown_fast<<<dim3((N / 2 + 255) / 256, Ls), 256, 0, st>>>(M);
-            RC(launch_status());
+            RC(launch_k(k_moddown_fast, dim3((N / 2 + 255) / 256, Ls), dim3(256), 0, st, M));
         }
         if (Ls < L) {
-            k_moddown_ordinary<<<ew_grid(N, L - Ls), EW_THREADS, 0, st>>>(dh, N, L, K, N, lv->Rs, lv->PiR, effh, adds[h],
-                                                                        add_stride, outs[h], out_stride, Ls, m, add_ginv[h]);
-            RC(launch_status());
+            RC(launch_k(k_moddown_ordinary, ew_grid(N, L - Ls), dim3(EW_THREADS), 0, st, dh, N, L, K, N, lv->Rs, lv->PiR, effh,
+                        adds[h], add_stride, outs[h], out_stride, Ls, m, add_ginv[h]));
         }
     }
     RC(tscope.join());

@@ -18,6 +18,17 @@
 
 namespace ckks {
 
+// Programmatic dependent launch (sm_90+): a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may be
+// scheduled while its predecessor in the stream is still draining.  Every hot-path kernel starts with pdl_enter():
+// "my dependents may be scheduled as soon as all my CTAs have started", then "wait until everything before me in the
+// stream has completed and is visible" -- before ANY global access, so there is no RAW or WAR hazard; what is gained is the
+// launch latency and the ramp-up of the next grid under the tail of this one.  No-ops for ordinary launches.
+__device__ __forceinline__ void pdl_enter() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+
 constexpr uint64_t MASK62 = (1ull << 62) - 1;
 
 struct LimbConst {

@@ -660,6 +660,7 @@ __device__ __forceinline__ void fast_fwd_col_body(const FastArgs& F, const Resca
 
 template <int B>
 __global__ void __launch_bounds__(NTT_THREADS, FAST_COL_CTAS) fast_fwd_colpass(const FastArgs F) {
+    pdl_enter();
     extern __shared__ __align__(16) int64_t sm[];
     const RowId rid = fast_row(F);
     const int limb = rid.limb;
@@ -673,6 +674,7 @@ __global__ void __launch_bounds__(NTT_THREADS, FAST_COL_CTAS) fast_fwd_colpass(c
 // the tensor stage's column pass: rescale fused into the load (rows = 4 polynomials x L limbs, period L, F.scal = R mod q)
 template <int B>
 __global__ void __launch_bounds__(NTT_THREADS, FAST_COL_CTAS) fast_fwd_colpass_rescale(const FastArgs F, const RescaleIn R) {
+    pdl_enter();
     extern __shared__ __align__(16) int64_t sm[];
     const RowId rid = fast_row(F);
     const int limb = rid.limb;
@@ -767,6 +769,7 @@ __device__ __forceinline__ void ext_target(const ExtArgs& X, const ExtShared& S,
 // AMAX = capacity of the per-thread digit arrays (>= alpha, and >= 2 for the 31-bit split of a wide digit)
 template <int AMAX>
 __global__ void __launch_bounds__(256) k_extend_fast(const ExtArgs X, int t0, int t1) {
+    pdl_enter();
     __shared__ ExtShared S;
     const int p = blockIdx.y;
     const int alpha = X.alphas[p];
@@ -828,6 +831,7 @@ struct InnerArgs {
 };
 
 __global__ void __launch_bounds__(256) k_ksk_inner_fast(const InnerArgs X) {
+    pdl_enter();
     const int t = X.t0 + blockIdx.y;
     const long long j = 2ll * (blockIdx.x * 256 + threadIdx.x);
     if (j >= X.N) return;
@@ -895,6 +899,7 @@ struct ModDownArgs {
 };
 
 __global__ void __launch_bounds__(256) k_moddown_fast(const ModDownArgs X) {
+    pdl_enter();
     const int t = blockIdx.y;
     const long long j = 2ll * (blockIdx.x * 256 + threadIdx.x);
     if (j >= X.N) return;
@@ -1074,6 +1079,7 @@ __device__ __forceinline__ void fast_fwd_block_body(const FastArgs& F, int64_t* 
 
 template <int B>
 __global__ void __launch_bounds__(NTT_THREADS, FAST_BLK_CTAS) fast_fwd_blockpass(const FastArgs F) {
+    pdl_enter();
     extern __shared__ __align__(16) int64_t sm[];
     const RowId rid = fast_row(F);
     if (fast_use_f64(F, rid))
@@ -1142,6 +1148,7 @@ __device__ __forceinline__ void fast_inv_block_body(const FastArgs& F, int64_t* 
 
 template <int B>
 __global__ void __launch_bounds__(NTT_THREADS, FAST_BLK_CTAS) fast_inv_blockpass(const FastArgs F) {
+    pdl_enter();
     extern __shared__ __align__(16) int64_t sm[];
     const RowId rid = fast_row(F);
     if (fast_use_f64(F, rid))
@@ -1199,6 +1206,7 @@ __device__ __forceinline__ void fast_inv_col_body(const FastArgs& F, int64_t* sm
 
 template <int B>
 __global__ void __launch_bounds__(NTT_THREADS, FAST_COL_CTAS) fast_inv_colpass(const FastArgs F) {
+    pdl_enter();
     extern __shared__ __align__(16) int64_t sm[];
     const RowId rid = fast_row(F);
     const int limb = rid.limb;
