@@ -422,7 +422,9 @@ struct FastArgs {
 #define LAB_SKIP_MEM(F) false
 #endif
 
-__device__ __forceinline__ int grid_row(const FastArgs& F) { return blockIdx.y; }
+// rows are dispatched LAST ROW FIRST: the 60-bit limbs (base + special primes, the last rows of every period / slab group) take
+// ~2.3x the instructions of an FP64 row, so they should not be what the final wave of a launch consists of
+__device__ __forceinline__ int grid_row(const FastArgs& F) { return (int)gridDim.y - 1 - (int)blockIdx.y; }
 __device__ __forceinline__ unsigned grid_chunk(const FastArgs& F) { return blockIdx.x; }
 
 struct RowId {
@@ -431,8 +433,8 @@ struct RowId {
 };
 // the tile that a CTA dispatched about `ahead` rows x (chunks per row) tiles later will load: data row (or -1) and chunk
 __device__ __forceinline__ long long fast_row_ahead(const FastArgs& F, int ahead, unsigned& chunk) {
-    const int r = blockIdx.y + ahead;
-    if (r >= (int)gridDim.y) return -1;
+    const int r = grid_row(F) - ahead;
+    if (r < 0) return -1;
     chunk = blockIdx.x;
     if (F.slab_rows == 0) return r;
     const int g = r / F.slab_rows, m = r - g * F.slab_rows;
