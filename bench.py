@@ -773,10 +773,13 @@ def run_ours(args):
         line["comm_breakdown"] = comm
 
     # ---- the reference's own CUDA path on the same box ---------------------------------------------------
+    # N > 1: rank 0 drives the reference's own multi-GPU mode (one process, devices=[0..N-1]); the other ranks must leave
+    # their GPUs alone meanwhile, so they wait on the rendezvous store (host side), not in an NCCL barrier (a spinning kernel)
     if not args.no_reference_cuda:
         torch.cuda.synchronize()
         if dist is not None:
             dist.barrier()
+            torch.cuda.synchronize()
         if rank == 0:
             try:
                 if world == 1:
@@ -787,6 +790,12 @@ def run_ours(args):
             except Exception as e:
                 line["reference_cuda"] = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
         if dist is not None:
+            store = dist.distributed_c10d._get_default_store()
+            if rank == 0:
+                store.set("bench_reference_cuda_done", "1")
+            else:
+                import datetime
+                store.wait(["bench_reference_cuda_done"], datetime.timedelta(seconds=600))
             torch.cuda.synchronize()
             dist.barrier()
 
