@@ -4,25 +4,26 @@ sm_100a kernels.  Method names, arguments, data_struct states/origins and error 
 reference so that user code runs unchanged; file:line citations below are to the reference.
 
 What is B200-native here (the mult / rotate hot path):
-  * rescale                 one fused kernel per polynomial            (ref: ~8 torch ops + 2 launches, :967-1052)
-  * enter_ntt / intt_exit_reduce   two kernels per batched transform   (ref: logN+1 .. logN+3 launches)
-  * tensor product          one kernel for d0,d1,d2                    (ref: 4 mont_mult + mont_add, :1095-1101)
-  * key switch (create_switcher, :746-904):
-        Garner digits       one kernel per partition                   (ref: ~5 tiny launches x (alpha-1), :654-705)
-        extend              one kernel per partition                   (ref: repeat + 2 launches x alpha, :707-743)
-        evk inner product   one kernel per partition, running sum      (ref: 2 mont_mult + 2 mont_add)
-        ModDown             two kernels per polynomial incl. the final add+reduce (ref: ~12 launches x K, :851-901)
-        digit exchange      direct GPU->GPU / one NCCL all_gather      (ref: via pinned host memory, :778-810)
-  * rotate                  one automorphism kernel (+ canonicalise)   (ref: scatter through a transposed view)
-Every kernel evaluates the reference's per-element integer expressions, so keys, ciphertexts and even the
-lazy [0,2q) representatives are bit-identical (tests/test_gpu_engine.py against tests/golden).
+  * mult (cc_mult + relinearize, :1072-1151)   two C calls = 24 kernel launches through the executor (fhe/executor.py):
+        rescale fused into the batched NTT's load, tensor product, batched iNTT, Garner digits, then per slab
+        extend -> NTT -> evk inner product on internal streams, and iNTT -> ModDown per output polynomial
+        (reference: ~600 launches, two host-staged exchanges)
+  * rotate_single (:1180-1214)                 the same key-switch stage; the Galois map is applied by the kernels that
+        read the ciphertext (no rotated copy in HBM); rotate_hoisted shares one ModUp among many rotations
+  * rescale / cc_add / cc_sub / level_up       one fused kernel per polynomial
+  * digit exchange / rescale limb              one NCCL all_gather (overlapped with the rank's own partitions) / one broadcast
+        (reference: via pinned host memory, :778-810, :999-1011)
+  * cpu / cuda / save / load                   the reference's wire format (:1790-1906, :2001-2029)
+Everything else (keys, encrypt, decrypt, scalar and plaintext operands) runs operator by operator on the level-1
+kernels, which evaluate the reference's per-element integer expressions: keys, ciphertexts and even the lazy [0,2q)
+representatives are bit-identical (tests/test_gpu_engine.py against tests/golden, tests/test_gpu_vs_reference_engine.py).
 
 Devices: ``devices=[...]`` in one process behaves like the reference (lists of per-device tensors).  Under
 torch.distributed (``distributed=True``) each rank owns logical device ``rank``; lists keep the logical
 indexing and hold ``None`` for devices owned by other ranks.
 
 Not carried over (out of scope): multiparty key generation, the statistics
-helpers built from add/mult/rotate, the ChaCha20 CSPRNG kernels (see liberate_b200.csprng).
+helpers built from add/mult/rotate.
 """
 import math
 import pickle
@@ -209,22 +210,10 @@ class ckks_engine:
         return hit[1]
 
     def _galois_ntt_index(self, g, dev):
-        """P with NTT(pi_g(x))[i] == NTT(x)[P[i]] for the reference's bit-reversed NTT order: slot i evaluates at
-        psi^(2 bitrev(i) + 1), and pi_g: X -> X^g moves that point to its g-th power."""
         key = ("gal_ntt", g, str(dev))
         P = self._ptr_cache.get(key)
         if P is None:
-            logN, N = self.ctx.logN, self.ctx.N
-            i = torch.arange(N, dtype=torch.int64, device=dev)
-
-            def bitrev(x):
-                r = torch.zeros_like(x)
-                for b in range(logN):
-                    r |= ((x >> b) & 1) << (logN - 1 - b)
-                return r
-            e = ((2 * bitrev(i) + 1) * g) % (2 * N)
-            P = bitrev((e - 1) // 2)
-            self._ptr_cache[key] = P
+            P = self._ptr_cache[key] = galois_ntt_index(g, self.ctx.logN, dev)
         return P
 
     def _hoist_key(self, t, g, permuted):
@@ -1352,6 +1341,22 @@ class ckks_engine:
         with open(filename, "rb") as f:
             text = _as(_WireUnpickler(f).load(), data_struct)
         return self.cuda(text) if move_to_gpu else text
+
+
+def galois_ntt_index(g, logN, device="cpu"):
+    """P with NTT(pi_g(x))[i] == NTT(x)[P[i]] for the reference's bit-reversed NTT order: slot i evaluates the polynomial at
+    psi^(2 bitrev(i) + 1), and pi_g: X -> X^g moves that point to its g-th power (tests/test_host_logic.py checks it against
+    the oracle's transform)."""
+    N = 1 << logN
+    i = torch.arange(N, dtype=torch.int64, device=device)
+
+    def bitrev(x):
+        r = torch.zeros_like(x)
+        for b in range(logN):
+            r |= ((x >> b) & 1) << (logN - 1 - b)
+        return r
+    e = ((2 * bitrev(i) + 1) * g) % (2 * N)
+    return bitrev((e - 1) // 2)
 
 
 # ---------------------------------------------------------------------------------------------------

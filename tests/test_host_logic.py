@@ -86,3 +86,34 @@ def test_base_prime_is_a_partition_of_its_own_and_scale_tables_straddle_2_42_onl
         else:
             assert 0 < n_wide < len(primes), key
     assert all(q >= (1 << 42) for per_n in t["message_special_primes"]["60"].values() for q in per_n)
+
+
+def test_ntt_domain_galois_permutation_matches_the_oracle_transform():
+    """engine.rotate_hoisted moves rotation keys to their NTT-domain pre-image with galois_ntt_index: NTT(pi_g(x))[i] ==
+    NTT(x)[P[i]].  Checked against the oracle's forward transform (kern.cu:236-275 restated) and a schoolbook Galois map."""
+    import numpy as np
+    from conftest import primes_for
+    from liberate_b200.fhe.ckks_engine import galois_ntt_index
+    from oracle import oracle as O
+    logN = 12
+    N = 1 << logN
+    P = O.Params(primes_for(logN, 1, 1), logN)
+    q = np.array(P.q, dtype=np.int64)
+    rng = np.random.default_rng(3)
+    x = rng.integers(0, q[:, None], (len(q), N), dtype=np.int64)
+
+    def ntt(a):
+        a = a.copy()
+        O.C.ntt(a, P.psi, P._2q, *P.mont)
+        O.C.reduce_2q(a, P._2q)
+        return a
+    A = ntt(x)
+    for g in (3, pow(3, 5, 2 * N), 2 * N - 1, pow(3, -7, 2 * N)):
+        j = np.arange(N)
+        t = (g * j) % (2 * N)
+        moved = np.zeros_like(x)
+        moved[:, t % N] = np.where(t < N, x, (-x) % q[:, None])
+        idx = galois_ntt_index(g, logN).numpy()
+        assert (ntt(moved) == A[:, idx]).all(), g
+        inv = galois_ntt_index(pow(g, -1, 2 * N), logN).numpy()
+        assert (idx[inv] == j).all()
