@@ -779,33 +779,6 @@ def run_ours(args):
         eng.debug_skip_collectives = set()
         line["comm_breakdown"] = comm
 
-    # ---- the reference's own CUDA path on the same box ---------------------------------------------------
-    # N > 1: rank 0 drives the reference's own multi-GPU mode (one process, devices=[0..N-1]); the other ranks must leave
-    # their GPUs alone meanwhile, so they wait on the rendezvous store (host side), not in an NCCL barrier (a spinning kernel)
-    if not args.no_reference_cuda:
-        torch.cuda.synchronize()
-        if dist is not None:
-            dist.barrier()
-            torch.cuda.synchronize()
-        if rank == 0:
-            try:
-                if world == 1:
-                    line["reference_cuda"] = reference_cuda_leg(torch, np, [local_rank], args.steps, args.warmup,
-                                                                shared=(sk, evk, ct_a, ct_b, ma * mb, prod))
-                else:   # the reference's own multi-GPU mode: one process, devices=[0..N-1] (engine.py:56-60)
-                    line["reference_cuda"] = reference_cuda_leg(torch, np, list(range(world)), args.steps, args.warmup)
-            except Exception as e:
-                line["reference_cuda"] = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
-        if dist is not None:
-            store = dist.distributed_c10d._get_default_store()
-            if rank == 0:
-                store.set("bench_reference_cuda_done", "1")
-            else:
-                import datetime
-                store.wait(["bench_reference_cuda_done"], datetime.timedelta(seconds=600))
-            torch.cuda.synchronize()
-            dist.barrier()
-
     if rank == 0 and world == 1 and not args.no_sweep:
         line["ntt_sweep"] = {"unit": "GB/s of algorithmic traffic (16 B/coefficient)", "peak": peak,
                              "rows": ntt_sweep(H, peak)}
@@ -818,6 +791,47 @@ def run_ours(args):
             line["platinum_depth10"] = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(eng, ct_a, ct_b, evk, prod)
+    # ---- the reference's own CUDA path on the same box (LAST: whatever it does to the process cannot cost the line) -------
+    # N = 1: in this process, on OUR keys and ciphertexts, output compared bit for bit.  N > 1: rank 0 runs the reference's own
+    # multi-GPU mode (one process, devices=[0..N-1], engine.py:56-60) in a CHILD process -- its CUDA context is isolated from
+    # ours (an illegal access inside the reference's kernels at 8 devices took rank 0 down with it when it ran in-process) --
+    # while the other ranks leave their GPUs alone: they wait on the rendezvous store (host side), not in an NCCL barrier.
+    if not args.no_reference_cuda:
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+        if rank == 0:
+            try:
+                if world == 1:
+                    line["reference_cuda"] = reference_cuda_leg(torch, np, [local_rank], args.steps, args.warmup,
+                                                                shared=(sk, evk, ct_a, ct_b, ma * mb, prod))
+                else:
+                    env = {k: v for k, v in os.environ.items()
+                           if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT", "OMP_NUM_THREADS",
+                                        "TORCHELASTIC_RUN_ID", "GROUP_RANK", "ROLE_RANK", "LOCAL_WORLD_SIZE", "ROLE_WORLD_SIZE")}
+                    out = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference_gpu", "--gpus", str(world),
+                                          "--steps", str(args.steps), "--warmup", str(args.warmup)],
+                                         capture_output=True, text=True, timeout=420, env=env, cwd=str(ROOT))
+                    rows = [x for x in out.stdout.splitlines() if x.startswith("{")]
+                    if out.returncode == 0 and rows:
+                        got = json.loads(rows[-1])
+                        line["reference_cuda"] = {k: v for k, v in got.items() if k not in ("impl", "metric", "config", "data", "dtype")}
+                    else:
+                        tail = (out.stderr or out.stdout).strip().splitlines()
+                        why = next((x for x in reversed(tail) if "Error" in x or "error" in x), tail[-1] if tail else "no output")
+                        line["reference_cuda"] = {"unavailable": f"the reference's own {world}-device mode failed on this box "
+                                                                 f"(exit {out.returncode}): {why.strip()[:240]}"}
+            except Exception as e:
+                line["reference_cuda"] = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
+        if dist is not None:
+            store = dist.distributed_c10d._get_default_store()
+            if rank == 0:
+                store.set("bench_reference_cuda_done", "1")
+            else:
+                import datetime
+                store.wait(["bench_reference_cuda_done"], datetime.timedelta(seconds=600))
+
     if rank == 0:
         print(json.dumps(line), flush=True)
     H.finish(hard_exit=graph is not None)

@@ -1,7 +1,11 @@
 """Kernel lab: times the fast forward / inverse transforms (whole call, column pass alone, block pass alone) for a
 list of option sets on the key-switch shape ([parts*E rows, N], constants with period E) and checks that every
 option set produces the same bits as the default kernels.
-    python scripts/ntt_lab.py [--logN 16] [--rows 380] [--period 38] [--opts "3=1;3=1,2=0"]"""
+    python liberate-fhe_b200/csrc/build.py --lab          # libckks_b200_lab.so: adds the measurement knobs 5 and 21
+    CKKS_B200_LIB=liberate-fhe_b200/csrc/libckks_b200_lab.so python scripts/ntt_lab.py [--logN 16] [--rows 380] [--period 38]
+                                       [--big 5] [--perm 1] [--opts "2=28;11=400;21=1;21=2"]
+knob 5 = skip the column (1) / block (2) pass, knob 21 = skip the butterflies (1) / the global loads and stores (2); with the
+product library the per-pass columns are NaN and those knobs are refused."""
 import argparse
 import json
 import sys
