@@ -335,9 +335,9 @@ class Harness:
             eng = fhe.ckks_engine(devices=[f"cuda:{self.local_rank}"] * self.world, distributed=True, **params)
         else:
             eng = fhe.ckks_engine(devices=[self.local_rank], **params)
-        # identical sampler state on every rank so that the replicated channels agree
+        # identical sampler state (key AND nonce) on every rank so that the replicated channels agree
         eng.rng = Csprng(eng.ctx.N, [len(d) for d in eng.ntt.p.d], max(eng.ntt.num_special_primes, 2),
-                         devices=eng.ntt.devices, local_ids=eng.local_ids, seed=seed)
+                         devices=eng.ntt.devices, local_ids=eng.local_ids, seed=seed, nonce=seed ^ 0x5DEECE66D)
         return eng
 
     def barrier(self):
@@ -767,6 +767,7 @@ def run_ours(args):
         line["n_gt1_bit_exact"] = check_against_single_process(H, PRESET, ct_a, ct_b, evk, prod, rotk, rot)
         # what the two collectives cost inside the step: the same graph captured with one / both left out (results are then
         # wrong by construction -- timing only; engine.debug_skip_collectives)
+        line["deep_chain"] = deep_chain_check(H, eng, sk, pk, evk, np)
         comm = {"step_ms": ms}
         for name, skip in (("no_digit_all_gather_ms", {"gather"}), ("no_rescale_broadcast_ms", {"bcast"}),
                            ("no_collectives_ms", {"gather", "bcast"})):
@@ -837,6 +838,31 @@ def run_ours(args):
     H.finish(hard_exit=graph is not None)
 
 
+def deep_chain_check(H, eng, sk, pk, evk, np):
+    """N > 1: x <- (x + x) * c down the levels until every rank's device has been the source of a rescale broadcast
+    (K * N + 1 levels), then decrypt on rank 0.  The bit-for-bit comparison above cannot see ranks that disagree on shared
+    randomness (decryption reads device 0's limbs only, and so would the first levels of such a ciphertext); this does."""
+    rs = np.random.default_rng(11)
+    m = rs.uniform(-1, 1, eng.num_slots) + 1j * rs.uniform(-1, 1, eng.num_slots)
+    m /= np.abs(m).max() * 1.5
+    w = 0.5 * np.exp(0.3j)
+    x = eng.encorypt(m, pk)
+    cw = eng.encorypt(np.full(eng.num_slots, w), pk)
+    depth = min(eng.num_levels - 1, eng.ntt.num_special_primes * H.world + 1)
+    sources = set()
+    v = m
+    for _ in range(depth):
+        sources.add(eng.ntt.p.rescaler_loc[x.level])
+        x = eng.mult(eng.add(x, x), cw, evk)
+        v = 2 * v * w
+    out = eng.decrode(x, sk)
+    res = {"depth": depth, "rescale_sources": sorted(sources)}
+    if H.rank == 0:
+        res["decrypt_error"] = float(np.abs(out - v).max())
+        res["decrypt_ok"] = bool(res["decrypt_error"] < 1e-5)
+    return res
+
+
 def platinum_depth10(H, np):
     """BASELINE config 5: platinum preset (logN=17, 73 + 6 limbs), depth-10 chain of (add, mult, rotate) from level 0,
     end-to-end HE ops/s over all ranks; the first (add, mult, rotate) is checked against the single-process engine when
@@ -887,8 +913,7 @@ def platinum_depth10(H, np):
         want = plain(m)
         res["decrypt_error"] = float(np.abs(eng.decrode(out, sk) - want).max())
         res["plain_absmax"] = float(np.abs(want).max())
-    if H.rank == 0:
-        assert res["decrypt_error"] < 1e-5, f"platinum circuit does not decrypt: {res['decrypt_error']}"
+        res["decrypt_ok"] = bool(res["decrypt_error"] < 1e-5)      # (reported, not asserted: the ranks stay in lockstep)
     if H.world > 1:
         y = eng.add(ct, ct)
         first = eng.mult(y, ct, evk)

@@ -121,7 +121,9 @@ class Csprng:
     def refresh(self, seed=None, nonce=None):
         """new key / nonce (os.urandom unless given) and all block counters back to their start"""
         self.key = _words(seed, 8, "seed")
-        self.nonce = _words(nonce, 2, "nonce")
+        # a caller-supplied seed without a nonce gives a reproducible stream (zero nonce), not a half-random one: one
+        # process per GPU, the ranks must agree on BOTH words or their repeated channels differ
+        self.nonce = _words(0 if (nonce is None and seed is not None) else nonce, 2, "nonce")
         self._kn = (ctypes.c_uint32 * 10)(*(self.key + self.nonce))
         for e in self._epoch.values():
             e.zero_()

@@ -77,16 +77,7 @@ class ckks_engine:
         self.num_levels = self.ntt.num_levels - 1
         self.num_slots = self.ctx.N // 2
         if rng is None:
-            seed = nonce = None
-            if distributed:
-                # one process per GPU: every rank must run the SAME ChaCha20 key and nonce, or the repeated channels
-                # (secret key, shared randomness of the public key) would differ between the ranks
-                box = [None]
-                if self.comm.rank == 0:
-                    from ..csprng import _words
-                    box = [(_words(None, 8, "seed"), _words(None, 2, "nonce"))]
-                self.comm.dist.broadcast_object_list(box, src=0, group=self.comm.group)
-                seed, nonce = box[0]
+            seed, nonce = self._shared_key_material()
             rng = Csprng(self.ctx.N, [len(d) for d in self.ntt.p.d], max(self.ntt.num_special_primes, 2),
                          devices=self.ntt.devices, local_ids=self.local_ids, seed=seed, nonce=nonce)
         self.rng = rng
@@ -1248,7 +1239,21 @@ class ckks_engine:
         return self._dispatch(self.sub_dispatch_dict, a, b)
 
     def refresh(self):
-        self.rng.refresh()
+        self.rng.refresh(*self._shared_key_material())
+
+    def _shared_key_material(self):
+        """(seed, nonce) of the sampler.  One process: os.urandom, as the reference (csprng.py:215-223).  One process per GPU:
+        rank 0 draws them and every rank runs the SAME ChaCha20 key and nonce, or the repeated channels (secret key, shared
+        randomness of public keys and encryptions) would differ between the ranks -- such ciphertexts decrypt only as long
+        as device 0's limbs alone are looked at."""
+        if not isinstance(self.comm, DistComm):
+            return None, None
+        box = [None]
+        if self.comm.rank == 0:
+            from ..csprng import _words
+            box = [(_words(None, 8, "seed"), _words(None, 2, "nonce"))]
+        self.comm.dist.broadcast_object_list(box, src=0, group=self.comm.group)
+        return box[0]
 
     def reduce_error(self, ct):
         return self.mult_scalar(ct, 1.0)

@@ -21,6 +21,40 @@ from golden_utils import Checker  # noqa: E402
 from seeded_rng import SeededCsprng  # noqa: E402
 
 
+def own_sampler_chain(fhe, params, rank, world, local):
+    """the engine's OWN sampler (key and nonce broadcast from rank 0, ckks_engine._shared_key_material), before and after
+    refresh(): keys and ciphertexts made by the ranks together must decrypt after a chain that makes every device the
+    source of a rescale.  (Ranks that disagree on the repeated channels produce ciphertexts that still decrypt at the
+    levels where only device 0's limbs are read -- the golden flow, with its injected streams, cannot see that.)"""
+    failures = []
+    eng = fhe.ckks_engine(devices=[f"cuda:{local}"] * world, distributed=True, fast=True, **params)
+    rs = np.random.default_rng(3)
+    m = rs.uniform(-1, 1, eng.num_slots) + 1j * rs.uniform(-1, 1, eng.num_slots)
+    m /= np.abs(m).max() * 1.5
+    w = 0.5 * np.exp(0.3j)
+    for label in ("fresh", "after refresh()"):
+        sk = eng.create_secret_key()
+        pk = eng.create_public_key(sk)
+        evk = eng.create_evk(sk)
+        rotk = eng.create_rotation_key(sk, 1)
+        x = eng.encorypt(m, pk)
+        cw = eng.encorypt(np.full(eng.num_slots, w), pk)
+        v, sources = m, set()
+        while x.level < eng.num_levels - 1:
+            sources.add(eng.ntt.p.rescaler_loc[x.level])
+            x = eng.rotate_single(eng.mult(eng.add(x, x), cw, evk), rotk)
+            v = np.roll(2 * v * w, 1)
+        out = eng.decrode(x, sk)
+        if world > 1 and len(sources) < 2:
+            failures.append(f"[own sampler, {label}] the chain never rescaled from a device other than {sources}")
+        if rank == 0:
+            err = float(np.abs(out - v).max())
+            if not err < 1e-3:
+                failures.append(f"[own sampler, {label}] chain to level {x.level} decrypts with error {err}")
+        eng.refresh()
+    return failures
+
+
 def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
@@ -70,6 +104,7 @@ def main():
                 if mine is not None and not torch.equal(mine, again):
                     failures.append(f"[{mode}] cpu()/cuda() round trip differs on rank {rank}")
             del want
+    failures += own_sampler_chain(fhe, g["params"], rank, world, local)
     ok = torch.tensor([0 if failures else 1], device="cuda")
     dist.all_reduce(ok, op=dist.ReduceOp.MIN)
     if failures:
