@@ -29,7 +29,7 @@ extern "C" {
 #define CKKS_E_LOGN (-2)       /* logN outside [12, 17] */
 #define CKKS_E_ALIGN (-3)      /* pointer or stride not 16-byte aligned */
 
-int ckks_abi_version(void);                 /* 3; the Python loader refuses any other value */
+int ckks_abi_version(void);                 /* 4; the Python loader refuses any other value */
 /* tuning knobs (defaults are the measured best):
  *   2 = L2 prefetch distance in rows (28, 0 = off);  9 = MB of extended rows per key-switch slab (100);
  *   10 = internal side streams (2; 1..4);  11 = MB per row slab of a big batched transform (24);
@@ -124,6 +124,24 @@ int ckks_perm_rows(const int64_t* in, int64_t in_stride, int64_t* out, int64_t o
 int ckks_rescale(const int64_t* in, int64_t in_stride, const int64_t* r0, int64_t* out, int64_t out_stride, int C,
                  int N, const int64_t* scale, int64_t round_at, int canon, const int64_t* _2q, const int64_t* ql,
                  const int64_t* qh, const int64_t* kl, const int64_t* kh, void* stream);
+/* rescale with a per-limb Montgomery scalar folded in before and / or after it, one pass, the integers of the reference's
+ * kernel sequences:  pre  != NULL: in[i] <- reduce_2q(mont(in[i], pre[i])) first  (mult_scalar, engine.py:2052-2098; r0 is
+ * the dropped limb after the same scaling);  post != NULL: out[i] <- reduce_2q(mont(out[i], post[i])) last  (level_up,
+ * engine.py:1410-1467).  Both NULL == ckks_rescale with canon = 0. */
+int ckks_rescale_scaled(const int64_t* in, int64_t in_stride, const int64_t* r0, int64_t* out, int64_t out_stride, int C,
+                        int N, const int64_t* pre, const int64_t* scale, int64_t round_at, const int64_t* post,
+                        const int64_t* _2q, const int64_t* ql, const int64_t* qh, const int64_t* kl, const int64_t* kh,
+                        void* stream);
+/* plaintext x ciphertext in the NTT domain (mc_mult / pc_mult, engine.py:2100-2140: two mont_mult calls):
+ * d0 = mont(p, c0), d1 = mont(p, c1); p, c0, c1 share in_stride; d0 / d1 may alias c0 / c1. */
+int ckks_pc_product(const int64_t* p, const int64_t* c0, const int64_t* c1, int64_t in_stride, int64_t* d0, int64_t* d1,
+                    int64_t out_stride, int C, int N, const int64_t* _2q, const int64_t* ql, const int64_t* qh,
+                    const int64_t* kl, const int64_t* kh, void* stream);
+/* plaintext + ciphertext (mc_add, engine.py:2142-2175): out = reduce_2q(mont_redc(mont_add(mont(p, Rs_scale), mont(c0, Rs)))),
+ * the integers of the reference's five kernels, one pass.  Rs_scale = R^2 * 2^scale_bits mod q (nctx.py:138-142). */
+int ckks_pc_add(const int64_t* p, int64_t p_stride, const int64_t* c0, int64_t c_stride, int64_t* out, int64_t out_stride,
+                int C, int N, const int64_t* Rs_scale, const int64_t* Rs, const int64_t* _2q, const int64_t* ql,
+                const int64_t* qh, const int64_t* kl, const int64_t* kh, void* stream);
 
 /* tensor product (engine.py:1095-1101): d0 = x0*y0, d1 = x0*y1 (+) x1*y0, d2 = x1*y1 (lazy, NTT domain) */
 int ckks_tensor_product(const int64_t* x0, const int64_t* x1, const int64_t* y0, const int64_t* y1, int64_t in_stride,

@@ -11,7 +11,7 @@
 
 using namespace ckks;
 
-#define CKKS_ABI_VERSION 3
+#define CKKS_ABI_VERSION 4
 
 namespace {
 
@@ -170,6 +170,71 @@ __global__ void k_rescale(const int64_t* __restrict__ in, long long is, const in
         o.x += (o.x < 0) ? q : 0;
         o.y += (o.y < 0) ? q : 0;
     }
+    st2(out + i * os + j, o);
+}
+
+// rescale with a per-limb Montgomery scalar folded in before (mult_scalar, engine.py:2052-2098: mont_enter_scalar + reduce_2q,
+// then rescale) and / or after it (level_up, engine.py:1410-1467: rescale, then mont_enter_scalar + reduce_2q): the same
+// integers as the three-kernel sequences, one pass.  r0 is the dropped limb AFTER the pre-scaling (the caller scales that row).
+template <bool PRE, bool POST>
+__global__ void k_rescale_scaled(const int64_t* __restrict__ in, long long is, const int64_t* __restrict__ r0,
+                                 int64_t* __restrict__ out, long long os, int N, const int64_t* __restrict__ pre,
+                                 const int64_t* __restrict__ scale, int64_t round_at, const int64_t* __restrict__ post,
+                                 MontPack m) {
+    const int i = blockIdx.y;
+    const int j = 2 * (blockIdx.x * EW_THREADS + threadIdx.x);
+    if (j >= N) return;
+    const LimbConst k = lc(m, i);
+    const int64_t sc = scale[i], q = (int64_t)(k.q2 >> 1);
+    longlong2 x = ld2(in + i * is + j);
+    const longlong2 r = ld2(r0 + j);
+    if (PRE) {
+        const int64_t s = pre[i];
+        x.x = reduce_q(mont_mul_ss(x.x, s, k.q4, k.k), q);
+        x.y = reduce_q(mont_mul_ss(x.y, s, k.q4, k.k), q);
+    }
+    longlong2 o;
+    o.x = reduce_q(mont_mul_ss(x.x - r.x, sc, k.q4, k.k) + (r.x > round_at ? 1 : 0), q);
+    o.y = reduce_q(mont_mul_ss(x.y - r.y, sc, k.q4, k.k) + (r.y > round_at ? 1 : 0), q);
+    if (POST) {
+        const int64_t s = post[i];
+        o.x = reduce_q(mont_mul_ss(o.x, s, k.q4, k.k), q);
+        o.y = reduce_q(mont_mul_ss(o.y, s, k.q4, k.k), q);
+    }
+    st2(out + i * os + j, o);
+}
+
+// plaintext x ciphertext in the NTT domain (mc_mult, engine.py:2100-2140): d0 = mont(p, c0), d1 = mont(p, c1), one pass
+__global__ void k_pc_product(const int64_t* __restrict__ p, const int64_t* __restrict__ c0, const int64_t* __restrict__ c1,
+                             long long is, int64_t* __restrict__ d0, int64_t* __restrict__ d1, long long os, int N, MontPack m) {
+    const int i = blockIdx.y;
+    const int j = 2 * (blockIdx.x * EW_THREADS + threadIdx.x);
+    if (j >= N) return;
+    const LimbConst k = lc(m, i);
+    const long long o = i * is + j;
+    const longlong2 a = ld2(p + o), b0 = ld2(c0 + o), b1 = ld2(c1 + o);
+    longlong2 r0, r1;
+    r0.x = mont_mul_ss(a.x, b0.x, k.q4, k.k);
+    r0.y = mont_mul_ss(a.y, b0.y, k.q4, k.k);
+    r1.x = mont_mul_ss(a.x, b1.x, k.q4, k.k);
+    r1.y = mont_mul_ss(a.y, b1.y, k.q4, k.k);
+    st2(d0 + i * os + j, r0);
+    st2(d1 + i * os + j, r1);
+}
+
+// plaintext + ciphertext (mc_add, engine.py:2142-2175: mont_enter_scale(pt), mont_enter(c0), mont_add, mont_redc, reduce_2q)
+__global__ void k_pc_add(const int64_t* __restrict__ p, long long ps, const int64_t* __restrict__ c0, long long cs,
+                         int64_t* __restrict__ out, long long os, int N, const int64_t* __restrict__ Rs_scale,
+                         const int64_t* __restrict__ Rs, MontPack m) {
+    const int i = blockIdx.y;
+    const int j = 2 * (blockIdx.x * EW_THREADS + threadIdx.x);
+    if (j >= N) return;
+    const LimbConst k = lc(m, i);
+    const int64_t rp = Rs_scale[i], rc = Rs[i], q = (int64_t)(k.q2 >> 1);
+    const longlong2 a = ld2(p + i * ps + j), b = ld2(c0 + i * cs + j);
+    longlong2 o;
+    o.x = reduce_q(mont_redc(lazy_add(mont_mul_ss(a.x, rp, k.q4, k.k), mont_mul_ss(b.x, rc, k.q4, k.k), (int64_t)k.q2), k.q4, k.k), q);
+    o.y = reduce_q(mont_redc(lazy_add(mont_mul_ss(a.y, rp, k.q4, k.k), mont_mul_ss(b.y, rc, k.q4, k.k), (int64_t)k.q2), k.q4, k.k), q);
     st2(out + i * os + j, o);
 }
 
@@ -941,6 +1006,42 @@ int ckks_rescale(const int64_t* in, int64_t is, const int64_t* r0, int64_t* out,
     if (!row_ok(in, is) || !row_ok(out, os) || !aligned16(r0)) return CKKS_E_ALIGN;
     k_rescale<<<ew_grid(N, C), EW_THREADS, 0, S(stream)>>>(in, is, r0, out, os, N, scale, round_at, canon,
                                                            MontPack{_2q, ql, qh, kl, kh});
+    return launch_status();
+}
+
+int ckks_rescale_scaled(const int64_t* in, int64_t is, const int64_t* r0, int64_t* out, int64_t os, int C, int N,
+                        const int64_t* pre, const int64_t* scale, int64_t round_at, const int64_t* post, const int64_t* _2q,
+                        const int64_t* ql, const int64_t* qh, const int64_t* kl, const int64_t* kh, void* stream) {
+    CHECK_PTRS(in, r0, out, scale, _2q, ql, qh, kl, kh);
+    if (C <= 0 || N <= 0 || (N & 1)) return CKKS_E_BADARG;
+    if (!row_ok(in, is) || !row_ok(out, os) || !aligned16(r0)) return CKKS_E_ALIGN;
+    const MontPack m{_2q, ql, qh, kl, kh};
+    const dim3 grid = ew_grid(N, C);
+    cudaStream_t st = S(stream);
+    if (pre && post) k_rescale_scaled<true, true><<<grid, EW_THREADS, 0, st>>>(in, is, r0, out, os, N, pre, scale, round_at, post, m);
+    else if (pre) k_rescale_scaled<true, false><<<grid, EW_THREADS, 0, st>>>(in, is, r0, out, os, N, pre, scale, round_at, post, m);
+    else if (post) k_rescale_scaled<false, true><<<grid, EW_THREADS, 0, st>>>(in, is, r0, out, os, N, pre, scale, round_at, post, m);
+    else k_rescale<<<grid, EW_THREADS, 0, st>>>(in, is, r0, out, os, N, scale, round_at, 0, m);
+    return launch_status();
+}
+
+int ckks_pc_product(const int64_t* p, const int64_t* c0, const int64_t* c1, int64_t is, int64_t* d0, int64_t* d1, int64_t os,
+                    int C, int N, const int64_t* _2q, const int64_t* ql, const int64_t* qh, const int64_t* kl,
+                    const int64_t* kh, void* stream) {
+    CHECK_PTRS(p, c0, c1, d0, d1, _2q, ql, qh, kl, kh);
+    if (C <= 0 || N <= 0 || (N & 1)) return CKKS_E_BADARG;
+    if (!row_ok(p, is) || !row_ok(c0, is) || !row_ok(c1, is) || !row_ok(d0, os) || !row_ok(d1, os)) return CKKS_E_ALIGN;
+    k_pc_product<<<ew_grid(N, C), EW_THREADS, 0, S(stream)>>>(p, c0, c1, is, d0, d1, os, N, MontPack{_2q, ql, qh, kl, kh});
+    return launch_status();
+}
+
+int ckks_pc_add(const int64_t* p, int64_t ps, const int64_t* c0, int64_t cs, int64_t* out, int64_t os, int C, int N,
+                const int64_t* Rs_scale, const int64_t* Rs, const int64_t* _2q, const int64_t* ql, const int64_t* qh,
+                const int64_t* kl, const int64_t* kh, void* stream) {
+    CHECK_PTRS(p, c0, out, Rs_scale, Rs, _2q, ql, qh, kl, kh);
+    if (C <= 0 || N <= 0 || (N & 1)) return CKKS_E_BADARG;
+    if (!row_ok(p, ps) || !row_ok(c0, cs) || !row_ok(out, os)) return CKKS_E_ALIGN;
+    k_pc_add<<<ew_grid(N, C), EW_THREADS, 0, S(stream)>>>(p, ps, c0, cs, out, os, N, Rs_scale, Rs, MontPack{_2q, ql, qh, kl, kh});
     return launch_status();
 }
 

@@ -43,6 +43,10 @@ SIGNATURES = {
     "ckks_perm_rows": [_i64p, _i64, _i64p, _i64, _int, _int, _int, _vp],
     "ckks_ntt_fast": [_i64p, _i64, _int, _int, _int, _vp, _vp, _vp, _vp, _i64p, _vp, _i64p, _i64p, _int, _int, _vp],
     "ckks_intt_fast": [_i64p, _i64, _int, _int, _int, _vp, _vp, _vp, _vp, _i64p, _vp, _i64p, _i64p, _int, _int, _int, _vp],
+    "ckks_rescale_scaled": [_i64p, _i64, _i64p, _i64p, _i64, _int, _int, _i64p, _i64p, _i64, _i64p, _i64p, _i64p, _i64p, _i64p,
+                            _i64p, _vp],
+    "ckks_pc_product": [_i64p, _i64p, _i64p, _i64, _i64p, _i64p, _i64, _int, _int, _i64p, _i64p, _i64p, _i64p, _i64p, _vp],
+    "ckks_pc_add": [_i64p, _i64, _i64p, _i64, _i64p, _i64, _int, _int, _i64p, _i64p, _i64p, _i64p, _i64p, _i64p, _i64p, _vp],
     "ckks_rescale": [_i64p, _i64, _i64p, _i64p, _i64, _int, _int, _i64p, _i64, _int, _i64p, _i64p, _i64p, _i64p, _i64p, _vp],
     "ckks_tensor_product": [_i64p, _i64p, _i64p, _i64p, _i64, _i64p, _i64p, _i64p, _i64, _int, _int,
                             _i64p, _i64p, _i64p, _i64p, _i64p, _vp],
@@ -73,7 +77,7 @@ class CkksLibError(RuntimeError):
     pass
 
 
-ABI_VERSION = 3      # the version SIGNATURES (and fhe/executor.LevelT) were written for
+ABI_VERSION = 4      # the version SIGNATURES (and fhe/executor.LevelT) were written for
 
 
 def _build_locked():

@@ -843,11 +843,7 @@ class ckks_engine:
         round_at = self.ctx.q[prime_id] // 2 if exact_rounding else (1 << 62)
         new = []
         for c in (0, 1):
-            if isinstance(self.comm, LocalComm):
-                r0 = self.comm.bcast(ct.data[c][src][0], src, range(n_before))
-            else:
-                mine = ct.data[c][src][0] if self._local(src) else None
-                r0 = self.comm.bcast(mine, src, range(n_before), shape=(self.ctx.N,))
+            r0 = self._dropped_limb(ct.data[c][src][0] if self._local(src) else None, src, n_before)
             out = [None] * n_after
             for dev in range(n_after):
                 if not self._local(dev):
@@ -857,6 +853,13 @@ class ckks_engine:
                                          self.ntt.pack5(nxt, dev, -1), canon=_canon)
             new.append(out)
         return self._ct((new[0], new[1]), nxt, "ct")
+
+    def _dropped_limb(self, row, src, n_before):
+        """the limb a rescale drops ([N], on device `src`; None on the ranks that do not own it) -> {dev: [N] tensor} on every
+        local device that holds rows before the rescale (engine.py:999-1011; one process per GPU: a broadcast, collective)"""
+        if isinstance(self.comm, LocalComm):
+            return self.comm.bcast(row, src, range(n_before))
+        return self.comm.bcast(row, src, range(n_before), shape=(self.ctx.N,))
 
     def cc_mult(self, a: data_struct, b: data_struct, evk: data_struct, relin=True) -> data_struct:
         if a.origin != types.origins["ct"]:
@@ -1053,24 +1056,41 @@ class ckks_engine:
     def level_up(self, ct: data_struct, dst_level: int):
         if types.origins["ct"] != ct.origin:
             raise errors.NotMatchType(origin=ct.origin, to=types.origins["ct"])
-        new_ct = self.rescale(ct)
-        src_level = ct.level + 1
+        level, src_level = ct.level, ct.level + 1
+        if src_level >= self.num_levels:
+            raise errors.MaximumLevelError(level=ct.level, level_max=self.num_levels)
         n_dst = len(self.ntt.p.destination_arrays[dst_level])
         diff_deviation = self.deviations[dst_level] / np.sqrt(self.deviations[src_level])
         deviated_delta = round(self.scale * diff_deviation)
-        if dst_level - src_level > 0:
-            src_lens = [len(d) for d in self.ntt.p.destination_arrays[src_level]]
-            dst_lens = [len(d) for d in self.ntt.p.destination_arrays[dst_level]]
-            drop = [x - y for x, y in zip(src_lens, dst_lens)]
+        src_lens = [len(d) for d in self.ntt.p.destination_arrays[src_level]]
+        dst_lens = [len(d) for d in self.ntt.p.destination_arrays[dst_level]]
+        drop = [x - y for x, y in zip(src_lens, dst_lens)]
+        mult = self._scalar_rows(lambda q: deviated_delta * self.ctx.R % q, dst_level, n_dst)
+        if not self.fast:
+            new_ct = self.rescale(ct)
             d0 = [new_ct.data[0][dev][drop[dev]:] if self._local(dev) else None for dev in range(n_dst)]
             d1 = [new_ct.data[1][dev][drop[dev]:] if self._local(dev) else None for dev in range(n_dst)]
-        else:
-            d0, d1 = new_ct.data
-        mult = self._scalar_rows(lambda q: deviated_delta * self.ctx.R % q, dst_level, n_dst)
-        for d in (d0, d1):
-            self.ntt.mont_enter_scalar(d, mult, dst_level)
-            self.ntt.reduce_2q(d, dst_level)
-        return self._ct((d0, d1), dst_level, "ct")
+            for d in (d0, d1):
+                self.ntt.mont_enter_scalar(d, mult, dst_level)
+                self.ntt.reduce_2q(d, dst_level)
+            return self._ct((d0, d1), dst_level, "ct")
+        # one kernel per polynomial and device: rescale of the rows that survive to dst_level only, with the scale
+        # correction (mont_enter_scalar + reduce_2q) folded into the same pass
+        src = self.ntt.p.rescaler_loc[level]
+        n_before = self.len_devices[level]
+        round_at = self.ctx.q[self.ntt.p.destination_arrays[level][src][0]] // 2
+        new = []
+        for c in (0, 1):
+            r0 = self._dropped_limb(ct.data[c][src][0] if self._local(src) else None, src, n_before)
+            out = [None] * n_dst
+            for dev in range(n_dst):
+                if not self._local(dev):
+                    continue
+                first = (1 if dev == src else 0) + drop[dev]
+                out[dev] = fused.rescale_scaled(ct.data[c][dev][first:], r0[dev], self.rescale_scales[level][dev][drop[dev]:],
+                                                round_at, self.ntt.pack5(dst_level, dev, -1), post=mult[dev])
+            new.append(out)
+        return self._ct((new[0], new[1]), dst_level, "ct")
 
     # -----------------------------------------------------------------------------------------------
     # clone / negate / scalar and plaintext operands (:1740-1788, :2035-2219)
@@ -1110,7 +1130,37 @@ class ckks_engine:
 
     def mult_scalar(self, ct, scalar, evk=None, relin=True):
         scaled = int(scalar * self.scale * np.sqrt(self.deviations[ct.level + 1]) + 0.5)
-        return self.rescale(self._times_scalar(ct, scaled))
+        if not self.fast:
+            return self.rescale(self._times_scalar(ct, scaled))
+        if ct.origin != types.origins["ct"]:
+            raise errors.NotMatchType(origin=ct.origin, to=types.origins["ct"])
+        # one kernel per polynomial and device: the scalar product (mont_enter_scalar + reduce_2q) folded into the rescale
+        level, nxt = ct.level, ct.level + 1
+        if nxt >= self.num_levels:
+            raise errors.MaximumLevelError(level=ct.level, level_max=self.num_levels)
+        src = self.ntt.p.rescaler_loc[level]
+        n_before, n_after = self.len_devices[level], self.len_devices[nxt]
+        round_at = self.ctx.q[self.ntt.p.destination_arrays[level][src][0]] // 2
+        rows = self._scalar_rows(lambda q: scaled * self.ctx.R % q, level, n_before)
+        new = []
+        for c in (0, 1):
+            top = None
+            if self._local(src):    # the dropped limb, scaled like the others (one row)
+                top = ct.data[c][src][0:1].clone()
+                pk5 = [t[0:1] for t in self.ntt.pack5(level, src, -1)]
+                ntt_cuda.mont_enter([top], [rows[src][0:1]], *[[t] for t in pk5[1:]])
+                ntt_cuda.reduce_2q([top], [pk5[0]])
+                top = top[0]
+            r0 = self._dropped_limb(top, src, n_before)
+            out = [None] * n_after
+            for dev in range(n_after):
+                if not self._local(dev):
+                    continue
+                first = 1 if dev == src else 0
+                out[dev] = fused.rescale_scaled(ct.data[c][dev][first:], r0[dev], self.rescale_scales[level][dev], round_at,
+                                                self.ntt.pack5(nxt, dev, -1), pre=rows[dev][first:])
+            new.append(out)
+        return self._ct((new[0], new[1]), nxt, "ct")
 
     def add_scalar(self, ct, scalar):
         scaled = int(scalar * self.scale * self.deviations[ct.level] + 0.5)
@@ -1144,6 +1194,23 @@ class ckks_engine:
         m = np.array(m) * np.sqrt(self.deviations[ct.level + 1])
         pt = self.encode(m, 0)
         pt_tiled = self.ntt.tile_unsigned(self._alive(pt, ct.level, -1), ct.level)
+        if self.fast:
+            # plaintext and both ciphertext polynomials in ONE batched transform per direction, both products in one pass
+            level = ct.level
+            out = ([None] * len(ct.data[0]), [None] * len(ct.data[0]))
+            for dev, p in enumerate(pt_tiled):
+                if p is None or not self._local(dev):
+                    continue
+                rows, N = p.size(0), p.size(1)
+                X = torch.empty((3, rows, N), dtype=torch.int64, device=p.device)
+                X[0].copy_(p)
+                X[1].copy_(ct.data[0][dev])
+                X[2].copy_(ct.data[1][dev])
+                self.ntt.ntt_fast(X.view(3 * rows, N), level, dev, enter=True, batched=True)
+                fused.pc_product(X[0], X[1], X[2], self.ntt.pack5(level, dev, -1), X[1], X[2])
+                self.ntt.intt_fast(X[1:].view(2 * rows, N), level, dev, batched=True)
+                out[0][dev], out[1][dev] = X[1], X[2]
+            return self.rescale(ct._replace(data=[out[0], out[1]]))
         self.ntt.enter_ntt(pt_tiled, ct.level)
         new_ct = self.clone(ct)
         out = []
@@ -1157,6 +1224,16 @@ class ckks_engine:
     def mc_add(self, m, ct):
         pt = self.encode(m, ct.level)
         pt_tiled = self.ntt.tile_unsigned(self._alive(pt, ct.level, -1), ct.level)
+        if self.fast:       # the five elementwise kernels of the sum as one pass per device
+            level = ct.level
+            d0 = [None] * len(ct.data[0])
+            for dev, p in enumerate(pt_tiled):
+                if p is None or not self._local(dev):
+                    continue
+                (_, a, b), = self.ntt.rows(level, dev, -1)
+                d0[dev] = fused.pc_add(p, ct.data[0][dev], self.ntt.Rs_scale[dev][a:b], self.ntt.Rs[dev][a:b],
+                                       self.ntt.pack5(level, dev, -1))
+            return ct._replace(data=[d0, self.clone_tensors(ct.data[1])])
         self.ntt.mont_enter_scale(pt_tiled, ct.level)
         new_ct = self.clone(ct)
         self.ntt.mont_enter(new_ct.data[0], ct.level)

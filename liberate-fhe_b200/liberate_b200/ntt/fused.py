@@ -24,6 +24,44 @@ def rescale(x, r0, scale, round_at, mp, canon=False):
     return out
 
 
+def rescale_scaled(x, r0, scale, round_at, mp, pre=None, post=None):
+    """rescale with mont_enter_scalar + reduce_2q folded in before (``pre``: mult_scalar, engine.py:2052-2098) and / or after
+    it (``post``: level_up, engine.py:1410-1467): the integers of the kernel sequences, one pass.  r0: the dropped limb after
+    the same pre-scaling.  -> new [C,N]"""
+    xs = _rows(x, "rescale_scaled")
+    out = torch.empty((x.size(0), x.size(1)), dtype=torch.int64, device=x.device)
+    r0 = r0 if r0.is_contiguous() else r0.contiguous()
+    opt = lambda t: _ptr(_vec(t)) if t is not None else None
+    with _Launch(x):
+        check(lib.ckks_rescale_scaled(_ptr(x), xs, _ptr(r0), _ptr(out), out.size(1), x.size(0), x.size(1), opt(pre),
+                                      _ptr(_vec(scale)), int(round_at), opt(post), *[_ptr(_vec(t)) for t in mp], _stream(x)),
+              "rescale_scaled")
+    return out
+
+
+def pc_product(p, c0, c1, mp, out0, out1):
+    """plaintext x ciphertext in the NTT domain (mc_mult, engine.py:2100-2140): out0 = mont(p, c0), out1 = mont(p, c1);
+    p, c0, c1 share one row stride; out may alias c"""
+    s = _rows(p, "pc_product")
+    if _rows(c0, "pc_product") != s or _rows(c1, "pc_product") != s or _rows(out0, "pc_product") != _rows(out1, "pc_product"):
+        raise ValueError("pc_product: operands must share one row stride")
+    C, N = p.shape
+    with _Launch(p):
+        check(lib.ckks_pc_product(_ptr(p), _ptr(c0), _ptr(c1), s, _ptr(out0), _ptr(out1), _rows(out0, "pc_product"), C, N,
+                                  *[_ptr(_vec(t)) for t in mp], _stream(p)), "pc_product")
+
+
+def pc_add(p, c0, Rs_scale, Rs, mp):
+    """plaintext + ciphertext (mc_add, engine.py:2142-2175: mont_enter_scale, mont_enter, mont_add, mont_redc, reduce_2q)
+    in one pass -> new [C,N]"""
+    sp, sc = _rows(p, "pc_add"), _rows(c0, "pc_add")
+    out = torch.empty((c0.size(0), c0.size(1)), dtype=torch.int64, device=c0.device)
+    with _Launch(c0):
+        check(lib.ckks_pc_add(_ptr(p), sp, _ptr(c0), sc, _ptr(out), out.size(1), c0.size(0), c0.size(1), _ptr(_vec(Rs_scale)),
+                              _ptr(_vec(Rs)), *[_ptr(_vec(t)) for t in mp], _stream(c0)), "pc_add")
+    return out
+
+
 def addsub_reduce(a, b, _2q, sub=False):
     """mont_add / mont_sub + reduce_2q in one pass (cc_add / cc_sub, engine.py:1268-1330) -> new [C,N]"""
     sa, sb = _rows(a, "addsub_reduce"), _rows(b, "addsub_reduce")

@@ -233,12 +233,13 @@ class ntt_context:
         fused.ntt_fast(x, self.tw_fast_fwd[dev][a:b], None, self.q[dev][a:b], sc[0], sc[1],
                        period=(b - a) if batched else None, qinv=self.qinv[dev][a:b])
 
-    def intt_fast(self, x, lvl, dev, part=-1, exit=True, centred=False):
-        """x: [rows, N] in [0,2q) -> canonical iNTT(x) * N^-1 [* R^-1]  (== intt_exit_reduce / intt + reduce)"""
+    def intt_fast(self, x, lvl, dev, part=-1, exit=True, centred=False, batched=False):
+        """x: [rows, N] (or [parts*rows, N] with batched=True) in [0,2q) -> canonical iNTT(x) * N^-1 [* R^-1]
+        (== intt_exit_reduce / intt + reduce)"""
         (_, a, b), = self.rows(lvl, dev, part)
         sc = self.fs_exit if exit else self.fs_ninv
         fused.intt_fast(x, self.tw_fast_inv[dev][a:b], None, self.q[dev][a:b], sc[0][dev][a:b], sc[1][dev][a:b],
-                        centred=centred, qinv=self.qinv[dev][a:b])
+                        centred=centred, period=(b - a) if batched else None, qinv=self.qinv[dev][a:b])
 
     @staticmethod
     def _live(a):

@@ -56,6 +56,9 @@ def run(fhe, label, extra):
            "add_us": round(timed(lambda: eng.add(a, b), args.iters), 1),
            "rescale_us": round(timed(lambda: eng.rescale(a), args.iters), 1),
            "level_up_us": round(timed(lambda: eng.level_up(a, 3), args.iters), 1),
+           "mult_scalar_us": round(timed(lambda: eng.mult(a, 0.5), args.iters), 1),
+           "mc_mult_us": round(timed(lambda: eng.mult(m, a), 10), 1),
+           "mc_add_us": round(timed(lambda: eng.add(m, a), 10), 1),
            "decrode_us": round(timed(lambda: eng.decrode(prod, sk), 10), 1)}
     err = float(np.abs(eng.decrode(eng.rotate_single(prod, rotk), sk) - np.roll(m * m, 1)).max())
     out["mult_rotate_decrypt_error"] = err

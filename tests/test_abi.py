@@ -27,7 +27,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     for name, n in decls.items():
         assert hasattr(_lib.lib, name), name
         assert len(_lib.SIGNATURES[name]) == n, name
-    assert _lib.lib.ckks_abi_version() == _lib.ABI_VERSION == 3
+    assert _lib.lib.ckks_abi_version() == _lib.ABI_VERSION == 4
 
 
 def test_no_cpu_fallback():
