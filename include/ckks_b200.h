@@ -38,6 +38,8 @@ int ckks_abi_version(void);                 /* 4; the Python loader refuses any 
  *   18 = the executor keeps NTT-domain data in warp-interleaved order (1; needs permuted key copies, ckks_perm_rows);
  *   19 = hot-path kernels launched with programmatic stream serialization (1): the next grid ramps up under the tail of
  *        the previous one; every such kernel waits (griddepcontrol.wait) before its first global access.
+ *   22 = least number of slabs of the key switch's forward chain (2): a 1/8 limb shard would fit one slab and run its
+ *        kernels strictly one after the other; two slabs on two internal streams overlap the FP64 rows with the 60-bit rows.
  * Unknown keys return CKKS_E_BADARG.  The library is single-threaded per device (one host thread per device issues calls). */
 int ckks_set_option(int key, int value);
 int ckks_get_option(int key);               /* current value of a knob (negative: unknown key) */

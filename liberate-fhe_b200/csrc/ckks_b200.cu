@@ -554,6 +554,7 @@ int g_ntt_slab_mb = 24;   // 11: MB of rows per slab of a big batched transform
 int g_fuse_rescale = 1;   // 12: rescale fused into the tensor stage's column pass
 int g_split_tail = 1;     // 16: inverse transform + ModDown of the two output polynomials on two streams
 int g_packed = 1;         // 17: block passes read the last-group twiddles from the packed tables (when the caller passes them)
+int g_min_slabs = 2;      // 22: the key switch's forward chain runs in at least this many slabs (so that small shards also pipeline)
 int g_perm = 1;           // 18: the executor keeps NTT-domain data in warp-interleaved order (needs permuted key copies)
 #ifdef CKKS_LAB
 int g_skip = 0;           // 5 (lab builds only): measurement -- bit 0 skips the column pass, bit 1 the block pass
@@ -793,6 +794,7 @@ static int* option_slot(int key) {
         case 17: return &g_packed;
         case 18: return &g_perm;
         case 19: return &g_pdl;
+        case 22: return &g_min_slabs;
     }
     return nullptr;
 }
@@ -1239,7 +1241,8 @@ int ckks_exec_keyswitch_stage(const ckks_level_t* lv, const int64_t* const* digi
         const long long slab_budget = (long long)g_slab_mb << 20;   // bytes of extended rows per slab
         const int Pr = pe - pb;                                      // partitions this call transforms
         const long long all_bytes = (long long)Pr * E * N * 8;
-        const int nslabs = (int)((all_bytes + slab_budget - 1) / slab_budget);
+        int nslabs = (int)((all_bytes + slab_budget - 1) / slab_budget);
+        if (nslabs < g_min_slabs && E >= 4 * g_min_slabs) nslabs = g_min_slabs;   // (one process per GPU: a 1/8 shard fits one slab)
         const int slab = (E + nslabs - 1) / nslabs;
         if (slab > EXT_MAX_E) return CKKS_E_BADARG;
         cudaStream_t main_st = S(stream);

@@ -140,7 +140,7 @@ class _Counted:
 
 
 lib = _Counted(_load())
-OPTION_KEYS = (2, 9, 10, 11, 12, 16, 17, 18, 19)
+OPTION_KEYS = (2, 9, 10, 11, 12, 16, 17, 18, 19, 22)
 _OPTION_DEFAULTS = {k: lib.ckks_get_option(k) for k in OPTION_KEYS}
 
 

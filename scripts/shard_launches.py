@@ -37,7 +37,7 @@ if len(sys.argv) > 2 and sys.argv[2] == "sweep":
         e1.record(); torch.cuda.synchronize()
         return e0.elapsed_time(e1) / n
     print("default", round(timed(), 4), "ms for all", D, "shards")
-    for key, vals in ((16, (0, 1)), (10, (1, 2, 3)), (11, (4, 24, 4000)), (9, (25, 100, 4000)), (2, (0, 1)), (19, (0, 1))):
+    for key, vals in ((22, (1, 2, 3)), (16, (0, 1)), (10, (1, 2, 3)), (11, (4, 24, 4000)), (9, (25, 100, 4000)), (2, (0, 1)), (19, (0, 1))):
         old = lib.ckks_get_option(key)
         for v in vals:
             lib.ckks_set_option(key, v)

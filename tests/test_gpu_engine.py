@@ -155,9 +155,9 @@ def test_captured_graph_replays_the_same_bits(D):
 
 
 @pytest.mark.parametrize("opts", [[(12, 0)], [(18, 0)], [(17, 0)], [(17, 0), (18, 0)], [(10, 1), (9, 400)], [(9, 1)], [(16, 0)],
-                                  [(19, 0)]],
+                                  [(19, 0)], [(22, 1)], [(22, 3)]],
                          ids=["no-rescale-fusion", "natural-order", "plain-twiddles", "plain+natural", "one-stream",
-                              "many-slabs", "joint-tail", "no-pdl"])
+                              "many-slabs", "joint-tail", "no-pdl", "single-slab", "three-slabs"])
 def test_optional_fused_paths_reproduce_reference_tensors(opts):
     """every ckks_set_option variant of the executor (rescale fusion, warp-interleaved NTT-domain order with permuted key
     copies, packed twiddles, slab and side-stream settings) must hit the same golden digests as the default path"""
