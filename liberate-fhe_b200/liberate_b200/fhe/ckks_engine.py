@@ -174,6 +174,7 @@ class ckks_engine:
                 per_p.append(per_dev)
             self.PiRs.append(per_p)
         self._PiR_dense = {}
+        self._scalar_cache = {}
         self._ptr_cache = {}
         self._plans = {}
         self._ws = {}
@@ -1048,10 +1049,22 @@ class ckks_engine:
 
     cc_subtract = cc_sub
 
-    def _scalar_rows(self, value_of_q, level, n_dev):
+    def _scalar_rows(self, value_of_q, level, n_dev, key=None):
+        """per-limb scalars of the rows live at `level`, one small tensor per local device.  With a `key` the tensors are kept
+        (the same constant at the same level is the common case in a circuit, and an upload from a Python list is a
+        synchronous copy that a CUDA-graph capture of the call would not allow)."""
+        if key is not None:
+            hit = self._scalar_cache.get((key, level, n_dev))
+            if hit is not None:
+                return hit
         dest = self.ntt.p.destination_arrays[level]
-        return [self._t([value_of_q(self.ctx.q[i]) for i in dest[dev]], dev) if self._local(dev) else None
+        rows = [self._t([value_of_q(self.ctx.q[i]) for i in dest[dev]], dev) if self._local(dev) else None
                 for dev in range(n_dev)]
+        if key is not None:
+            if len(self._scalar_cache) >= 256:
+                self._scalar_cache.pop(next(iter(self._scalar_cache)))
+            self._scalar_cache[(key, level, n_dev)] = rows
+        return rows
 
     def level_up(self, ct: data_struct, dst_level: int):
         if types.origins["ct"] != ct.origin:
@@ -1065,7 +1078,7 @@ class ckks_engine:
         src_lens = [len(d) for d in self.ntt.p.destination_arrays[src_level]]
         dst_lens = [len(d) for d in self.ntt.p.destination_arrays[dst_level]]
         drop = [x - y for x, y in zip(src_lens, dst_lens)]
-        mult = self._scalar_rows(lambda q: deviated_delta * self.ctx.R % q, dst_level, n_dst)
+        mult = self._scalar_rows(lambda q: deviated_delta * self.ctx.R % q, dst_level, n_dst, key=("mont", deviated_delta))
         if not self.fast:
             new_ct = self.rescale(ct)
             d0 = [new_ct.data[0][dev][drop[dev]:] if self._local(dev) else None for dev in range(n_dst)]
@@ -1117,7 +1130,7 @@ class ckks_engine:
 
     def _times_scalar(self, ct, scalar_int):
         new_ct = self.clone(ct)
-        rows = self._scalar_rows(lambda q: scalar_int * self.ctx.R % q, ct.level, len(ct.data[0]))
+        rows = self._scalar_rows(lambda q: scalar_int * self.ctx.R % q, ct.level, len(ct.data[0]), key=("mont", scalar_int))
         for i in (0, 1):
             self.ntt.mont_enter_scalar(new_ct.data[i], rows, ct.level)
             self.ntt.reduce_2q(new_ct.data[i], ct.level)
@@ -1141,7 +1154,7 @@ class ckks_engine:
         src = self.ntt.p.rescaler_loc[level]
         n_before, n_after = self.len_devices[level], self.len_devices[nxt]
         round_at = self.ctx.q[self.ntt.p.destination_arrays[level][src][0]] // 2
-        rows = self._scalar_rows(lambda q: scaled * self.ctx.R % q, level, n_before)
+        rows = self._scalar_rows(lambda q: scaled * self.ctx.R % q, level, n_before, key=("mont", scaled))
         new = []
         for c in (0, 1):
             top = None
@@ -1168,7 +1181,7 @@ class ckks_engine:
             scaled *= self.ctx.N
         scaled *= self.int_scale
         new_ct = self.clone(ct)
-        rows = self._scalar_rows(lambda q: scaled % q, ct.level, len(ct.data[0]))
+        rows = self._scalar_rows(lambda q: scaled % q, ct.level, len(ct.data[0]), key=("plain", scaled))
         for dev, d in enumerate(new_ct.data[0]):
             if d is not None:
                 d[:, 0] += rows[dev]

@@ -154,6 +154,41 @@ def test_captured_graph_replays_the_same_bits(D):
     torch.cuda.synchronize()
 
 
+@pytest.mark.parametrize("D", [1, 2])
+def test_captured_circuit_with_levelling_and_scalars(D):
+    """a whole circuit as one CUDA graph: (add, mult by a level-0 ciphertext -> auto level_up, scalar product, rotate) x 3.  The
+    per-limb scalar tables of level_up / mult_scalar are cached on the engine, so the warm-up calls of capture() leave no
+    host->device upload inside the captured region; the replay gives the eager result bit for bit."""
+    g = json.loads((GOLDEN / f"engine_D{D}.json").read_text())
+    eng = make_engine(D, g["params"])
+    sk = eng.create_secret_key()
+    pk = eng.create_public_key(sk)
+    evk = eng.create_evk(sk)
+    rotk = eng.create_rotation_key(sk, 1)
+    rng = np.random.default_rng(9)
+    m = rng.uniform(-1, 1, eng.num_slots) + 1j * rng.uniform(-1, 1, eng.num_slots)
+    m /= np.abs(m).max() * 1.5
+    w = 0.5 * np.exp(0.3j)
+    ct, cw = eng.encorypt(m, pk), eng.encorypt(np.full(eng.num_slots, w), pk)
+
+    def circuit(x):
+        for i in range(3):
+            x = eng.mult(eng.add(x, x), cw, evk)
+            if i == 1:
+                x = eng.mult(x, 1.0)            # mult_scalar: one more level
+            x = eng.rotate_single(x, rotk)
+        return x
+    want = circuit(ct)
+    graph = eng.capture(circuit, ct)
+    graph.replay()
+    torch.cuda.synchronize()
+    same = all(torch.equal(u, v) for p, q in zip(graph.result.data, want.data) for u, v in zip(p, q))
+    assert same, "the replayed circuit differs from the eager circuit"
+    assert graph.result.level == 4
+    err = np.abs(eng.decrode(graph.result, sk) - np.roll(8 * m * w ** 3, 3)).max()
+    assert err < 1e-4, err
+
+
 @pytest.mark.parametrize("opts", [[(12, 0)], [(18, 0)], [(17, 0)], [(17, 0), (18, 0)], [(10, 1), (9, 400)], [(9, 1)], [(16, 0)],
                                   [(19, 0)], [(22, 1)], [(22, 3)]],
                          ids=["no-rescale-fusion", "natural-order", "plain-twiddles", "plain+natural", "one-stream",
