@@ -1332,18 +1332,9 @@ class ckks_engine:
         self.rng.refresh(*self._shared_key_material())
 
     def _shared_key_material(self):
-        """(seed, nonce) of the sampler.  One process: os.urandom, as the reference (csprng.py:215-223).  One process per GPU:
-        rank 0 draws them and every rank runs the SAME ChaCha20 key and nonce, or the repeated channels (secret key, shared
-        randomness of public keys and encryptions) would differ between the ranks -- such ciphertexts decrypt only as long
-        as device 0's limbs alone are looked at."""
-        if not isinstance(self.comm, DistComm):
-            return None, None
-        box = [None]
-        if self.comm.rank == 0:
-            from ..csprng import _words
-            box = [(_words(None, 8, "seed"), _words(None, 2, "nonce"))]
-        self.comm.dist.broadcast_object_list(box, src=0, group=self.comm.group)
-        return box[0]
+        """(seed, nonce) of the sampler: None, None in one process (os.urandom, as the reference, csprng.py:215-223); one
+        process per GPU: drawn by rank 0 and broadcast, so that the repeated channels agree (comm.DistComm)."""
+        return self.comm.shared_key_material()
 
     def reduce_error(self, ct):
         return self.mult_scalar(ct, 1.0)

@@ -44,6 +44,10 @@ class LocalComm:
     def barrier(self):
         pass
 
+    def shared_key_material(self):
+        """one process: the sampler draws its own key and nonce from os.urandom, as the reference (csprng.py:215-223)"""
+        return None, None
+
 
 class DistComm:
     """logical device id == torch.distributed rank; this process owns exactly one device"""
@@ -59,6 +63,19 @@ class DistComm:
         self.devices = devices
         self.local_ids = [self.rank]
         self.device = devices[self.rank]
+
+    def shared_key_material(self):
+        """collective: (seed, nonce) = 8 + 2 random 32-bit words drawn by rank 0 and handed to every rank.  All ranks must
+        run the SAME ChaCha20 key and nonce, or the sampler's repeated channels (secret key, shared randomness of public keys
+        and encryptions) differ between the ranks -- such ciphertexts decrypt only while device 0's limbs alone are read."""
+        import os
+        box = [None]
+        if self.rank == 0:
+            words = [int.from_bytes(os.urandom(4), "big") for _ in range(10)]
+            box = [(words[:8], words[8:])]
+        self.dist.broadcast_object_list(box, src=0, group=self.group)
+        seed, nonce = box[0]
+        return list(seed), list(nonce)
 
     def bcast(self, t, src, dst_ids, shape=None, dtype=torch.int64):
         """collective: every rank calls it; ranks other than `src` pass t=None (+ shape)"""

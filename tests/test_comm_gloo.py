@@ -59,6 +59,16 @@ def _worker(rank, world, port, L, K):
             row = torch.arange(N, dtype=torch.int64) * (level + 3)
             out = comm.bcast(row if rank == src else None, src, range(world), shape=(N,))
             assert torch.equal(out[rank], row)
+        # the sampler's key material: every rank ends up with rank 0's 8 + 2 words (and a second call gives new ones)
+        seed, nonce = comm.shared_key_material()
+        assert len(seed) == 8 and len(nonce) == 2 and all(0 <= w < 2 ** 32 for w in seed + nonce)
+        mine = torch.tensor(seed + nonce, dtype=torch.int64)
+        ref = mine.clone()
+        dist.broadcast(ref, src=0)
+        assert torch.equal(mine, ref), "ranks disagree on the sampler's key / nonce"
+        again, _ = comm.shared_key_material()
+        assert again != seed
+        assert comm_mod.LocalComm(["cpu"]).shared_key_material() == (None, None)
         comm.barrier()
     finally:
         dist.destroy_process_group()
